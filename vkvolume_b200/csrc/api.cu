@@ -1,0 +1,521 @@
+// api.cu — the C ABI of include/vkv.h: contexts, volumes, uploads, orchestration.
+// Each entry point names the reference interface it replaces in include/vkv.h.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+
+namespace vkv {
+
+static thread_local char t_error[512] = "";
+std::atomic<uint64_t>    g_kernel_launches{0};
+
+void set_error(const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(t_error, sizeof t_error, fmt, ap);
+	va_end(ap);
+}
+
+int sync_arrays_from_linear(vkv_volume *vol, bool gradient, cudaStream_t s)
+{
+	cudaArray_t dst = gradient ? vol->a_G : vol->a_V;
+	uint8_t    *src = gradient ? vol->d_G : vol->d_V;
+	if (!dst || !src) return VKV_OK;
+	cudaMemcpy3DParms p{};
+	p.srcPtr   = make_cudaPitchedPtr(src, vol->dim[0], vol->dim[0], vol->dim[1]);
+	p.dstArray = dst;
+	p.extent   = make_cudaExtent(vol->dim[0], vol->dim[1], vol->dim[2]);
+	p.kind     = cudaMemcpyDeviceToDevice;
+	VKV_CUDA_CHECK(cudaMemcpy3DAsync(&p, s));
+	return VKV_OK;
+}
+
+static int make_texture(cudaArray_t arr, cudaTextureObject_t *out)
+{
+	cudaResourceDesc rd{};
+	rd.resType         = cudaResourceTypeArray;
+	rd.res.array.array = arr;
+	cudaTextureDesc td{};
+	// VK_FILTER_LINEAR + CLAMP_TO_EDGE + R8_UNORM (src/volume_component.cpp:139-148)
+	td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+	td.filterMode       = cudaFilterModeLinear;
+	td.readMode         = cudaReadModeNormalizedFloat;
+	td.normalizedCoords = 1;
+	VKV_CUDA_CHECK(cudaCreateTextureObject(out, &rd, &td, nullptr));
+	return VKV_OK;
+}
+
+struct DeviceGuard {
+	int prev = -1;
+	explicit DeviceGuard(int dev)
+	{
+		cudaGetDevice(&prev);
+		if (prev != dev) cudaSetDevice(dev);
+		else prev = -1;
+	}
+	~DeviceGuard()
+	{
+		if (prev >= 0) cudaSetDevice(prev);
+	}
+};
+
+}        // namespace vkv
+
+using namespace vkv;
+
+extern "C" {
+
+const char *vkv_last_error(void) { return t_error; }
+const char *vkv_version(void) { return "vkvolume_b200 0.1 (sm_100a)"; }
+uint64_t    vkv_kernel_launch_count(void) { return g_kernel_launches.load(); }
+
+int vkv_context_create(int device, vkv_context **out)
+{
+	VKV_REQUIRE(out, VKV_ERR_ARGUMENT, "vkv_context_create: out is NULL");
+	*out  = nullptr;
+	int n = 0;
+	VKV_CUDA_CHECK(cudaGetDeviceCount(&n));
+	VKV_REQUIRE(device >= 0 && device < n, VKV_ERR_ARGUMENT, "vkv_context_create: no such CUDA device");
+	VKV_CUDA_CHECK(cudaSetDevice(device));
+	auto *ctx = new (std::nothrow) vkv_context();
+	VKV_REQUIRE(ctx, VKV_ERR_NOMEM, "out of host memory");
+	ctx->device = device;
+	VKV_CUDA_CHECK(cudaGetDeviceProperties(&ctx->prop, device));
+	ctx->sm_count = ctx->prop.multiProcessorCount;
+	if (ctx->prop.major < 10) {
+		set_error("vkv_context_create: device %d is sm_%d%d; this library carries sm_100a code only", device, ctx->prop.major,
+		          ctx->prop.minor);
+		delete ctx;
+		return VKV_ERR_CUDA;
+	}
+	*out = ctx;
+	return VKV_OK;
+}
+
+void vkv_context_destroy(vkv_context *ctx) { delete ctx; }
+int  vkv_context_device(const vkv_context *ctx) { return ctx ? ctx->device : -1; }
+int  vkv_context_sm_count(const vkv_context *ctx) { return ctx ? ctx->sm_count : 0; }
+
+int vkv_stream_synchronize(vkv_context *ctx, void *stream)
+{
+	VKV_REQUIRE(ctx, VKV_ERR_ARGUMENT, "ctx is NULL");
+	VKV_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t) stream));
+	return VKV_OK;
+}
+
+int vkv_volume_create(vkv_context *ctx, uint32_t width, uint32_t height, uint32_t depth, uint32_t block_size,
+                      int use_precomputed_gradient, vkv_volume **out)
+{
+	VKV_REQUIRE(ctx && out, VKV_ERR_ARGUMENT, "vkv_volume_create: NULL argument");
+	VKV_REQUIRE(width && height && depth && block_size, VKV_ERR_ARGUMENT, "vkv_volume_create: zero extent or block size");
+	*out = nullptr;
+	DeviceGuard guard(ctx->device);
+	auto *vol = new (std::nothrow) vkv_volume();
+	VKV_REQUIRE(vol, VKV_ERR_NOMEM, "out of host memory");
+	vol->ctx    = ctx;
+	vol->dim[0] = width; vol->dim[1] = height; vol->dim[2] = depth;
+	vol->bs_requested = block_size;
+	for (int a = 0; a < 3; ++a) {
+		vol->dim_b[a] = rnd_up(vol->dim[a], block_size);        // volume_component.cpp:91-93
+		vol->bs[a]    = rnd_up(vol->dim[a], vol->dim_b[a]);     // compute_distance_map.cpp:108-113
+	}
+	vol->N = (size_t) width * height * depth;
+	vol->M = (size_t) vol->dim_b[0] * vol->dim_b[1] * vol->dim_b[2];
+	vol->precomputed_gradient = use_precomputed_gradient != 0;
+	auto fail = [&](cudaError_t e, const char *what) {
+		set_error("vkv_volume_create: %s failed: %s", what, cudaGetErrorString(e));
+		vkv_volume_destroy(vol);
+		return VKV_ERR_CUDA;
+	};
+	cudaError_t e;
+	if ((e = cudaMalloc(&vol->d_V, vol->N)) != cudaSuccess) return fail(e, "cudaMalloc(V)");
+	cudaChannelFormatDesc fd  = cudaCreateChannelDesc<unsigned char>();
+	cudaExtent            ext = make_cudaExtent(width, height, depth);
+	if ((e = cudaMalloc3DArray(&vol->a_V, &fd, ext)) != cudaSuccess) return fail(e, "cudaMalloc3DArray(V)");
+	if (make_texture(vol->a_V, &vol->t_V)) { vkv_volume_destroy(vol); return VKV_ERR_CUDA; }
+	if (vol->precomputed_gradient) {
+		if ((e = cudaMalloc(&vol->d_G, vol->N)) != cudaSuccess) return fail(e, "cudaMalloc(G)");
+		if ((e = cudaMalloc3DArray(&vol->a_G, &fd, ext)) != cudaSuccess) return fail(e, "cudaMalloc3DArray(G)");
+		if (make_texture(vol->a_G, &vol->t_G)) { vkv_volume_destroy(vol); return VKV_ERR_CUDA; }
+	}
+	if ((e = cudaMalloc(&vol->d_tf, 256 * 256 * 4)) != cudaSuccess) return fail(e, "cudaMalloc(tf)");
+	if ((e = cudaMalloc(&vol->d_mask2, kMaskWords * sizeof(uint2))) != cudaSuccess) return fail(e, "cudaMalloc(mask)");
+	if ((e = cudaMalloc(&vol->d_bounds, sizeof(TFBounds))) != cudaSuccess) return fail(e, "cudaMalloc(bounds)");
+	if ((e = cudaMalloc(&vol->d_swap, vol->M)) != cudaSuccess) return fail(e, "cudaMalloc(swap)");
+	if ((e = cudaMalloc(&vol->d_tmp, vol->M)) != cudaSuccess) return fail(e, "cudaMalloc(tmp)");
+	if ((e = cudaMalloc(&vol->d_count, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc(count)");
+	if ((e = cudaMalloc(&vol->d_counts_scratch, sizeof(vkv_sample_counts))) != cudaSuccess) return fail(e, "cudaMalloc(counts)");
+	if ((e = cudaMallocHost(&vol->h_count, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMallocHost");
+	*out = vol;
+	return VKV_OK;
+}
+
+void vkv_volume_destroy(vkv_volume *vol)
+{
+	if (!vol) return;
+	DeviceGuard guard(vol->ctx->device);
+	if (vol->t_V) cudaDestroyTextureObject(vol->t_V);
+	if (vol->t_G) cudaDestroyTextureObject(vol->t_G);
+	if (vol->a_V) cudaFreeArray(vol->a_V);
+	if (vol->a_G) cudaFreeArray(vol->a_G);
+	cudaFree(vol->d_V); cudaFree(vol->d_G); cudaFree(vol->d_tf); cudaFree(vol->d_mask2); cudaFree(vol->d_bounds);
+	for (auto *m : vol->d_maps) cudaFree(m);
+	cudaFree(vol->d_swap); cudaFree(vol->d_tmp); cudaFree(vol->d_count); cudaFree(vol->d_counts_scratch);
+	cudaFree(vol->d_fb_scratch);
+	if (vol->h_count) cudaFreeHost(vol->h_count);
+	delete vol;
+}
+
+int vkv_volume_upload(vkv_volume *vol, const uint8_t *voxels, void *stream)
+{
+	VKV_REQUIRE(vol && voxels, VKV_ERR_ARGUMENT, "vkv_volume_upload: NULL argument");
+	DeviceGuard  guard(vol->ctx->device);
+	cudaStream_t s = (cudaStream_t) stream;
+	VKV_CUDA_CHECK(cudaMemcpyAsync(vol->d_V, voxels, vol->N, cudaMemcpyHostToDevice, s));
+	vol->has_V = true;
+	return sync_arrays_from_linear(vol, false, s);
+}
+
+int vkv_volume_upload_device(vkv_volume *vol, const uint8_t *voxels_dev, void *stream)
+{
+	VKV_REQUIRE(vol && voxels_dev, VKV_ERR_ARGUMENT, "vkv_volume_upload_device: NULL argument");
+	DeviceGuard  guard(vol->ctx->device);
+	cudaStream_t s = (cudaStream_t) stream;
+	if (voxels_dev != vol->d_V) VKV_CUDA_CHECK(cudaMemcpyAsync(vol->d_V, voxels_dev, vol->N, cudaMemcpyDeviceToDevice, s));
+	vol->has_V = true;
+	return sync_arrays_from_linear(vol, false, s);
+}
+
+int vkv_volume_upload_gradient(vkv_volume *vol, const uint8_t *gradient, void *stream)
+{
+	VKV_REQUIRE(vol && gradient, VKV_ERR_ARGUMENT, "vkv_volume_upload_gradient: NULL argument");
+	VKV_REQUIRE(vol->d_G, VKV_ERR_STATE, "volume was created without a precomputed gradient map");
+	DeviceGuard  guard(vol->ctx->device);
+	cudaStream_t s = (cudaStream_t) stream;
+	VKV_CUDA_CHECK(cudaMemcpyAsync(vol->d_G, gradient, vol->N, cudaMemcpyDefault, s));
+	vol->has_G = true;
+	return sync_arrays_from_linear(vol, true, s);
+}
+
+int vkv_volume_upload_raw(vkv_volume *vol, const void *raw, size_t raw_bytes, const char *type, const char *endianness,
+                          float lo, float hi, void *stream)
+{
+	VKV_REQUIRE(vol && raw && type && endianness, VKV_ERR_ARGUMENT, "vkv_volume_upload_raw: NULL argument");
+	int kind;
+	if (!strcmp(type, "uint8_t")) kind = 0;
+	else if (!strcmp(type, "int8_t")) kind = 1;
+	else if (!strcmp(type, "uint16_t")) kind = 2;
+	else if (!strcmp(type, "int16_t")) kind = 3;
+	else {
+		set_error("unsupported image data type");        // load_volume.cpp:106-109
+		return VKV_ERR_IO;
+	}
+	const size_t expect = vol->N * (kind >= 2 ? 2 : 1);
+	VKV_REQUIRE(raw_bytes == expect, VKV_ERR_IO, "File size does not match expected size for the given image format/dimensions");
+	DeviceGuard  guard(vol->ctx->device);
+	cudaStream_t s   = (cudaStream_t) stream;
+	void        *tmp = nullptr;
+	VKV_CUDA_CHECK(cudaMallocAsync(&tmp, raw_bytes, s));
+	VKV_CUDA_CHECK(cudaMemcpyAsync(tmp, raw, raw_bytes, cudaMemcpyHostToDevice, s));
+	int rc = launch_normalise(tmp, vol->N, kind, strcmp(endianness, "big") == 0, lo, hi, vol->d_V, s);
+	VKV_CUDA_CHECK(cudaFreeAsync(tmp, s));
+	if (rc) return rc;
+	vol->has_V = true;
+	return sync_arrays_from_linear(vol, false, s);
+}
+
+int vkv_volume_set_number_of_distance_maps(vkv_volume *vol, size_t n)
+{
+	VKV_REQUIRE(vol, VKV_ERR_ARGUMENT, "vol is NULL");
+	VKV_REQUIRE(n <= 8, VKV_ERR_ARGUMENT, "at most 8 distance maps");
+	DeviceGuard guard(vol->ctx->device);
+	if (n <= vol->d_maps.size()) return VKV_OK;        // volume_component.cpp:157-160: never shrinks
+	while (vol->d_maps.size() < n) {
+		uint8_t *m = nullptr;
+		VKV_CUDA_CHECK(cudaMalloc(&m, vol->M));
+		vol->d_maps.push_back(m);
+	}
+	return VKV_OK;
+}
+
+int vkv_transfer_function_uniform_from_options(const vkv_volume_options *o, vkv_transfer_function_uniform *u)
+{
+	VKV_REQUIRE(o && u, VKV_ERR_ARGUMENT, "NULL argument");
+	u->sampling_factor         = o->sampling_factor;
+	u->voxel_alpha_factor      = o->voxel_alpha_factor;
+	u->grad_magnitude_modifier = 1.0f;
+	u->use_gradient            = o->gradient_max != o->gradient_min ? 1u : 0u;
+	u->intensity_min           = o->intensity_min;
+	u->intensity_range_inv     = 1.0f / (o->intensity_max - o->intensity_min);
+	u->gradient_min            = o->gradient_min;
+	u->gradient_range_inv      = 1.0f / (o->gradient_max - o->gradient_min);
+	return VKV_OK;
+}
+
+int vkv_volume_update_transfer_function_texture(vkv_volume *vol, const vkv_volume_options *opt, void *stream)
+{
+	VKV_REQUIRE(vol && opt, VKV_ERR_ARGUMENT, "NULL argument");
+	DeviceGuard  guard(vol->ctx->device);
+	cudaStream_t s = (cudaStream_t) stream;
+	int          rc;
+	if ((rc = launch_tf_texture(vol, opt, s))) return rc;
+	vkv_transfer_function_uniform u;
+	vkv_transfer_function_uniform_from_options(opt, &u);
+	return launch_tf_masks(vol, &u, s);
+}
+
+int vkv_volume_set_transfer_function_texture(vkv_volume *vol, const uint8_t *rgba, void *stream)
+{
+	VKV_REQUIRE(vol && rgba, VKV_ERR_ARGUMENT, "NULL argument");
+	DeviceGuard  guard(vol->ctx->device);
+	cudaStream_t s = (cudaStream_t) stream;
+	VKV_CUDA_CHECK(cudaMemcpyAsync(vol->d_tf, rgba, 256 * 256 * 4, cudaMemcpyHostToDevice, s));
+	vol->has_tf = true;
+	return launch_tf_masks(vol, nullptr, s);
+}
+
+int vkv_compute_gradient_map(vkv_volume *vol, const vkv_transfer_function_uniform *tfu, void *stream)
+{
+	VKV_REQUIRE(vol && tfu, VKV_ERR_ARGUMENT, "NULL argument");
+	VKV_REQUIRE(vol->has_V, VKV_ERR_STATE, "vkv_compute_gradient_map: no voxels uploaded");
+	VKV_REQUIRE(vol->d_G, VKV_ERR_STATE, "volume was created without a precomputed gradient map");
+	DeviceGuard  guard(vol->ctx->device);
+	cudaStream_t s = (cudaStream_t) stream;
+	int          rc;
+	// quirk A.8.1: the map is all 1.0 when use_gradient is false at this moment
+	if ((rc = launch_gradient(vol, tfu->use_gradient != 0, tfu->grad_magnitude_modifier, s))) return rc;
+	return sync_arrays_from_linear(vol, true, s);
+}
+
+static int ensure_analytic_mask(vkv_volume *vol, const vkv_transfer_function_uniform *tfu, cudaStream_t s)
+{
+	if (vol->mask_ana_valid && !memcmp(&vol->mask_tfu, tfu, sizeof *tfu)) return VKV_OK;
+	return launch_tf_masks(vol, tfu, s);
+}
+
+static int check_gradient_inputs(vkv_volume *vol, const vkv_transfer_function_uniform *tfu)
+{
+	if (tfu->use_gradient) {
+		VKV_REQUIRE(vol->precomputed_gradient, VKV_ERR_STATE,
+		            "on-the-fly gradient variant (--gradient_test) is not implemented; create the volume with use_precomputed_gradient");
+		VKV_REQUIRE(vol->has_G, VKV_ERR_STATE, "gradient map not computed yet (vkv_compute_gradient_map)");
+	}
+	return VKV_OK;
+}
+
+int vkv_compute_occupied_voxel_count(vkv_volume *vol, const vkv_transfer_function_uniform *tfu, uint64_t *count_out, void *stream)
+{
+	VKV_REQUIRE(vol && tfu, VKV_ERR_ARGUMENT, "NULL argument");
+	VKV_REQUIRE(vol->has_V && vol->has_tf, VKV_ERR_STATE, "vkv_compute_occupied_voxel_count: upload voxels and a transfer function first");
+	int rc;
+	if ((rc = check_gradient_inputs(vol, tfu))) return rc;
+	DeviceGuard  guard(vol->ctx->device);
+	cudaStream_t s = (cudaStream_t) stream;
+	if ((rc = ensure_analytic_mask(vol, tfu, s))) return rc;
+	VKV_CUDA_CHECK(cudaMemsetAsync(vol->d_count, 0, sizeof(unsigned long long), s));
+	if ((rc = launch_occupancy(vol, tfu->use_gradient != 0, true, nullptr, 0, vol->dim_b[2], vol->d_count, s))) return rc;
+	if (count_out) {
+		VKV_CUDA_CHECK(cudaMemcpyAsync(vol->h_count, vol->d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+		VKV_CUDA_CHECK(cudaStreamSynchronize(s));
+		*count_out = vol->h_count[0];
+	}
+	return VKV_OK;
+}
+
+static int n_maps_for(int skipping_type) { return skipping_type == VKV_SKIP_ANISOTROPIC_DISTANCE ? 8 : 1; }
+
+int vkv_compute_occupancy_slab(vkv_volume *vol, const vkv_transfer_function_uniform *tfu, int skipping_type, uint32_t zb_first,
+                               uint32_t zb_count, uint64_t *count_dev, void *stream)
+{
+	VKV_REQUIRE(vol && tfu, VKV_ERR_ARGUMENT, "NULL argument");
+	VKV_REQUIRE(skipping_type >= 0 && skipping_type <= 3, VKV_ERR_ARGUMENT, "bad skipping type");
+	VKV_REQUIRE(vol->has_V && vol->has_tf, VKV_ERR_STATE, "upload voxels and a transfer function first");
+	VKV_REQUIRE(zb_first + zb_count <= vol->dim_b[2], VKV_ERR_ARGUMENT, "slab exceeds the map depth");
+	int rc;
+	if ((rc = check_gradient_inputs(vol, tfu))) return rc;
+	DeviceGuard  guard(vol->ctx->device);
+	cudaStream_t s = (cudaStream_t) stream;
+	const int    n = n_maps_for(skipping_type);
+	if ((rc = vkv_volume_set_number_of_distance_maps(vol, n))) return rc;
+	if (count_dev && (rc = ensure_analytic_mask(vol, tfu, s))) return rc;
+	vol->maps_valid_for = -1;
+	return launch_occupancy(vol, tfu->use_gradient != 0, count_dev != nullptr, vol->d_maps[n - 1], zb_first, zb_count,
+	                        reinterpret_cast<unsigned long long *>(count_dev), s);
+}
+
+int vkv_compute_distance_from_occupancy(vkv_volume *vol, int skipping_type, void *stream)
+{
+	VKV_REQUIRE(vol, VKV_ERR_ARGUMENT, "NULL argument");
+	VKV_REQUIRE(skipping_type >= 0 && skipping_type <= 3, VKV_ERR_ARGUMENT, "bad skipping type");
+	VKV_REQUIRE((int) vol->d_maps.size() >= n_maps_for(skipping_type), VKV_ERR_STATE, "occupancy map not computed");
+	DeviceGuard guard(vol->ctx->device);
+	int         rc = launch_distance(vol, skipping_type, (cudaStream_t) stream);
+	if (!rc) vol->maps_valid_for = skipping_type;
+	return rc;
+}
+
+int vkv_compute_distance_map(vkv_volume *vol, const vkv_transfer_function_uniform *tfu, int skipping_type, void *stream)
+{
+	int rc = vkv_compute_occupancy_slab(vol, tfu, skipping_type, 0, vol ? vol->dim_b[2] : 0, nullptr, stream);
+	if (rc) return rc;
+	return vkv_compute_distance_from_occupancy(vol, skipping_type, stream);
+}
+
+int vkv_update_transfer_function(vkv_volume *vol, const vkv_volume_options *opt, int skipping_type, uint64_t *count_out, void *stream)
+{
+	VKV_REQUIRE(vol && opt, VKV_ERR_ARGUMENT, "NULL argument");
+	DeviceGuard  guard(vol->ctx->device);
+	cudaStream_t s = (cudaStream_t) stream;
+	int          rc;
+	if ((rc = vkv_volume_update_transfer_function_texture(vol, opt, stream))) return rc;
+	vkv_transfer_function_uniform u;
+	vkv_transfer_function_uniform_from_options(opt, &u);
+	if (count_out) VKV_CUDA_CHECK(cudaMemsetAsync(vol->d_count, 0, sizeof(unsigned long long), s));
+	if ((rc = vkv_compute_occupancy_slab(vol, &u, skipping_type, 0, vol->dim_b[2], count_out ? (uint64_t *) vol->d_count : nullptr, stream))) return rc;
+	if ((rc = vkv_compute_distance_from_occupancy(vol, skipping_type, stream))) return rc;
+	if (count_out) {
+		VKV_CUDA_CHECK(cudaMemcpyAsync(vol->h_count, vol->d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+		VKV_CUDA_CHECK(cudaStreamSynchronize(s));
+		*count_out = vol->h_count[0];
+	}
+	return VKV_OK;
+}
+
+static int check_render(vkv_volume *vol, const vkv_transfer_function_uniform *tfu, const vkv_render_options *opt, int width, int height,
+                        int tile_w, int tile_h, int tile_stride)
+{
+	VKV_REQUIRE(width > 0 && height > 0, VKV_ERR_ARGUMENT, "bad framebuffer extent");
+	VKV_REQUIRE(tile_w > 0 && tile_h > 0 && tile_w % 16 == 0 && tile_h % 8 == 0, VKV_ERR_ARGUMENT, "tile extent must be a multiple of 16x8");
+	VKV_REQUIRE(tile_stride > 0, VKV_ERR_ARGUMENT, "tile stride must be positive");
+	VKV_REQUIRE(opt->skipping_type >= 0 && opt->skipping_type <= 3, VKV_ERR_ARGUMENT, "bad skipping type");
+	VKV_REQUIRE(opt->test >= 0 && opt->test <= 3, VKV_ERR_ARGUMENT, "bad test mode");
+	VKV_REQUIRE(!opt->depth_attachment, VKV_ERR_ARGUMENT, "depth_attachment is not supported by the headless renderer");
+	VKV_REQUIRE(vol->has_V && vol->has_tf, VKV_ERR_STATE, "vkv_render: upload voxels and a transfer function first");
+	int rc;
+	if ((rc = check_gradient_inputs(vol, tfu))) return rc;
+	if (opt->skipping_type != VKV_SKIP_NONE) {
+		VKV_REQUIRE((int) vol->d_maps.size() >= n_maps_for(opt->skipping_type), VKV_ERR_STATE,
+		            "vkv_render: distance maps for this skipping type were not computed");
+		VKV_REQUIRE(vol->maps_valid_for == opt->skipping_type ||
+		                (opt->skipping_type == VKV_SKIP_BLOCK && vol->maps_valid_for == VKV_SKIP_NONE),
+		            VKV_ERR_STATE, "vkv_render: maps hold a different skipping type; call vkv_compute_distance_map first");
+	}
+	return VKV_OK;
+}
+
+int vkv_render_tiles(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_cast_uniform *ray,
+                     const vkv_transfer_function_uniform *tfu, const vkv_render_options *opt, int width, int height, int tile_w,
+                     int tile_h, int tile_first, int tile_stride, uint8_t *rgba8_dev, float *depth_dev, vkv_sample_counts *counts_dev,
+                     void *stream)
+{
+	VKV_REQUIRE(vol && cam && ray && tfu && opt && rgba8_dev, VKV_ERR_ARGUMENT, "vkv_render: NULL argument");
+	VKV_REQUIRE(tile_first >= 0, VKV_ERR_ARGUMENT, "tile_first must be >= 0");
+	int rc;
+	if ((rc = check_render(vol, tfu, opt, width, height, tile_w, tile_h, tile_stride))) return rc;
+	DeviceGuard guard(vol->ctx->device);
+	return launch_render(vol, cam, ray, tfu, opt, width, height, tile_w, tile_h, tile_first, tile_stride, rgba8_dev, depth_dev,
+	                     counts_dev, (cudaStream_t) stream);
+}
+
+int vkv_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_cast_uniform *ray, const vkv_transfer_function_uniform *tfu,
+               const vkv_render_options *opt, int width, int height, uint8_t *rgba8_dev, float *depth_dev,
+               vkv_sample_counts *counts_dev, void *stream)
+{
+	return vkv_render_tiles(vol, cam, ray, tfu, opt, width, height, 64, 32, 0, 1, rgba8_dev, depth_dev, counts_dev, stream);
+}
+
+int vkv_render_to_host(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_cast_uniform *ray,
+                       const vkv_transfer_function_uniform *tfu, const vkv_render_options *opt, int width, int height,
+                       uint8_t *rgba8_host, vkv_sample_counts *counts_host, void *stream)
+{
+	VKV_REQUIRE(vol && rgba8_host, VKV_ERR_ARGUMENT, "vkv_render_to_host: NULL argument");
+	DeviceGuard  guard(vol->ctx->device);
+	cudaStream_t s     = (cudaStream_t) stream;
+	const size_t bytes = (size_t) width * height * 4;
+	if (vol->fb_scratch_bytes < bytes) {
+		cudaFree(vol->d_fb_scratch);
+		vol->d_fb_scratch     = nullptr;
+		vol->fb_scratch_bytes = 0;
+		VKV_CUDA_CHECK(cudaMalloc(&vol->d_fb_scratch, bytes));
+		vol->fb_scratch_bytes = bytes;
+	}
+	if (counts_host) VKV_CUDA_CHECK(cudaMemsetAsync(vol->d_counts_scratch, 0, sizeof(vkv_sample_counts), s));
+	int rc = vkv_render(vol, cam, ray, tfu, opt, width, height, vol->d_fb_scratch, nullptr, counts_host ? vol->d_counts_scratch : nullptr, stream);
+	if (rc) return rc;
+	VKV_CUDA_CHECK(cudaMemcpyAsync(rgba8_host, vol->d_fb_scratch, bytes, cudaMemcpyDeviceToHost, s));
+	if (counts_host) VKV_CUDA_CHECK(cudaMemcpyAsync(counts_host, vol->d_counts_scratch, sizeof(vkv_sample_counts), cudaMemcpyDeviceToHost, s));
+	VKV_CUDA_CHECK(cudaStreamSynchronize(s));
+	return VKV_OK;
+}
+
+int vkv_volume_extent(const vkv_volume *vol, uint32_t out[3])
+{
+	VKV_REQUIRE(vol && out, VKV_ERR_ARGUMENT, "NULL argument");
+	memcpy(out, vol->dim, sizeof vol->dim);
+	return VKV_OK;
+}
+int vkv_volume_map_extent(const vkv_volume *vol, uint32_t out[3])
+{
+	VKV_REQUIRE(vol && out, VKV_ERR_ARGUMENT, "NULL argument");
+	memcpy(out, vol->dim_b, sizeof vol->dim_b);
+	return VKV_OK;
+}
+int vkv_volume_block_size(const vkv_volume *vol, uint32_t out[3])
+{
+	VKV_REQUIRE(vol && out, VKV_ERR_ARGUMENT, "NULL argument");
+	memcpy(out, vol->bs, sizeof vol->bs);
+	return VKV_OK;
+}
+size_t   vkv_volume_number_of_distance_maps(const vkv_volume *vol) { return vol ? vol->d_maps.size() : 0; }
+uint8_t *vkv_volume_device_voxels(vkv_volume *vol) { return vol ? vol->d_V : nullptr; }
+uint8_t *vkv_volume_device_gradient(vkv_volume *vol) { return vol ? vol->d_G : nullptr; }
+uint8_t *vkv_volume_device_distance_map(vkv_volume *vol, size_t idx) { return vol && idx < vol->d_maps.size() ? vol->d_maps[idx] : nullptr; }
+uint8_t *vkv_volume_device_transfer_function(vkv_volume *vol) { return vol ? vol->d_tf : nullptr; }
+
+static int download(vkv_volume *vol, const uint8_t *src, size_t bytes, uint8_t *out, size_t out_size)
+{
+	VKV_REQUIRE(vol && out, VKV_ERR_ARGUMENT, "NULL argument");
+	VKV_REQUIRE(src, VKV_ERR_STATE, "resource does not exist");
+	VKV_REQUIRE(out_size >= bytes, VKV_ERR_ARGUMENT, "output buffer too small");
+	DeviceGuard guard(vol->ctx->device);
+	VKV_CUDA_CHECK(cudaDeviceSynchronize());
+	VKV_CUDA_CHECK(cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost));
+	return VKV_OK;
+}
+int vkv_volume_download_voxels(vkv_volume *vol, uint8_t *out, size_t n) { return download(vol, vol ? vol->d_V : nullptr, vol ? vol->N : 0, out, n); }
+int vkv_volume_download_gradient(vkv_volume *vol, uint8_t *out, size_t n) { return download(vol, vol ? vol->d_G : nullptr, vol ? vol->N : 0, out, n); }
+int vkv_volume_download_distance_map(vkv_volume *vol, size_t idx, uint8_t *out, size_t n)
+{
+	return download(vol, vkv_volume_device_distance_map(vol, idx), vol ? vol->M : 0, out, n);
+}
+int vkv_volume_download_transfer_function(vkv_volume *vol, uint8_t *out, size_t n) { return download(vol, vol ? vol->d_tf : nullptr, 256 * 256 * 4, out, n); }
+
+int vkv_ipc_export(void *dev_ptr, uint8_t handle_out[VKV_IPC_HANDLE_BYTES])
+{
+	static_assert(sizeof(cudaIpcMemHandle_t) == VKV_IPC_HANDLE_BYTES, "IPC handle size");
+	VKV_REQUIRE(dev_ptr && handle_out, VKV_ERR_ARGUMENT, "NULL argument");
+	cudaIpcMemHandle_t h;
+	VKV_CUDA_CHECK(cudaIpcGetMemHandle(&h, dev_ptr));
+	memcpy(handle_out, &h, sizeof h);
+	return VKV_OK;
+}
+int vkv_ipc_open(const uint8_t handle[VKV_IPC_HANDLE_BYTES], void **dev_ptr_out)
+{
+	VKV_REQUIRE(handle && dev_ptr_out, VKV_ERR_ARGUMENT, "NULL argument");
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle, sizeof h);
+	VKV_CUDA_CHECK(cudaIpcOpenMemHandle(dev_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+	return VKV_OK;
+}
+int vkv_ipc_close(void *dev_ptr)
+{
+	VKV_REQUIRE(dev_ptr, VKV_ERR_ARGUMENT, "NULL argument");
+	VKV_CUDA_CHECK(cudaIpcCloseMemHandle(dev_ptr));
+	return VKV_OK;
+}
+
+}        // extern "C"

@@ -1,0 +1,121 @@
+// common.cuh — internal declarations shared by the libvkv translation units.
+//
+// The product path: everything below runs on the device as hand-written sm_100a
+// kernels.  There is no CPU fallback; a missing/failed CUDA device surfaces as
+// VKV_ERR_CUDA from every entry point.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/vkv.h"
+
+namespace vkv {
+
+void set_error(const char *fmt, ...);
+extern std::atomic<uint64_t> g_kernel_launches;
+
+#define VKV_CUDA_CHECK(expr)                                                                      \
+	do {                                                                                          \
+		cudaError_t _e = (expr);                                                                  \
+		if (_e != cudaSuccess) {                                                                  \
+			::vkv::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+			return VKV_ERR_CUDA;                                                                  \
+		}                                                                                         \
+	} while (0)
+
+#define VKV_REQUIRE(cond, code, msg)  \
+	do {                              \
+		if (!(cond)) {                \
+			::vkv::set_error("%s", msg); \
+			return code;              \
+		}                             \
+	} while (0)
+
+// Launch bookkeeping: every kernel launch in the library goes through this so
+// vkv_kernel_launch_count() is an honest count.
+#define VKV_LAUNCHED()                                   \
+	do {                                                 \
+		::vkv::g_kernel_launches.fetch_add(1, std::memory_order_relaxed); \
+		VKV_CUDA_CHECK(cudaGetLastError());              \
+	} while (0)
+
+static inline uint32_t rnd_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+// Visibility masks derived from the transfer function (one bit per (gradient, intensity) texel):
+//   .x : TF-texture alpha byte > 0            (occupancy, shaders/occupancy_map.comp:63-64)
+//   .y : analytic alphaI*alphaG > 0           (voxel count, shaders/occupied_voxel_count.comp:39-43)
+// word index = gradient * 8 + (intensity >> 5), bit = intensity & 31.
+constexpr int kMaskWords = 256 * 256 / 32;
+
+// Conservative [lo, hi] byte ranges outside which no texel is visible; lets the
+// O(N) pass reject 4 voxels at a time with SIMD byte compares before touching the LUT.
+struct TFBounds {
+	// [0]: all rows, texture mask only; [1]: all rows, union of both masks;
+	// [2]: row 255 only (use_gradient == false), texture mask; [3]: row 255, union.
+	uint32_t v_lo[4], v_hi[4], g_lo[4], g_hi[4];
+};
+
+}        // namespace vkv
+
+struct vkv_context {
+	int            device   = 0;
+	int            sm_count = 0;
+	cudaDeviceProp prop{};
+};
+
+struct vkv_volume {
+	vkv_context *ctx = nullptr;
+	uint32_t     dim[3]{};         // W H D voxels
+	uint32_t     dim_b[3]{};       // map extent = ceil(dim / bs_requested)   (volume_component.cpp:91-93)
+	uint32_t     bs[3]{};          // effective block size = ceil(dim / dim_b) (compute_distance_map.cpp:108-113)
+	uint32_t     bs_requested = 4;
+	bool         precomputed_gradient = true;
+	size_t       N = 0, M = 0;
+
+	uint8_t *d_V = nullptr;        // linear voxels   (K1, K2 read these)
+	uint8_t *d_G = nullptr;        // linear gradient
+	cudaArray_t         a_V = nullptr, a_G = nullptr;        // 3D arrays (K4 samples these)
+	cudaTextureObject_t t_V = 0, t_G = 0;
+	bool     has_V = false, has_G = false;
+
+	uint8_t        *d_tf      = nullptr;        // 256*256 RGBA8
+	uint2          *d_mask2   = nullptr;        // kMaskWords x {texture, analytic}
+	vkv::TFBounds  *d_bounds  = nullptr;
+	bool            has_tf    = false;
+	vkv_transfer_function_uniform mask_tfu{};   // tfu the analytic mask was built for
+	bool            mask_ana_valid = false;
+
+	std::vector<uint8_t *> d_maps;        // distance maps (map n-1 doubles as the occupancy map)
+	uint8_t               *d_swap = nullptr;
+	uint8_t               *d_tmp  = nullptr;        // second scratch map (anisotropic x-pass results)
+	int                    maps_valid_for = -1;     // skipping type the maps currently hold
+
+	unsigned long long *d_count = nullptr;        // device-side count + render counters
+	unsigned long long *h_count = nullptr;        // pinned
+	vkv_sample_counts  *d_counts_scratch = nullptr;
+	uint8_t            *d_fb_scratch = nullptr;        // framebuffer for vkv_render_to_host
+	size_t              fb_scratch_bytes = 0;
+	uint8_t            *h_fb_scratch = nullptr;        // unused unless caller memory is pageable
+};
+
+namespace vkv {
+// kernels' host-side launchers (one per translation unit)
+int launch_tf_texture(vkv_volume *vol, const vkv_volume_options *opt, cudaStream_t s);
+int launch_tf_masks(vkv_volume *vol, const vkv_transfer_function_uniform *tfu_or_null, cudaStream_t s);
+int launch_gradient(vkv_volume *vol, bool use_gradient, float modifier, cudaStream_t s);
+int launch_occupancy(vkv_volume *vol, bool use_gradient, bool count, uint8_t *O, uint32_t zb_first, uint32_t zb_count,
+                     unsigned long long *count_dev, cudaStream_t s);
+int launch_distance(vkv_volume *vol, int skipping_type, cudaStream_t s);
+int launch_normalise(const void *raw_dev, size_t n, int kind, bool big_endian, float lo, float hi, uint8_t *out,
+                     cudaStream_t s);
+int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_cast_uniform *ray,
+                  const vkv_transfer_function_uniform *tfu, const vkv_render_options *opt, int width, int height,
+                  int tile_w, int tile_h, int tile_first, int tile_stride, uint8_t *rgba8, float *depth,
+                  vkv_sample_counts *counts, cudaStream_t s);
+int sync_arrays_from_linear(vkv_volume *vol, bool gradient, cudaStream_t s);
+}        // namespace vkv

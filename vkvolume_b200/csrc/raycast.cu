@@ -1,0 +1,401 @@
+// raycast.cu — K4v + K4: per-pixel ray caster with empty-space skipping and early ray termination.
+//
+// Replaces VolumeRenderSubpass::draw (src/volume_render_subpass.cpp:159-294): two indexed draws
+// (clipped unit cube via shaders/volume_render_clipped.vert + HW user clip plane + back-face cull,
+// box/plane polygon via shaders/volume_render_plane_intersection.vert), the rasteriser, the fragment
+// shader shaders/volume_render.frag and the fixed-function blend + R8G8B8A8_SRGB store.
+//
+// B200 design:
+//   * no geometry at all: each pixel computes its ray/box/clip-plane entry analytically in fp64
+//     from an affine pixel->direction basis built on the host;
+//   * one thread per pixel, a warp is an 8x4 pixel tile (coherent rays -> coherent texture and
+//     distance-map fetches), a CTA is a 16x8 tile;
+//   * V and G are cudaArray 3D textures sampled with hardware trilinear filtering
+//     (tex3D, normalised coordinates, clamp, UNORM->float); an EXACT variant does 8 point loads
+//     from the linear copies and fp32 lerps in the oracle's operation order;
+//   * the distance / occupancy maps are plain byte loads through L1 (texelFetch semantics);
+//   * the transfer function is a 256x256 RGBA8 table read through the read-only path; the
+//     opacity-correction pow() is hoisted into a 256-entry shared-memory table;
+//   * blend-with-clear, sRGB encode and the RGBA8 store happen in the epilogue; the store
+//     target may be a peer-mapped framebuffer (multi-GPU tile gather fused into the kernel).
+// The march loop is the fragment shader's, statement for statement, in fp32 without contraction.
+#include "common.cuh"
+
+namespace vkv {
+
+struct RayParams {
+	double o[3];                    // camera position, texture space
+	double d0[3], ddx[3], ddy[3];   // far-plane direction of pixel (px,py): d0 + px*ddx + py*ddy
+	double plane[4];                // clip plane, texture space
+	double pvm_z[4], pvm_w[4];      // rows z and w of proj*view*model (depth output)
+	float  cam_pos_tex[3];
+	float  dimf[3];
+	float  block_size[3];
+	int    dim[3];
+	int    dim_b[3];
+	int    dim_max;
+	float  sampling_factor, sampling_factor_inv, voxel_alpha_factor, grad_modifier;
+	int    use_gradient;
+	int    ert, test;
+	int    width, height;
+	int    tile_w, tile_h, tiles_x, tile_first, tile_stride, ctas_per_tile_x, ctas_per_tile;
+	cudaTextureObject_t tex_v, tex_g;
+	const uint8_t *V, *G;
+	const uchar4  *tf;
+	const uint8_t *maps;            // map 0; map i at maps_stride * i (anisotropic)
+	const uint8_t *map_ptrs[8];
+	uint8_t       *rgba8;
+	float         *depth;
+	unsigned long long *counts;     // vkv_sample_counts or null
+};
+
+__device__ __forceinline__ float clampf_(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+__device__ __forceinline__ int   clampi_(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
+__device__ __forceinline__ int   tf_texel(float c) { return clampi_((int) floorf(c * 256.0f), 0, 255); }
+
+// texture(sampler3D, pos), LINEAR / CLAMP_TO_EDGE / UNORM — fp32 restatement on the linear copy
+__device__ __forceinline__ float sample_exact(const uint8_t *__restrict__ T, const int dim[3], float px, float py, float pz)
+{
+	const float u = px * (float) dim[0] - 0.5f, v = py * (float) dim[1] - 0.5f, w = pz * (float) dim[2] - 0.5f;
+	const float fu = floorf(u), fv = floorf(v), fw = floorf(w);
+	const float a = u - fu, b = v - fv, c = w - fw;
+	int         x0 = (int) fu, y0 = (int) fv, z0 = (int) fw;
+	const int   mx = dim[0] - 1, my = dim[1] - 1, mz = dim[2] - 1;
+	const int   x1 = clampi_(x0 + 1, 0, mx), y1 = clampi_(y0 + 1, 0, my), z1 = clampi_(z0 + 1, 0, mz);
+	x0 = clampi_(x0, 0, mx); y0 = clampi_(y0, 0, my); z0 = clampi_(z0, 0, mz);
+	const size_t W = dim[0], WH = (size_t) dim[0] * dim[1];
+	auto ld = [&](int x, int y, int z) { return (float) __ldg(T + (size_t) z * WH + (size_t) y * W + x) / 255.0f; };
+	const float t000 = ld(x0, y0, z0), t100 = ld(x1, y0, z0), t010 = ld(x0, y1, z0), t110 = ld(x1, y1, z0);
+	const float t001 = ld(x0, y0, z1), t101 = ld(x1, y0, z1), t011 = ld(x0, y1, z1), t111 = ld(x1, y1, z1);
+	const float c00 = t000 * (1.0f - a) + t100 * a, c10 = t010 * (1.0f - a) + t110 * a;
+	const float c01 = t001 * (1.0f - a) + t101 * a, c11 = t011 * (1.0f - a) + t111 * a;
+	const float c0 = c00 * (1.0f - b) + c10 * b, c1 = c01 * (1.0f - b) + c11 * b;
+	return c0 * (1.0f - c) + c1 * c;
+}
+
+__device__ __forceinline__ float srgb_encode(float c) { return c <= 0.0031308f ? 12.92f * c : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f; }
+__device__ __forceinline__ unsigned unorm8(float c) { return (unsigned) (clampf_(c, 0.0f, 1.0f) * 255.0f + 0.5f); }
+
+template <int SKIP, bool EXACT>
+__global__ void __launch_bounds__(128) raycast_kernel(const __grid_constant__ RayParams P)
+{
+	__shared__ float s_acorr[256];        // opacity correction per TF alpha byte (volume_render.frag:283)
+	__shared__ unsigned long long s_cnt[4][4];
+	for (int k = threadIdx.x; k < 256; k += blockDim.x) {
+		const float a = (float) k / 255.0f;
+		s_acorr[k]    = clampf_(P.voxel_alpha_factor * (1.0f - powf(1.0f - a, P.sampling_factor_inv)), 0.0f, 1.0f);
+	}
+	__syncthreads();
+
+	// CTA -> tile -> pixel
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int local_tile = blockIdx.x / P.ctas_per_tile, in_tile = blockIdx.x % P.ctas_per_tile;
+	const int tile = P.tile_first + local_tile * P.tile_stride;
+	const int tx0 = (tile % P.tiles_x) * P.tile_w + (in_tile % P.ctas_per_tile_x) * 16;
+	const int ty0 = (tile / P.tiles_x) * P.tile_h + (in_tile / P.ctas_per_tile_x) * 8;
+	const int px = tx0 + (warp & 1) * 8 + (lane & 7);
+	const int py = ty0 + (warp >> 1) * 4 + (lane >> 3);
+	const bool in_frame = px < P.width && py < P.height && px < (tile % P.tiles_x) * P.tile_w + P.tile_w &&
+	                      py < (tile / P.tiles_x) * P.tile_h + P.tile_h;
+
+	unsigned n_vol = 0, n_dist = 0, n_empty = 0, covered = 0;
+	float    out[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+	float    frag_depth = 0.0f;
+	float    r = 0.0f, g = 0.0f, b = 0.0f, a = 1.0f;        // clear colour (0,0,0,1)  (render_pipeline.cpp:38)
+
+	if (in_frame) {
+		// ---- analytic ray entry (replaces both vertex shaders + rasteriser) ----
+		double d[3], tn = -INFINITY, tf = INFINITY;
+		bool   hit = true;
+#pragma unroll
+		for (int k = 0; k < 3; ++k) {
+			d[k] = P.d0[k] + (double) px * P.ddx[k] + (double) py * P.ddy[k];
+			if (d[k] == 0.0) {
+				if (P.o[k] < 0.0 || P.o[k] > 1.0) hit = false;
+			} else {
+				double t0 = (0.0 - P.o[k]) / d[k], t1 = (1.0 - P.o[k]) / d[k];
+				if (t0 > t1) { const double t = t0; t0 = t1; t1 = t; }
+				if (t0 > tn) tn = t0;
+				if (t1 < tf) tf = t1;
+			}
+		}
+		const double s0 = P.plane[0] * P.o[0] + P.plane[1] * P.o[1] + P.plane[2] * P.o[2] + P.plane[3];
+		const double sd = P.plane[0] * d[0] + P.plane[1] * d[1] + P.plane[2] * d[2];
+		float        entry[3] = {0.0f, 0.0f, 0.0f};
+		if (hit && sd > 0.0) {
+			const double t_clip = -s0 / sd;
+			double       t0     = tn > t_clip ? tn : t_clip;
+			if (t0 < 0.0) t0 = 0.0;
+			if (t0 < tf) {
+				covered = 1;
+#pragma unroll
+				for (int k = 0; k < 3; ++k) entry[k] = (float) (P.o[k] + t0 * d[k]);
+			}
+		}
+
+		if (covered) {
+			// ---- fragment shader main() (volume_render.frag:117-336) ----
+			const float dv[3] = {entry[0] - P.cam_pos_tex[0], entry[1] - P.cam_pos_tex[1], entry[2] - P.cam_pos_tex[2]};
+			const float dl    = sqrtf((dv[0] * dv[0] + dv[1] * dv[1]) + dv[2] * dv[2]);
+			const float dir[3] = {dv[0] / dl, dv[1] / dl, dv[2] / dl};
+			float t2[3];
+#pragma unroll
+			for (int k = 0; k < 3; ++k) {
+				const float inv   = 1.0f / dir[k];
+				const float t_min = -entry[k] * inv, t_max = (1.0f - entry[k]) * inv;
+				t2[k]             = fmaxf(t_min, t_max);
+			}
+			const float t_far       = fminf(fminf(t2[0], t2[1]), t2[2]);
+			const float ray_exit[3] = {t_far * dir[0] + entry[0], t_far * dir[1] + entry[1], t_far * dir[2] + entry[2]};
+			const float ev[3]       = {entry[0] - ray_exit[0], entry[1] - ray_exit[1], entry[2] - ray_exit[2]};
+			const float ray_distance = sqrtf((ev[0] * ev[0] + ev[1] * ev[1]) + ev[2] * ev[2]);
+
+			if (P.test == VKV_TEST_RAY_ENTRY) {
+				out[0] = entry[0]; out[1] = entry[1]; out[2] = entry[2]; out[3] = 1.0f;
+			} else if (P.test == VKV_TEST_RAY_EXIT) {
+				out[0] = ray_exit[0]; out[1] = ray_exit[1]; out[2] = ray_exit[2]; out[3] = 1.0f;
+			} else {
+				const int n_steps = (int) ceilf((float) P.dim_max * ray_distance * P.sampling_factor);
+				float     step[3];
+#pragma unroll
+				for (int k = 0; k < 3; ++k) step[k] = dir[k] * ray_distance / ((float) n_steps - 1.0f);
+				bool inside = true;
+#pragma unroll
+				for (int k = 0; k < 3; ++k) {
+					const float t = entry[k] + step[k];
+					if (!(t > 0.0f && t < 1.0f)) inside = false;        // lessThanEqual 0 / greaterThanEqual 1 / NaN
+				}
+				if (inside) {
+					float vol_to_map[3], sdt_inv[3];
+					int   dim_map_1[3];
+#pragma unroll
+					for (int k = 0; k < 3; ++k) {
+						vol_to_map[k]   = P.dimf[k] / P.block_size[k];
+						dim_map_1[k]    = P.dim_b[k] - 1;
+						const float sdt = step[k] * P.dimf[k] / P.block_size[k];
+						sdt_inv[k]      = 1.0f / sdt;
+					}
+					const uint8_t *__restrict__ Dm = P.map_ptrs[0];
+					if (SKIP == VKV_SKIP_ANISOTROPIC_DISTANCE)
+						Dm = P.map_ptrs[(dir[2] < 0 ? 1 : 0) + (dir[1] < 0 ? 2 : 0) + (dir[0] < 0 ? 4 : 0)];
+					int  i_min = 0, u_last[3] = {0, 0, 0};
+					bool voxel_occupied = true;
+					int  i_first_hit    = n_steps;
+					const int back = (int) ceilf(P.sampling_factor);
+					for (int i = 0; i < n_steps;) {
+						const float fi     = (float) i;
+						const float pos[3] = {entry[0] + fi * step[0], entry[1] + fi * step[1], entry[2] + fi * step[2]};
+						float u[3];
+						int   u_i[3] = {0, 0, 0};
+						bool  do_skip = false;
+						if (SKIP != VKV_SKIP_NONE) {
+#pragma unroll
+							for (int k = 0; k < 3; ++k) {
+								u[k]   = vol_to_map[k] * pos[k];
+								u_i[k] = clampi_((int) u[k], 0, dim_map_1[k]);
+							}
+							do_skip = !voxel_occupied && (u_i[0] != u_last[0] || u_i[1] != u_last[1] || u_i[2] != u_last[2]);
+						}
+						if (SKIP != VKV_SKIP_NONE && do_skip) {
+							++n_dist;
+							const unsigned dist = __ldg(Dm + ((size_t) u_i[2] * P.dim_b[1] + (size_t) u_i[1]) * P.dim_b[0] + (size_t) u_i[0]);
+							if (dist > 0u) {
+								float dxyz[3];
+#pragma unroll
+								for (int k = 0; k < 3; ++k) {
+									const float rr = clampf_((float) u_i[k] - u[k], -1.0f, 0.0f);
+									if (SKIP == VKV_SKIP_BLOCK) {
+										dxyz[k] = ((sdt_inv[k] < 0.0f ? 0.0f : 1.0f) + rr) * sdt_inv[k];
+									} else {
+										const float st = (-sdt_inv[k] < 0.0f) ? 0.0f : 1.0f;
+										const float sg = sdt_inv[k] > 0.0f ? 1.0f : (sdt_inv[k] < 0.0f ? -1.0f : 0.0f);
+										dxyz[k]        = (st + sg * (float) dist + rr) * sdt_inv[k];
+									}
+								}
+								const float m       = fminf(fminf(dxyz[0], dxyz[1]), dxyz[2]);
+								int         i_delta = (int) ceilf(m);
+								if (i_delta < 1) i_delta = 1;
+								i += i_delta;
+							} else {
+								voxel_occupied = true;
+								u_last[0] = u_i[0]; u_last[1] = u_i[1]; u_last[2] = u_i[2];
+								i = max(i - back, i_min);
+							}
+						} else {
+							++n_vol;
+							float intensity, gradient = 1.0f;
+							if (EXACT) {
+								intensity = sample_exact(P.V, P.dim, pos[0], pos[1], pos[2]);
+								if (P.use_gradient) gradient = sample_exact(P.G, P.dim, pos[0], pos[1], pos[2]);
+							} else {
+								intensity = tex3D<float>(P.tex_v, pos[0], pos[1], pos[2]);
+								if (P.use_gradient) gradient = tex3D<float>(P.tex_g, pos[0], pos[1], pos[2]);
+							}
+							const uchar4 tx = __ldg(P.tf + tf_texel(gradient) * 256 + tf_texel(intensity));
+							voxel_occupied  = tx.w > 0;
+							if (voxel_occupied) {
+								if (SKIP != VKV_SKIP_NONE) { u_last[0] = u_i[0]; u_last[1] = u_i[1]; u_last[2] = u_i[2]; }
+								const float ca = s_acorr[tx.w];
+								const float c0 = ((float) tx.x / 255.0f) * ca, c1 = ((float) tx.y / 255.0f) * ca, c2 = ((float) tx.z / 255.0f) * ca;
+								const float w  = 1.0f - out[3];
+								out[0] = out[0] + w * c0; out[1] = out[1] + w * c1; out[2] = out[2] + w * c2; out[3] = out[3] + w * ca;
+								if (ca > 0.0f) i_first_hit = i;
+								if (out[3] > 0.99f && P.ert) {
+									out[3] = 1.0f;
+									break;
+								}
+							} else {
+								++n_empty;
+							}
+							++i;
+							if (SKIP != VKV_SKIP_NONE) i_min = i;
+						}
+					}
+					if (P.depth && out[3] > 0.0f && i_first_hit < n_steps) {
+						const double pm[3] = {(double) (entry[0] + step[0] * (float) i_first_hit) - 0.5,
+						                      (double) (entry[1] + step[1] * (float) i_first_hit) - 0.5,
+						                      (double) (entry[2] + step[2] * (float) i_first_hit) - 0.5};
+						const double z = P.pvm_z[0] * pm[0] + P.pvm_z[1] * pm[1] + P.pvm_z[2] * pm[2] + P.pvm_z[3];
+						const double w = P.pvm_w[0] * pm[0] + P.pvm_w[1] * pm[1] + P.pvm_w[2] * pm[2] + P.pvm_w[3];
+						frag_depth     = (float) (z / w);
+					}
+					if (P.test == VKV_TEST_NUM_TEXTURE_SAMPLES) {
+						const unsigned n_max = (unsigned) (ceilf((float) P.dim_max * sqrtf(3.0f)) * P.sampling_factor);
+						const float    s     = (float) (n_vol + n_dist) / (float) n_max;
+						out[0] = out[1] = out[2] = s;
+						out[3] = 1.0f;
+					}
+				}
+			}
+			// blend with the clear colour: rgb = src.rgb + dst.rgb*(1-src.a), a = src.a*(1-src.a) + dst.a*0
+			r = out[0]; g = out[1]; b = out[2];
+			a = out[3] * (1.0f - out[3]);
+		}
+		// R8G8B8A8_SRGB store
+		const unsigned packed = unorm8(srgb_encode(clampf_(r, 0.0f, 1.0f))) | (unorm8(srgb_encode(clampf_(g, 0.0f, 1.0f))) << 8) |
+		                        (unorm8(srgb_encode(clampf_(b, 0.0f, 1.0f))) << 16) | (unorm8(a) << 24);
+		const size_t p = (size_t) py * P.width + px;
+		reinterpret_cast<unsigned *>(P.rgba8)[p] = packed;
+		if (P.depth) P.depth[p] = frag_depth;
+	}
+
+	if (P.counts) {
+		unsigned long long c[4] = {n_vol, n_dist, n_empty, covered};
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) c[k] += __shfl_xor_sync(0xffffffffu, c[k], o);
+			if (lane == 0) s_cnt[warp][k] = c[k];
+		}
+		__syncthreads();
+		if (threadIdx.x < 4) {
+			const unsigned long long t = s_cnt[0][threadIdx.x] + s_cnt[1][threadIdx.x] + s_cnt[2][threadIdx.x] + s_cnt[3][threadIdx.x];
+			if (t) atomicAdd(P.counts + threadIdx.x, t);
+		}
+	}
+}
+
+// ---- host side: build RayParams in fp64 from the reference's uniforms ------------------------
+static void mul_mv(const double *m, const double *v, double *out)
+{
+	for (int r = 0; r < 4; ++r) out[r] = m[0 + r] * v[0] + m[4 + r] * v[1] + m[8 + r] * v[2] + m[12 + r] * v[3];
+}
+static void mul_mm(const double *a, const double *b, double *out)
+{
+	double t[16];
+	for (int c = 0; c < 4; ++c)
+		for (int r = 0; r < 4; ++r) {
+			double s = 0;
+			for (int k = 0; k < 4; ++k) s += a[k * 4 + r] * b[c * 4 + k];
+			t[c * 4 + r] = s;
+		}
+	for (int i = 0; i < 16; ++i) out[i] = t[i];
+}
+
+static void far_dir(const vkv_camera_uniform *cam, const vkv_ray_cast_uniform *ray, double px, double py, int W, int H, double d[3])
+{
+	double vpi[16], mi[16];
+	for (int i = 0; i < 16; ++i) { vpi[i] = cam->view_proj_inv[i]; mi[i] = cam->model_inv[i]; }
+	const double ndc[4] = {2.0 * (px + 0.5) / W - 1.0, 2.0 * (py + 0.5) / H - 1.0, 0.0, 1.0};        // z = 0: far plane (reverse-Z)
+	double       wp[4], mp[4];
+	mul_mv(vpi, ndc, wp);
+	for (int k = 0; k < 3; ++k) wp[k] /= wp[3];
+	wp[3] = 1.0;
+	mul_mv(mi, wp, mp);
+	for (int k = 0; k < 3; ++k) d[k] = mp[k] + 0.5 - (double) ray->cam_pos_tex[k];
+}
+
+int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_cast_uniform *ray,
+                  const vkv_transfer_function_uniform *tfu, const vkv_render_options *opt, int width, int height, int tile_w,
+                  int tile_h, int tile_first, int tile_stride, uint8_t *rgba8, float *depth, vkv_sample_counts *counts,
+                  cudaStream_t s)
+{
+	RayParams P{};
+	double    dx1[3], dy1[3];
+	far_dir(cam, ray, 0, 0, width, height, P.d0);
+	far_dir(cam, ray, 1, 0, width, height, dx1);
+	far_dir(cam, ray, 0, 1, width, height, dy1);
+	for (int k = 0; k < 3; ++k) {
+		P.ddx[k] = dx1[k] - P.d0[k];
+		P.ddy[k] = dy1[k] - P.d0[k];
+		P.o[k]   = ray->cam_pos_tex[k];
+		P.cam_pos_tex[k] = ray->cam_pos_tex[k];
+		P.dimf[k]        = (float) vol->dim[k];
+		P.dim[k]         = (int) vol->dim[k];
+		P.dim_b[k]       = (int) vol->dim_b[k];
+		P.block_size[k]  = ray->block_size[k];
+	}
+	for (int k = 0; k < 4; ++k) P.plane[k] = ray->plane_tex[k];
+	{
+		double pr[16], vw[16], md[16], pv[16], pvm[16];
+		for (int i = 0; i < 16; ++i) { pr[i] = cam->proj[i]; vw[i] = cam->view[i]; md[i] = cam->model[i]; }
+		mul_mm(pr, vw, pv);
+		mul_mm(pv, md, pvm);
+		for (int c = 0; c < 4; ++c) { P.pvm_z[c] = pvm[c * 4 + 2]; P.pvm_w[c] = pvm[c * 4 + 3]; }
+	}
+	P.dim_max             = (int) std::max(vol->dim[0], std::max(vol->dim[1], vol->dim[2]));
+	P.sampling_factor     = tfu->sampling_factor;
+	P.sampling_factor_inv = 1.0f / tfu->sampling_factor;
+	P.voxel_alpha_factor  = tfu->voxel_alpha_factor;
+	P.grad_modifier       = tfu->grad_magnitude_modifier;
+	P.use_gradient        = tfu->use_gradient ? 1 : 0;
+	P.ert                 = opt->early_ray_termination ? 1 : 0;
+	P.test                = opt->test;
+	P.width = width; P.height = height;
+	P.tile_w = tile_w; P.tile_h = tile_h;
+	P.tiles_x         = (width + tile_w - 1) / tile_w;
+	const int tiles_y = (height + tile_h - 1) / tile_h;
+	const int n_tiles = P.tiles_x * tiles_y;
+	P.tile_first = tile_first; P.tile_stride = tile_stride;
+	P.ctas_per_tile_x = tile_w / 16;
+	P.ctas_per_tile   = P.ctas_per_tile_x * (tile_h / 8);
+	const int my_tiles = tile_first < n_tiles ? (n_tiles - tile_first + tile_stride - 1) / tile_stride : 0;
+	if (my_tiles == 0) return VKV_OK;
+	P.tex_v = vol->t_V; P.tex_g = vol->t_G;
+	P.V = vol->d_V; P.G = vol->d_G;
+	P.tf = reinterpret_cast<const uchar4 *>(vol->d_tf);
+	for (int i = 0; i < 8; ++i) P.map_ptrs[i] = i < (int) vol->d_maps.size() ? vol->d_maps[i] : nullptr;
+	P.maps   = P.map_ptrs[0];
+	P.rgba8  = rgba8;
+	P.depth  = depth;
+	P.counts = reinterpret_cast<unsigned long long *>(counts);
+
+	const long long grid = (long long) my_tiles * P.ctas_per_tile;
+	const bool      exact = opt->filter == VKV_FILTER_EXACT;
+#define VKV_RC(SK)                                                                  \
+	do {                                                                            \
+		if (exact) raycast_kernel<SK, true><<<(unsigned) grid, 128, 0, s>>>(P);      \
+		else raycast_kernel<SK, false><<<(unsigned) grid, 128, 0, s>>>(P);           \
+	} while (0)
+	switch (opt->skipping_type) {
+		case VKV_SKIP_NONE: VKV_RC(VKV_SKIP_NONE); break;
+		case VKV_SKIP_BLOCK: VKV_RC(VKV_SKIP_BLOCK); break;
+		case VKV_SKIP_DISTANCE: VKV_RC(VKV_SKIP_DISTANCE); break;
+		default: VKV_RC(VKV_SKIP_ANISOTROPIC_DISTANCE); break;
+	}
+#undef VKV_RC
+	VKV_LAUNCHED();
+	return VKV_OK;
+}
+
+}        // namespace vkv
