@@ -1014,3 +1014,121 @@ void orc_render(const uint8_t *V, const uint8_t *G, const uint8_t *tf, const uin
 		counts->covered_pixels += ncov;
 	}
 }
+
+/* ------------------------------------------------------------------------- */
+/* Synthetic inputs (NOT reference behaviour): CPU twin of vkv_synth_volume    */
+/* (vkvolume_b200/csrc/synth.cu) so the reference arm of bench.py can build the */
+/* same workload without touching the GPU.                                      */
+/* ------------------------------------------------------------------------- */
+typedef struct { float cx, cy, cz, ex, ey, ez, r, amp; } synth_prim;
+
+static uint64_t splitmix64(uint64_t *x)
+{
+	uint64_t z = (*x += 0x9E3779B97F4A7C15ull);
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	return z ^ (z >> 31);
+}
+static inline uint32_t hash3(uint32_t x, uint32_t y, uint32_t z, uint32_t seed)
+{
+	uint32_t h = x * 0x8da6b343u ^ y * 0xd8163841u ^ z * 0xcb1ab31fu ^ seed;
+	h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+	return h;
+}
+static inline float capsule_dist2(float px, float py, float pz, const synth_prim *c)
+{
+	float bx = c->ex - c->cx, by = c->ey - c->cy, bz = c->ez - c->cz;
+	float ax = px - c->cx, ay = py - c->cy, az = pz - c->cz;
+	float t  = (ax * bx + ay * by + az * bz) / fmaxf(bx * bx + by * by + bz * bz, 1e-12f);
+	t        = fminf(fmaxf(t, 0.0f), 1.0f);
+	float dx = ax - t * bx, dy = ay - t * by, dz = az - t * bz;
+	return dx * dx + dy * dy + dz * dz;
+}
+
+int orc_synth_volume(int kind, uint64_t seed, uint32_t W, uint32_t H, uint32_t D, uint8_t *out)
+{
+	if (kind < 0 || kind > 3) return -1;
+	synth_prim prims[64];
+	int        n_prims;
+	uint32_t   m = W > H ? W : H;
+	if (D > m) m = D;
+	float mx = (float) m, inv_max = 1.0f / mx;
+	float ext[3] = {W / mx, H / mx, D / mx};
+	uint64_t st = seed;
+#define RND() ((float) ((splitmix64(&st) >> 40) * (1.0 / 16777216.0)))
+	uint32_t seed_lo = (uint32_t) splitmix64(&st);
+	uint32_t seed_hi = (uint32_t) splitmix64(&st);
+	memset(prims, 0, sizeof prims);
+	if (kind == 0 || kind == 3) {
+		n_prims = 64;
+		for (int i = 0; i < 64; ++i) {
+			synth_prim *b = &prims[i];
+			b->cx = RND() * ext[0]; b->cy = RND() * ext[1]; b->cz = RND() * ext[2];
+			b->r   = kind == 0 ? (6.0f + 18.0f * RND()) / 256.0f : (0.006f + 0.02f * RND());
+			b->amp = 64.0f + 191.0f * RND();
+		}
+	} else if (kind == 1) {
+		n_prims = 7;
+		synth_prim *e = &prims[0];
+		e->cx = 0.5f * ext[0]; e->cy = 0.5f * ext[1]; e->cz = 0.5f * ext[2];
+		e->ex = 0.30f * ext[0]; e->ey = 0.22f * ext[1]; e->ez = 0.36f * ext[2];
+		e->r = 0.02f; e->amp = 200.0f;
+		for (int i = 1; i < 7; ++i) {
+			synth_prim *c = &prims[i];
+			float side = (i & 1) ? 1.0f : -1.0f, along = ((i - 1) / 2 - 1) * 0.18f;
+			c->cx = e->cx + side * 0.25f * ext[0]; c->cy = e->cy + 0.1f * ext[1]; c->cz = e->cz + along * ext[2];
+			c->ex = e->cx + side * (0.42f + 0.04f * RND()) * ext[0]; c->ey = e->cy + (0.30f + 0.1f * RND()) * ext[1];
+			c->ez = c->cz + (RND() - 0.5f) * 0.1f;
+			c->r = 0.012f; c->amp = 170.0f;
+		}
+	} else {
+		n_prims = 24;
+		for (int i = 0; i < 24; ++i) {
+			synth_prim *c = &prims[i];
+			c->cx = RND() * ext[0]; c->cy = RND() * ext[1]; c->cz = RND() * ext[2];
+			c->ex = c->cx + (RND() - 0.5f) * 0.6f; c->ey = c->cy + (RND() - 0.5f) * 0.6f; c->ez = c->cz + (RND() - 0.5f) * 0.6f;
+			c->r   = 0.006f + 0.006f * RND();
+			c->amp = 150.0f + 100.0f * RND();
+		}
+	}
+#undef RND
+#pragma omp parallel for schedule(static)
+	for (long long z = 0; z < (long long) D; ++z)
+		for (uint32_t y = 0; y < H; ++y)
+			for (uint32_t x = 0; x < W; ++x) {
+				float    px = (x + 0.5f) * inv_max, py = (y + 0.5f) * inv_max, pz = ((uint32_t) z + 0.5f) * inv_max;
+				uint32_t h  = hash3(x, y, (uint32_t) z, seed_lo);
+				float    v  = 0.0f;
+				if (kind == 0 || kind == 3) {
+					for (int i = 0; i < n_prims; ++i) {
+						const synth_prim *b = &prims[i];
+						float dx = px - b->cx, dy = py - b->cy, dz = pz - b->cz;
+						float d2 = dx * dx + dy * dy + dz * dz, s2 = b->r * b->r;
+						if (d2 < 9.0f * s2) v += b->amp * expf(-0.5f * d2 / s2);
+					}
+					if (kind == 3) v *= 0.5f + 0.5f * ((hash3(x >> 2, y >> 2, (uint32_t) z >> 2, seed_hi) & 0xffffu) * (1.0f / 65535.0f));
+					v += (float) (h & 7u) - 4.0f + 4.0f;
+				} else if (kind == 1) {
+					const synth_prim *e = &prims[0];
+					float qx = (px - e->cx) / e->ex, qy = (py - e->cy) / e->ey, qz = (pz - e->cz) / e->ez;
+					float rr = sqrtf(qx * qx + qy * qy + qz * qz);
+					float sh = fabsf(rr - 1.0f) * fminf(e->ex, fminf(e->ey, e->ez));
+					if (sh < e->r) v = e->amp * (1.0f - 0.6f * sh / e->r);
+					for (int i = 1; i < n_prims; ++i) {
+						const synth_prim *c = &prims[i];
+						float d2 = capsule_dist2(px, py, pz, c);
+						if (d2 < c->r * c->r) v = fmaxf(v, c->amp * (1.0f - 0.5f * d2 / (c->r * c->r)));
+					}
+					v += (float) (h % 13u);
+				} else {
+					for (int i = 0; i < n_prims; ++i) {
+						const synth_prim *c = &prims[i];
+						float d2 = capsule_dist2(px, py, pz, c);
+						if (d2 < c->r * c->r) v = fmaxf(v, c->amp * (1.0f - 0.5f * d2 / (c->r * c->r)));
+					}
+					v += (float) (h % 9u);
+				}
+				out[((size_t) z * H + y) * W + x] = (uint8_t) fminf(fmaxf(v, 0.0f), 255.0f);
+			}
+	return 0;
+}

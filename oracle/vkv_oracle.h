@@ -67,6 +67,8 @@ void orc_render(const uint8_t *V, const uint8_t *G, const uint8_t *tf_rgba, cons
                 const vkv_render_options *opt, int precomputed_gradient, int width, int height, int y_first,
                 int y_count, uint8_t *rgba8, float *rgba_float_or_null, float *depth_or_null,
                 vkv_sample_counts *counts_or_null);
+/* synthetic inputs (CPU twin of vkv_synth_volume; not reference behaviour) */
+int orc_synth_volume(int kind, uint64_t seed, uint32_t W, uint32_t H, uint32_t D, uint8_t *out);
 int orc_num_threads(void);
 void orc_set_num_threads(int n);
 

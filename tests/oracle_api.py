@@ -181,3 +181,13 @@ def render(V, G, tf_rgba, maps, dim_b_whd, cu, ru, tfu, opt: RenderOptions, widt
                      rgba.ctypes.data_as(_P), rf.ctypes.data_as(_P) if want_float else None,
                      dp.ctypes.data_as(_P) if want_depth else None, C.byref(counts))
     return rgba, counts, rf, dp
+
+
+def synth_volume(kind: int, seed: int, width: int, height: int, depth: int) -> np.ndarray:
+    """CPU twin of capi.synth_volume (synthetic bench inputs; not reference behaviour)."""
+    out = np.empty((depth, height, width), dtype=np.uint8)
+    rc = lib().orc_synth_volume(C.c_int(kind), C.c_uint64(seed), C.c_uint32(width), C.c_uint32(height), C.c_uint32(depth),
+                                out.ctypes.data_as(_P))
+    if rc != 0:
+        raise ValueError("bad synthetic volume kind")
+    return out

@@ -1,0 +1,339 @@
+"""GPU parity tests (pytest -m gpu): every CUDA stage, called through the C ABI (libvkv.so via
+vkvolume_b200.capi), against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north star): occupancy maps, voxel counts and distance maps bit-exact;
+gradient within 1e-5 relative (we additionally require byte-exact); frames within 1/255 per
+channel on >= 99.9 % of pixels and PSNR >= 50 dB.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import oracle_api as orc
+from vkvolume_b200 import capi, scene
+from vkvolume_b200.capi import (FILTER_EXACT, FILTER_HARDWARE, RenderOptions, SampleCounts, VolumeOptions,
+                                SKIP_ANISOTROPIC_DISTANCE, SKIP_BLOCK, SKIP_DISTANCE, SKIP_NONE,
+                                TEST_NUM_TEXTURE_SAMPLES, TEST_RAY_ENTRY, TEST_RAY_EXIT)
+
+pytestmark = pytest.mark.gpu
+
+TF_SETS = [
+    dict(intensity_min=0.1, intensity_max=1.0, gradient_min=0.0, gradient_max=0.2),
+    dict(intensity_min=0.086, intensity_max=1.0, gradient_min=0.0, gradient_max=0.0),
+    dict(intensity_min=0.4, intensity_max=0.8, gradient_min=0.06, gradient_max=0.12),
+    dict(intensity_min=0.0, intensity_max=1.0, gradient_min=0.1, gradient_max=0.3),
+]
+
+
+def psnr(a, b):
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    return 99.0 if mse == 0 else 10 * math.log10(255.0 ** 2 / mse)
+
+
+def frame_bar(img, ref):
+    """north-star frame tolerance on RGB (the reference's only export path forces alpha to 255)."""
+    d = np.abs(img[..., :3].astype(int) - ref[..., :3].astype(int)).max(axis=2)
+    return float((d <= 1).mean()), psnr(img[..., :3], ref[..., :3])
+
+
+# ---- transfer function --------------------------------------------------------------------------
+@pytest.mark.parametrize("o", TF_SETS)
+def test_tf_texture_bit_exact(ctx, o):
+    vol = capi.Volume(ctx, 16, 16, 16)
+    opt = VolumeOptions(**o)
+    vol.update_transfer_function_texture(opt)
+    assert np.array_equal(vol.download_transfer_function(), orc.transfer_function_texture(opt))
+    u_gpu, u_cpu = capi.transfer_function_uniform(opt), orc.transfer_function_uniform(opt)
+    assert bytes(u_gpu) == bytes(u_cpu)
+    vol.close()
+
+
+# ---- loader ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("type_name,dtype", [("uint8_t", np.uint8), ("int8_t", np.int8), ("uint16_t", np.uint16), ("int16_t", np.int16)])
+@pytest.mark.parametrize("endian", ["little", "big"])
+def test_loader_normalise_bit_exact(ctx, tmp_path, type_name, dtype, endian):
+    W, H, D = 21, 10, 7
+    rng = np.random.default_rng(11)
+    info = np.iinfo(dtype)
+    v = rng.integers(info.min, info.max + 1, size=W * H * D).astype(dtype)
+    raw = v.astype(v.dtype.newbyteorder(">" if endian == "big" else "<"))
+    lo, hi = (400.0, 2538.0) if dtype in (np.uint16, np.int16) else (10.0, 200.0)
+    want = orc.normalise(raw.view(np.uint8), v.size, type_name, endian, lo, hi)
+    # device path fused with the upload
+    vol = capi.Volume(ctx, W, H, D)
+    vol.upload_raw(raw.view(np.uint8), type_name, endian, lo, hi)
+    assert np.array_equal(vol.download_voxels().ravel(), want)
+    vol.close()
+    # file path: header + raw file, LoadVolume::load_header / load_data
+    fn = tmp_path / "vol.raw"
+    raw.tofile(fn)
+    (tmp_path / "vol.raw.header").write_text(
+        f"{W} {H} {D} # extents\n0.004 0.004 0.008 # voxel size\n{lo} {hi} # normalisation\n{type_name} {endian} # type\n0 1 0 30 # rotation\n")
+    h = capi.load_header(str(fn) + ".header")
+    assert tuple(h.extent) == (W, H, D) and h.type.decode() == type_name
+    ho = orc.parse_header((tmp_path / "vol.raw.header").read_text())
+    assert np.allclose(list(h.image_transform), list(ho.image_transform), rtol=1e-6, atol=1e-7)
+    assert np.array_equal(capi.load_data(str(fn), h).ravel(), want)
+
+
+def test_loader_errors(ctx, tmp_path):
+    with pytest.raises(capi.VkvError, match="Failed to open header file"):
+        capi.load_header(str(tmp_path / "nope.header"))
+    fn = tmp_path / "short.raw"
+    np.zeros(10, np.uint8).tofile(fn)
+    (tmp_path / "short.raw.header").write_text("4 4 4\n1 1 1\n0 255\nuint8_t little\n1 0 0 0\n")
+    h = capi.load_header(str(fn) + ".header")
+    with pytest.raises(capi.VkvError, match="File size does not match"):
+        capi.load_data(str(fn), h)
+    (tmp_path / "bad.raw.header").write_text("4 4 4\n1 1 1\n0 255\nfloat little\n1 0 0 0\n")
+    hb = capi.load_header(str(tmp_path / "bad.raw.header"))
+    with pytest.raises(capi.VkvError, match="unsupported image data type"):
+        capi.load_data(str(fn), hb)
+
+
+# ---- K1 gradient ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(17, 17, 17), (9, 12, 32), (20, 33, 48), (5, 6, 16), (3, 4, 130), (1, 1, 16), (40, 40, 64)])
+def test_gradient_byte_exact(ctx, shape):
+    D, H, W = shape
+    V = np.random.default_rng(sum(shape)).integers(0, 256, size=shape, dtype=np.uint8)
+    if shape == (40, 40, 64):
+        V = scene.blobs_volume(shape, seed=4)
+    vol = capi.Volume(ctx, W, H, D)
+    vol.upload(V)
+    opt = VolumeOptions(gradient_min=0.0, gradient_max=0.2)
+    vol.compute_gradient_map(capi.transfer_function_uniform(opt))
+    G = vol.download_gradient()
+    assert np.array_equal(G, orc.gradient_map(V))
+    # use_gradient false at gradient time -> all 255 (quirk A.8.1)
+    vol.compute_gradient_map(capi.transfer_function_uniform(VolumeOptions(gradient_min=0.0, gradient_max=0.0)))
+    assert (vol.download_gradient() == 255).all()
+    vol.close()
+
+
+# ---- K2a / K2b -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,bs", [((16, 16, 32), 4), ((9, 10, 13), 4), ((24, 20, 48), 4), ((12, 12, 32), 2), ((16, 24, 64), 8),
+                                      ((7, 9, 10), 3), ((15, 11, 48), 5), ((10, 10, 10), 1), ((6, 6, 6), 8), ((33, 17, 80), 4),
+                                      ((8, 8, 1040), 3)])
+@pytest.mark.parametrize("o", TF_SETS)
+def test_occupancy_and_count_bit_exact(ctx, shape, bs, o):
+    D, H, W = shape
+    V = scene.blobs_volume(shape, seed=sum(shape) + bs, n_blobs=5)
+    opt = VolumeOptions(**o)
+    tfu = capi.transfer_function_uniform(opt)
+    G = orc.gradient_map(V, True)        # always feed the oracle's G
+    vol = capi.Volume(ctx, W, H, D, block_size=bs)
+    vol.upload(V)
+    vol.upload_gradient(G)
+    vol.update_transfer_function_texture(opt)
+    tf = orc.transfer_function_texture(opt)
+    want_O = orc.occupancy_map(V, G, tf, bs, bool(tfu.use_gradient))
+    assert vol.map_extent == want_O.shape[::-1]
+    vol.compute_distance_map(tfu, SKIP_BLOCK)        # occupancy only
+    assert np.array_equal(vol.download_distance_map(0), want_O)
+    want_n = orc.occupied_voxel_count(V, G, tfu)
+    assert vol.compute_occupied_voxel_count(tfu) == want_n
+    # fused TF-change path gives the same map and count
+    n = vol.update_transfer_function(opt, SKIP_BLOCK, count=True)
+    assert n == want_n and np.array_equal(vol.download_distance_map(0), want_O)
+    vol.close()
+
+
+def test_occupancy_arbitrary_texture(ctx):
+    """A host-supplied TF texture (not a grey ramp): occupancy follows the texture's alpha plane."""
+    shape = (16, 20, 32)
+    D, H, W = shape
+    V = np.random.default_rng(5).integers(0, 256, size=shape, dtype=np.uint8)
+    G = np.random.default_rng(6).integers(0, 256, size=shape, dtype=np.uint8)
+    tf = np.zeros((256, 256, 4), np.uint8)
+    rng = np.random.default_rng(7)
+    tf[..., 3] = np.where(rng.random((256, 256)) < 0.002, rng.integers(1, 256, (256, 256)), 0)
+    tf[..., :3] = rng.integers(0, 256, (256, 256, 3))
+    vol = capi.Volume(ctx, W, H, D)
+    vol.upload(V)
+    vol.upload_gradient(G)
+    vol.set_transfer_function_texture(tf)
+    tfu = capi.transfer_function_uniform(VolumeOptions(gradient_min=0.0, gradient_max=0.5))
+    vol.compute_distance_map(tfu, SKIP_BLOCK)
+    assert np.array_equal(vol.download_distance_map(0), orc.occupancy_map(V, G, tf, 4, True))
+    vol.close()
+
+
+# ---- K3 distance maps ---------------------------------------------------------------------------------------
+def _volume_with_occupancy(ctx, O):
+    """Builds a volume whose occupancy map equals O (1 voxel = 1 block) so K3 can be driven in isolation."""
+    Db, Hb, Wb = O.shape
+    vol = capi.Volume(ctx, Wb, Hb, Db, block_size=1)
+    vol.upload(np.where(O == 0, 255, 0).astype(np.uint8))
+    opt = VolumeOptions(intensity_min=0.5, intensity_max=1.0, gradient_min=0.0, gradient_max=0.0)
+    vol.update_transfer_function_texture(opt)
+    return vol, capi.transfer_function_uniform(opt)
+
+
+@pytest.mark.parametrize("shape,p", [((8, 9, 10), 0.05), ((16, 12, 20), 0.01), ((5, 24, 7), 0.1), ((1, 1, 30), 0.1), ((3, 1, 1), 0.5),
+                                     ((20, 40, 70), 0.002), ((33, 65, 129), 0.0005), ((4, 4, 300), 0.003), ((300, 3, 5), 0.003),
+                                     ((2, 1100, 3), 0.002), ((6, 6, 6), 0.0)])
+def test_distance_maps_bit_exact(ctx, shape, p):
+    rng = np.random.default_rng(abs(hash(shape)) % 1000)
+    O = np.where(rng.random(shape) < p, 0, 255).astype(np.uint8)
+    vol, tfu = _volume_with_occupancy(ctx, O)
+    vol.compute_distance_map(tfu, SKIP_BLOCK)
+    assert np.array_equal(vol.download_distance_map(0), O)
+    vol.compute_distance_map(tfu, SKIP_DISTANCE)
+    assert np.array_equal(vol.download_distance_map(0), orc.distance_map(O))
+    vol.compute_distance_map(tfu, SKIP_ANISOTROPIC_DISTANCE)
+    assert vol.map_extent == O.shape[::-1]
+    want = orc.distance_map_anisotropic(O)
+    for i in range(8):
+        assert np.array_equal(vol.download_distance_map(i), want[i]), f"octant map {i}"
+    vol.close()
+
+
+# ---- K4 ray caster ----------------------------------------------------------------------------------------------
+def _render_case(ctx, shape, opt, eye, clip, skip, width, height, voxel_size=(0.004, 0.004, 0.004), axis_angle=(1, 0, 0, 0),
+                 ert=1, test=0, bs=4, filt=FILTER_EXACT, seed=1):
+    D, H, W = shape
+    V = scene.blobs_volume(shape, seed=seed)
+    tfu = capi.transfer_function_uniform(opt)
+    G = orc.gradient_map(V, bool(tfu.use_gradient))
+    tf = orc.transfer_function_texture(opt)
+    O = orc.occupancy_map(V, G, tf, bs, bool(tfu.use_gradient))
+    maps = None
+    if skip == SKIP_BLOCK:
+        maps = O
+    elif skip == SKIP_DISTANCE:
+        maps = orc.distance_map(O)
+    elif skip == SKIP_ANISOTROPIC_DISTANCE:
+        maps = orc.distance_map_anisotropic(O)
+    vol = capi.Volume(ctx, W, H, D, block_size=bs)
+    vol.upload(V)
+    vol.upload_gradient(G)
+    vol.update_transfer_function_texture(opt)
+    vol.compute_distance_map(tfu, skip)
+    it = scene.image_transform(voxel_size, (W, H, D), axis_angle)
+    cam = scene.look_at_camera(eye, aspect=width / height)
+    cu, ru = vol.make_uniforms(cam, it, clip)
+    ropt = RenderOptions(skipping_type=skip, clip_distance=clip, early_ray_termination=ert, test=test, filter=filt)
+    img, counts = vol.render_to_host(cu, ru, tfu, ropt, width, height)
+    ref, rcounts, rf, _ = orc.render(V, G, tf, maps, vol.map_extent, cu, ru, tfu, ropt, width, height, want_float=True)
+    vol.close()
+    return img, counts, ref, rcounts, rf
+
+
+@pytest.mark.parametrize("skip", [SKIP_NONE, SKIP_BLOCK, SKIP_DISTANCE, SKIP_ANISOTROPIC_DISTANCE])
+@pytest.mark.parametrize("o", TF_SETS[:3])
+def test_render_exact_filter_matches_oracle(ctx, skip, o):
+    img, counts, ref, rcounts, _ = _render_case(ctx, (48, 64, 80), VolumeOptions(**o), (34, 22, 50), 5.0, skip, 160, 128)
+    frac, p = frame_bar(img, ref)
+    assert frac >= 0.999 and p >= 50.0, (frac, p)
+    assert counts.covered_pixels == rcounts.covered_pixels
+    # sample counters agree to within the handful of pixels whose step count flips by rounding
+    tot, rtot = counts.volume_samples + counts.distance_samples, rcounts.volume_samples + rcounts.distance_samples
+    assert abs(tot - rtot) <= 1e-3 * rtot + 8
+    assert np.array_equal(img[..., 3] == 255, ref[..., 3] == 255)        # coverage mask via the clear alpha
+
+
+@pytest.mark.parametrize("skip", [SKIP_NONE, SKIP_DISTANCE, SKIP_ANISOTROPIC_DISTANCE])
+def test_render_hardware_filter_within_frame_bar(ctx, skip):
+    o = TF_SETS[0]
+    img, counts, ref, rcounts, _ = _render_case(ctx, (48, 64, 80), VolumeOptions(**o), (34, 22, 50), 5.0, skip, 160, 128,
+                                                filt=FILTER_HARDWARE)
+    frac, p = frame_bar(img, ref)
+    assert frac >= 0.999 and p >= 50.0, (frac, p)
+
+
+def test_render_camera_inside_with_clip_plane_anisotropic_voxels(ctx):
+    """Config-3 shaped case: anisotropic voxels, rotated volume, camera inside the box, clip polygon on screen."""
+    opt = VolumeOptions(**TF_SETS[0])
+    img, counts, ref, rcounts, rf = _render_case(ctx, (40, 64, 64), opt, (3, 2, 6), 4.0, SKIP_ANISOTROPIC_DISTANCE, 128, 96,
+                                                 voxel_size=(0.003, 0.003, 0.007), axis_angle=(1, 0, 0, 90))
+    assert rcounts.covered_pixels == 128 * 96        # inside the box: every pixel enters through the clip polygon
+    frac, p = frame_bar(img, ref)
+    assert frac >= 0.999 and p >= 50.0, (frac, p)
+    assert counts.covered_pixels == rcounts.covered_pixels
+
+
+@pytest.mark.parametrize("test_mode", [TEST_RAY_ENTRY, TEST_RAY_EXIT, TEST_NUM_TEXTURE_SAMPLES])
+def test_render_debug_views(ctx, test_mode):
+    img, counts, ref, rcounts, _ = _render_case(ctx, (48, 64, 80), VolumeOptions(**TF_SETS[0]), (34, 22, 50), 5.0, SKIP_DISTANCE,
+                                                128, 128, ert=0, test=test_mode)
+    frac, p = frame_bar(img, ref)
+    assert frac >= 0.999 and p >= 50.0, (frac, p)
+
+
+def test_render_sampling_factor_and_alpha_factor(ctx):
+    opt = VolumeOptions(sampling_factor=2.0, voxel_alpha_factor=1.5, **TF_SETS[1])
+    img, counts, ref, rcounts, _ = _render_case(ctx, (48, 64, 80), opt, (34, 22, 50), 5.0, SKIP_DISTANCE, 128, 128)
+    frac, p = frame_bar(img, ref)
+    assert frac >= 0.999 and p >= 50.0, (frac, p)
+
+
+def test_render_tiles_equal_full_frame(ctx):
+    """Image-tile sharding: rendering tile subsets (as ranks would) reassembles the full frame byte for byte."""
+    import torch
+    shape = (48, 64, 80)
+    D, H, W = shape
+    V = scene.blobs_volume(shape, seed=1)
+    opt = VolumeOptions(**TF_SETS[0])
+    tfu = capi.transfer_function_uniform(opt)
+    vol = capi.Volume(ctx, W, H, D)
+    vol.upload(V)
+    vol.compute_gradient_map(tfu)
+    vol.update_transfer_function(opt, SKIP_DISTANCE)
+    it = scene.image_transform((0.004,) * 3, (W, H, D))
+    width, height = 200, 120
+    cu, ru = vol.make_uniforms(scene.look_at_camera((34, 22, 50), aspect=width / height), it, 5.0)
+    ropt = RenderOptions(skipping_type=SKIP_DISTANCE, clip_distance=5.0)
+    full = torch.zeros((height, width, 4), dtype=torch.uint8, device="cuda")
+    vol.render(cu, ru, tfu, ropt, width, height, full.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+    parts = torch.zeros_like(full)
+    for rank in range(3):
+        vol.render_tiles(cu, ru, tfu, ropt, width, height, 32, 16, rank, 3, parts.data_ptr(),
+                         stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(full, parts)
+    vol.close()
+
+
+# ---- end to end at BASELINE size: size-independent properties ---------------------------------------------------------------
+def test_full_size_properties_config2(ctx):
+    """832x832x494 synthetic beetle (config 2 size): properties that need no CPU pass over the full volume."""
+    import torch
+    W, H, D = 832, 832, 494
+    vol = capi.Volume(ctx, W, H, D)
+    capi.synth_volume(ctx, 1, 0x5EED0002, W, H, D, vol.device_voxels())
+    vol.upload_device(vol.device_voxels())
+    opt = VolumeOptions(intensity_min=0.086, intensity_max=1.0, gradient_min=0.0, gradient_max=0.0)
+    tfu = capi.transfer_function_uniform(opt)
+    vol.compute_gradient_map(tfu)
+    n = vol.update_transfer_function(opt, SKIP_ANISOTROPIC_DISTANCE, count=True)
+    maps = np.stack([vol.download_distance_map(i) for i in range(8)])
+    vol.update_transfer_function(opt, SKIP_DISTANCE)
+    iso = vol.download_distance_map(0)
+    vol.update_transfer_function(opt, SKIP_BLOCK)
+    O = vol.download_distance_map(0)
+    # (1) isotropic map == min over the 8 octant maps; zero exactly on occupied blocks
+    assert np.array_equal(iso, maps.min(axis=0))
+    assert np.array_equal(iso == 0, O == 0)
+    # (2) 1-Lipschitz in every axis (a Chebyshev distance field), saturating at 255
+    for ax in range(3):
+        d = np.abs(np.diff(iso.astype(np.int16), axis=ax))
+        assert d.max() <= 1
+    # (3) the count is a checksum of the occupancy: every counted voxel lies in an occupied block for this TF
+    #     (no gradient, so analytic alpha > 0 <=> V >= 22 while texture alpha > 0 <=> V >= 23)
+    Vh = vol.download_voxels()
+    assert n == int((Vh.astype(np.float32) / np.float32(255) > np.float32(0.086)).sum())
+    # effective block size is 4 in x,y; z: ceil(494/124) = 4 with a 2-voxel last block
+    Ob = np.zeros(iso.shape, bool)
+    vis = Vh >= 23
+    for z in range(iso.shape[0]):
+        Ob[z] = vis[z * 4:(z + 1) * 4].any(axis=0).reshape(H // 4, 4, W // 4, 4).any(axis=(1, 3))
+    assert np.array_equal(O == 0, Ob)
+    # (4) a crop of the full-size result equals the oracle run on the crop's own closed form neighbourhood
+    sub = O[40:56, 60:84, 70:100]
+    if (sub == 0).any():
+        crop = iso[40:56, 60:84, 70:100]
+        loc = orc.distance_map(sub)
+        assert (crop <= loc).all()        # more occupied blocks outside the crop can only shorten distances
+    vol.close()
