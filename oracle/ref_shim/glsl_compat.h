@@ -65,6 +65,7 @@ template <class T> struct vec<T, 3> {
 	template <class U, int N, int A, int B, int C> vec(const swz3<U, N, A, B, C> &s) : d{T(s.d[A]), T(s.d[B]), T(s.d[C])} {}
 	vec(const vec &o) { for (int i = 0; i < 3; ++i) d[i] = o.d[i]; }
 	vec &operator=(const vec &o) { for (int i = 0; i < 3; ++i) d[i] = o.d[i]; return *this; }
+	template <class S, class = typename std::enable_if<std::is_arithmetic<S>::value>::type> explicit operator S() const { return S(d[0]); }        // GLSL: scalar constructor takes the first component
 	T &operator[](int i) { return d[i]; }
 	const T &operator[](int i) const { return d[i]; }
 };

@@ -10,14 +10,15 @@
  * Built with -ffp-contract=off so every fp32 operation rounds exactly once, in the
  * order written.
  *
- * Parity status: the reference ships no tests or golden vectors for this path
- * (SURVEY.md §4).  The restatement is pinned against the reference's OWN sources
- * executed on the CPU by oracle/ref_shim (the GLSL shaders compiled as C++ through a
- * small GLSL-compatibility header, load_volume.cpp compiled as-is, glm for the host
- * maths) — see oracle/README.md and tests/test_oracle_vs_ref_shim.py.  What cannot be
- * pinned here (no Vulkan driver in this image): the fixed-function stages — rasteriser
- * coverage, sampler filtering precision, blending and sRGB store — which follow the
- * Vulkan specification's formulas.
+ * Parity status: PINNED against the reference's own sources.  The reference ships no tests
+ * or golden vectors for this path and its application cannot be built here,
+ * but its ten GLSL shaders (compiled as C++ through oracle/ref_shim), src/load_volume.cpp
+ * (as is) and its glm host maths can be, and are, executed on the CPU: oracle/_ref.  Their
+ * outputs on seeded cases are committed as tests/golden/reference_outputs.npz and
+ * tests/test_oracle_vs_reference.py holds this restatement to them (bit-exact for the
+ * integer stages).  Not pinnable here (no Vulkan driver in this image): fixed-function
+ * rasteriser coverage, sampler weight precision, blending and the sRGB store, which follow
+ * the Vulkan specification's formulas.  See oracle/README.md.
  */
 #ifndef VKV_ORACLE_H
 #define VKV_ORACLE_H
