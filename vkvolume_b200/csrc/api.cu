@@ -166,6 +166,7 @@ void vkv_volume_destroy(vkv_volume *vol)
 	for (auto *m : vol->d_maps) cudaFree(m);
 	cudaFree(vol->d_swap); cudaFree(vol->d_tmp); cudaFree(vol->d_count); cudaFree(vol->d_counts_scratch);
 	cudaFree(vol->d_fb_scratch);
+	cudaFree(vol->d_acorr);
 	if (vol->h_count) cudaFreeHost(vol->h_count);
 	delete vol;
 }
@@ -438,6 +439,7 @@ int vkv_render_to_host(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv
 	const size_t bytes = (size_t) width * height * 4;
 	if (vol->fb_scratch_bytes < bytes) {
 		cudaFree(vol->d_fb_scratch);
+	cudaFree(vol->d_acorr);
 		vol->d_fb_scratch     = nullptr;
 		vol->fb_scratch_bytes = 0;
 		VKV_CUDA_CHECK(cudaMalloc(&vol->d_fb_scratch, bytes));

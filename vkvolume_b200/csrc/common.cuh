@@ -100,7 +100,8 @@ struct vkv_volume {
 	vkv_sample_counts  *d_counts_scratch = nullptr;
 	uint8_t            *d_fb_scratch = nullptr;        // framebuffer for vkv_render_to_host
 	size_t              fb_scratch_bytes = 0;
-	uint8_t            *h_fb_scratch = nullptr;        // unused unless caller memory is pageable
+	float              *d_acorr = nullptr;             // ray caster: opacity-correction table + the key it was built for
+	float               acorr_sampling = -1.0f, acorr_alpha = -1.0f;
 };
 
 namespace vkv {

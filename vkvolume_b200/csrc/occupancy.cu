@@ -25,11 +25,24 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
 	return r;
 }
 
-// Per-byte a >= b / a <= b masks (0xff per byte).
-__device__ __forceinline__ unsigned in_range4(unsigned a, unsigned lo4, unsigned hi4)
-{
-	return __vcmpgeu4(a, lo4) & __vcmpleu4(a, hi4);
-}
+// SWAR byte-range prefilter: bit 7 of every byte of the result is set iff lo <= byte <= hi.
+// "byte >= lo" needs one AND, one ADD and one LOP3 per 4 voxels (no per-byte video instructions):
+//   lo <= 128: the byte passes if its top bit is set or its low 7 bits reach lo        -> ((x & 0x7f..) + (128-lo)) | x
+//   lo >  128: the byte passes if its top bit is set and its low 7 bits reach lo - 128 -> ((x & 0x7f..) + (256-lo)) & x
+// "byte <= hi" is the same test on ~x with lo' = 255 - hi.
+struct ByteGE {
+	unsigned add, or_sel;        // or_sel = ~0 selects the OR form
+	__device__ __forceinline__ void set(unsigned lo)
+	{
+		or_sel = lo <= 128u ? 0xffffffffu : 0u;
+		add    = (lo <= 128u ? 128u - lo : 256u - lo) * 0x01010101u;
+	}
+	__device__ __forceinline__ unsigned test(unsigned x) const
+	{
+		const unsigned m = (x & 0x7f7f7f7fu) + add;
+		return (m & x) | ((m | x) & or_sel);        // caller masks with 0x80808080
+	}
+};
 
 // Looks up the 4 voxels of word (v,g); returns occupancy hit in bit 0 and the
 // number of analytically visible voxels in bits 8.. .
@@ -39,7 +52,7 @@ __device__ __forceinline__ void classify_word(unsigned v, unsigned g, unsigned c
 {
 #pragma unroll
 	for (int b = 0; b < 4; ++b) {
-		if ((cand >> (8 * b)) & 1u) {
+		if ((cand >> (8 * b + 7)) & 1u) {
 			const unsigned vb  = (v >> (8 * b)) & 0xffu;
 			const unsigned gb  = USE_G ? ((g >> (8 * b)) & 0xffu) : 255u;
 			const uint2    m   = s_mask[gb * 8 + (vb >> 5)];
@@ -67,20 +80,21 @@ __global__ void __launch_bounds__(256) occupancy_fast_kernel(const uint8_t *__re
 	const int      bsel = (USE_G ? 0 : 2) + (COUNT ? 1 : 0);
 	const unsigned vlo = bounds->v_lo[bsel], vhi = bounds->v_hi[bsel];
 	const unsigned glo = bounds->g_lo[bsel], ghi = bounds->g_hi[bsel];
-	const unsigned vlo4 = vlo * 0x01010101u, vhi4 = vhi * 0x01010101u, glo4 = glo * 0x01010101u, ghi4 = ghi * 0x01010101u;
 	const bool     none = vlo > vhi;        // nothing visible anywhere
+	ByteGE         v_ge, v_le, g_ge, g_le;
+	v_ge.set(vlo); v_le.set(255u - vhi); g_ge.set(glo); g_le.set(255u - ghi);
+	const bool need_vlo = vlo > 0u, need_vhi = vhi < 255u, need_glo = USE_G && glo > 0u, need_ghi = USE_G && ghi < 255u;
 	__syncthreads();
 
 	const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int      tx = lane % TX, ty = lane / TX;
 	const uint32_t xchunks = (W + XV - 1) / XV;
-	const uint64_t ntasks  = (uint64_t) xchunks * Hb * zb_count;
+	const uint32_t ntasks  = xchunks * Hb * zb_count;        // < 2^32 (checked by the launcher)
 	unsigned long long local_count = 0;
 
-	for (uint64_t task = (uint64_t) blockIdx.x * 8 + warp; task < ntasks; task += (uint64_t) gridDim.x * 8) {
-		const uint32_t xc = (uint32_t) (task % xchunks);
-		const uint64_t r  = task / xchunks;
-		const uint32_t by = (uint32_t) (r % Hb), bz = zb_first + (uint32_t) (r / Hb);
+	for (uint32_t task = blockIdx.x * 8 + warp; task < ntasks; task += gridDim.x * 8) {
+		const uint32_t r  = task / xchunks, xc = task - r * xchunks;
+		const uint32_t bq = r / Hb, by = r - bq * Hb, bz = zb_first + bq;
 		const uint32_t x = xc * XV + tx * 16, y = by * BS + ty;
 		const bool     in_xy = x < W && y < H;
 		uint4          vv[BS], gg[BS];
@@ -105,8 +119,11 @@ __global__ void __launch_bounds__(256) occupancy_fast_kernel(const uint8_t *__re
 				const unsigned gw[4] = {gg[zz].x, gg[zz].y, gg[zz].z, gg[zz].w};
 #pragma unroll
 				for (int k = 0; k < 4; ++k) {
-					unsigned cand = in_range4(vw[k], vlo4, vhi4);
-					if (USE_G) cand &= in_range4(gw[k], glo4, ghi4);
+					unsigned cand = 0x80808080u;
+					if (need_vlo) cand &= v_ge.test(vw[k]);
+					if (need_vhi) cand &= v_le.test(~vw[k]);
+					if (need_glo) cand &= g_ge.test(gw[k]);
+					if (need_ghi) cand &= g_le.test(~gw[k]);
 					if (valid && cand) {
 						if (BS >= 4) {
 							bool hit = false;
@@ -116,7 +133,7 @@ __global__ void __launch_bounds__(256) occupancy_fast_kernel(const uint8_t *__re
 #pragma unroll
 							for (int h = 0; h < 2; ++h) {
 								bool hit = false;
-								classify_word<USE_G, COUNT>(vw[k] >> (16 * h), gw[k] >> (16 * h), (cand >> (16 * h)) & 0xffffu, s_mask, hit, cnt);
+								classify_word<USE_G, COUNT>(vw[k] >> (16 * h), gw[k] >> (16 * h), (cand >> (16 * h)) & 0x8080u, s_mask, hit, cnt);
 								if (hit) flags |= 1u << (k * 2 + h);
 							}
 						}
@@ -215,18 +232,30 @@ __global__ void __launch_bounds__(256) occupancy_generic_kernel(const uint8_t *_
 	}
 }
 
+template <int BS, bool USE_G, bool COUNT>
+static int launch_fast_inst(vkv_volume *vol, uint8_t *O, uint32_t zb_first, uint32_t zb_count, unsigned long long *count_dev, cudaStream_t s)
+{
+	// persistent grid: exactly the number of CTAs that are resident at once (a multiple of the SM count)
+	static int per_sm = 0;
+	if (per_sm == 0) {
+		VKV_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, occupancy_fast_kernel<BS, USE_G, COUNT>, 256, 0));
+		if (per_sm < 1) per_sm = 1;
+	}
+	occupancy_fast_kernel<BS, USE_G, COUNT><<<vol->ctx->sm_count * per_sm, 256, 0, s>>>(vol->d_V, vol->d_G, vol->d_mask2, vol->d_bounds, vol->dim[0], vol->dim[1],
+	                                                                                    vol->dim[2], vol->dim_b[0], vol->dim_b[1], zb_first, zb_count, O, count_dev);
+	VKV_LAUNCHED();
+	return VKV_OK;
+}
+
 template <int BS>
 static int launch_fast(vkv_volume *vol, bool use_g, bool count, uint8_t *O, uint32_t zb_first, uint32_t zb_count,
                        unsigned long long *count_dev, int grid, cudaStream_t s)
 {
-#define VKV_OCC_ARGS vol->d_V, vol->d_G, vol->d_mask2, vol->d_bounds, vol->dim[0], vol->dim[1], vol->dim[2], vol->dim_b[0], vol->dim_b[1], zb_first, zb_count, O, count_dev
-	if (use_g && count) occupancy_fast_kernel<BS, true, true><<<grid, 256, 0, s>>>(VKV_OCC_ARGS);
-	else if (use_g) occupancy_fast_kernel<BS, true, false><<<grid, 256, 0, s>>>(VKV_OCC_ARGS);
-	else if (count) occupancy_fast_kernel<BS, false, true><<<grid, 256, 0, s>>>(VKV_OCC_ARGS);
-	else occupancy_fast_kernel<BS, false, false><<<grid, 256, 0, s>>>(VKV_OCC_ARGS);
-#undef VKV_OCC_ARGS
-	VKV_LAUNCHED();
-	return VKV_OK;
+	(void) grid;
+	if (use_g && count) return launch_fast_inst<BS, true, true>(vol, O, zb_first, zb_count, count_dev, s);
+	if (use_g) return launch_fast_inst<BS, true, false>(vol, O, zb_first, zb_count, count_dev, s);
+	if (count) return launch_fast_inst<BS, false, true>(vol, O, zb_first, zb_count, count_dev, s);
+	return launch_fast_inst<BS, false, false>(vol, O, zb_first, zb_count, count_dev, s);
 }
 
 int launch_occupancy(vkv_volume *vol, bool use_gradient, bool count, uint8_t *O, uint32_t zb_first, uint32_t zb_count,
@@ -237,7 +266,8 @@ int launch_occupancy(vkv_volume *vol, bool use_gradient, bool count, uint8_t *O,
 	const bool use_g = use_gradient;
 	const int  grid  = vol->ctx->sm_count * 8;        // persistent: 8 CTAs/SM x 256 threads = full occupancy
 	const bool cubic = vol->bs[0] == vol->bs[1] && vol->bs[1] == vol->bs[2];
-	const bool fast  = cubic && (vol->bs[0] == 2 || vol->bs[0] == 4 || vol->bs[0] == 8) && vol->dim[0] % 16 == 0 &&
+	const uint64_t fast_tasks = (uint64_t) ((vol->dim[0] + 63) / 64) * vol->dim_b[1] * zb_count;        // upper bound over BS
+	const bool fast  = fast_tasks < (1ull << 32) && cubic && (vol->bs[0] == 2 || vol->bs[0] == 4 || vol->bs[0] == 8) && vol->dim[0] % 16 == 0 &&
 	                  vol->dim_b[0] * vol->bs[0] == vol->dim[0] && (reinterpret_cast<uintptr_t>(vol->d_V) % 16 == 0);
 	if (fast) {
 		switch (vol->bs[0]) {

@@ -44,6 +44,7 @@ struct RayParams {
 	const uchar4  *tf;
 	const uint8_t *maps;            // map 0; map i at maps_stride * i (anisotropic)
 	const uint8_t *map_ptrs[8];
+	const float   *acorr;           // 256-entry opacity-correction table (built once per (sampling, alpha factor))
 	uint8_t       *rgba8;
 	float         *depth;
 	unsigned long long *counts;     // vkv_sample_counts or null
@@ -76,15 +77,21 @@ __device__ __forceinline__ float sample_exact(const uint8_t *__restrict__ T, con
 __device__ __forceinline__ float srgb_encode(float c) { return c <= 0.0031308f ? 12.92f * c : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f; }
 __device__ __forceinline__ unsigned unorm8(float c) { return (unsigned) (clampf_(c, 0.0f, 1.0f) * 255.0f + 0.5f); }
 
+
+// color.a = clamp(voxel_alpha_factor * (1 - pow(1 - a, 1/sampling_factor)), 0, 1) for the 256 possible TF alpha bytes
+// (volume_render.frag:283).  Built once per (sampling_factor, voxel_alpha_factor) and cached in the volume.
+__global__ void acorr_table_kernel(float *__restrict__ table, float voxel_alpha_factor, float sampling_factor_inv)
+{
+	const float a      = (float) threadIdx.x / 255.0f;
+	table[threadIdx.x] = clampf_(voxel_alpha_factor * (1.0f - powf(1.0f - a, sampling_factor_inv)), 0.0f, 1.0f);
+}
+
 template <int SKIP, bool EXACT>
 __global__ void __launch_bounds__(128) raycast_kernel(const __grid_constant__ RayParams P)
 {
 	__shared__ float s_acorr[256];        // opacity correction per TF alpha byte (volume_render.frag:283)
 	__shared__ unsigned long long s_cnt[4][4];
-	for (int k = threadIdx.x; k < 256; k += blockDim.x) {
-		const float a = (float) k / 255.0f;
-		s_acorr[k]    = clampf_(P.voxel_alpha_factor * (1.0f - powf(1.0f - a, P.sampling_factor_inv)), 0.0f, 1.0f);
-	}
+	for (int k = threadIdx.x; k < 256; k += blockDim.x) s_acorr[k] = __ldg(P.acorr + k);
 	__syncthreads();
 
 	// CTA -> tile -> pixel
@@ -105,31 +112,52 @@ __global__ void __launch_bounds__(128) raycast_kernel(const __grid_constant__ Ra
 
 	if (in_frame) {
 		// ---- analytic ray entry (replaces both vertex shaders + rasteriser) ----
-		double d[3], tn = -INFINITY, tf = INFINITY;
-		bool   hit = true;
+		// (1) conservative fp32 rejection: two thirds of a typical frame miss the box, skip the fp64 work there
+		bool maybe = true;
+		{
+			float tnf = -INFINITY, tff = INFINITY, sdf = 0.0f;
 #pragma unroll
-		for (int k = 0; k < 3; ++k) {
-			d[k] = P.d0[k] + (double) px * P.ddx[k] + (double) py * P.ddy[k];
-			if (d[k] == 0.0) {
-				if (P.o[k] < 0.0 || P.o[k] > 1.0) hit = false;
-			} else {
-				double t0 = (0.0 - P.o[k]) / d[k], t1 = (1.0 - P.o[k]) / d[k];
-				if (t0 > t1) { const double t = t0; t0 = t1; t1 = t; }
-				if (t0 > tn) tn = t0;
-				if (t1 < tf) tf = t1;
+			for (int k = 0; k < 3; ++k) {
+				const float dk = (float) P.d0[k] + (float) px * (float) P.ddx[k] + (float) py * (float) P.ddy[k];
+				const float ok = (float) P.o[k];
+				const float a0 = (0.0f - ok) / dk, a1 = (1.0f - ok) / dk;
+				tnf = fmaxf(tnf, fminf(a0, a1));
+				tff = fminf(tff, fmaxf(a0, a1));
+				sdf += (float) P.plane[k] * dk;
 			}
+			const float s0f = (float) P.plane[0] * (float) P.o[0] + (float) P.plane[1] * (float) P.o[1] + (float) P.plane[2] * (float) P.o[2] + (float) P.plane[3];
+			const float t0f = fmaxf(fmaxf(tnf, -s0f / sdf), 0.0f);
+			// reject only when the miss is far outside fp32 rounding (relative 1e-3); NaNs fall through to fp64
+			if (t0f > tff + 1e-3f * (fabsf(tff) + fabsf(t0f)) + 1e-6f) maybe = false;
 		}
-		const double s0 = P.plane[0] * P.o[0] + P.plane[1] * P.o[1] + P.plane[2] * P.o[2] + P.plane[3];
-		const double sd = P.plane[0] * d[0] + P.plane[1] * d[1] + P.plane[2] * d[2];
-		float        entry[3] = {0.0f, 0.0f, 0.0f};
-		if (hit && sd > 0.0) {
-			const double t_clip = -s0 / sd;
-			double       t0     = tn > t_clip ? tn : t_clip;
-			if (t0 < 0.0) t0 = 0.0;
-			if (t0 < tf) {
-				covered = 1;
+		float entry[3] = {0.0f, 0.0f, 0.0f};
+		if (maybe) {
+			// (2) exact decision and entry point in fp64
+			double d[3], tn = -INFINITY, tf = INFINITY;
+			bool   hit = true;
 #pragma unroll
-				for (int k = 0; k < 3; ++k) entry[k] = (float) (P.o[k] + t0 * d[k]);
+			for (int k = 0; k < 3; ++k) {
+				d[k] = P.d0[k] + (double) px * P.ddx[k] + (double) py * P.ddy[k];
+				if (d[k] == 0.0) {
+					if (P.o[k] < 0.0 || P.o[k] > 1.0) hit = false;
+				} else {
+					double t0 = (0.0 - P.o[k]) / d[k], t1 = (1.0 - P.o[k]) / d[k];
+					if (t0 > t1) { const double t = t0; t0 = t1; t1 = t; }
+					if (t0 > tn) tn = t0;
+					if (t1 < tf) tf = t1;
+				}
+			}
+			const double s0 = P.plane[0] * P.o[0] + P.plane[1] * P.o[1] + P.plane[2] * P.o[2] + P.plane[3];
+			const double sd = P.plane[0] * d[0] + P.plane[1] * d[1] + P.plane[2] * d[2];
+			if (hit && sd > 0.0) {
+				const double t_clip = -s0 / sd;
+				double       t0     = tn > t_clip ? tn : t_clip;
+				if (t0 < 0.0) t0 = 0.0;
+				if (t0 < tf) {
+					covered = 1;
+#pragma unroll
+					for (int k = 0; k < 3; ++k) entry[k] = (float) (P.o[k] + t0 * d[k]);
+				}
 			}
 		}
 
@@ -371,6 +399,14 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 	P.ctas_per_tile   = P.ctas_per_tile_x * (tile_h / 8);
 	const int my_tiles = tile_first < n_tiles ? (n_tiles - tile_first + tile_stride - 1) / tile_stride : 0;
 	if (my_tiles == 0) return VKV_OK;
+	if (!vol->d_acorr) VKV_CUDA_CHECK(cudaMalloc(&vol->d_acorr, 256 * sizeof(float)));
+	if (vol->acorr_sampling != tfu->sampling_factor || vol->acorr_alpha != tfu->voxel_alpha_factor) {
+		acorr_table_kernel<<<1, 256, 0, s>>>(vol->d_acorr, tfu->voxel_alpha_factor, 1.0f / tfu->sampling_factor);
+		VKV_LAUNCHED();
+		vol->acorr_sampling = tfu->sampling_factor;
+		vol->acorr_alpha    = tfu->voxel_alpha_factor;
+	}
+	P.acorr = vol->d_acorr;
 	P.tex_v = vol->t_V; P.tex_g = vol->t_G;
 	P.V = vol->d_V; P.G = vol->d_G;
 	P.tf = reinterpret_cast<const uchar4 *>(vol->d_tf);
