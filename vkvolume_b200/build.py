@@ -100,8 +100,9 @@ def build_host_tools(force: bool = False, verbose: bool = False):
         if force or not _newer(exe, deps):
             if verbose:
                 print(f"[build] g++ {name}", flush=True)
-            _run(["g++", "-O2", "-std=c++17", "-Wall", "-I", str(ROOT / "include"), "-I", str(host), str(src),
-                  "-o", str(exe), "-L", str(LIBDIR), "-lvkv", "-Wl,-rpath,$ORIGIN"])
+            _run(["g++", "-O2", "-std=c++17", "-Wall", "-I", str(ROOT / "include"), "-I", str(host), "-I", "/usr/local/cuda/include",
+                  str(src), "-o", str(exe), "-L", str(LIBDIR), "-lvkv", "-L", "/usr/local/cuda/lib64", "-lcudart",
+                  "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,/usr/local/cuda/lib64"])
         out.append(exe)
     return out
 

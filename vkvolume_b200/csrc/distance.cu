@@ -15,15 +15,11 @@
 // B200 design: every output cell gets its own thread.
 //   * x pass: the row is turned into a bit mask with warp ballots and each lane finds the
 //     nearest set bit with clz/ffs over at most 8 words per side (255-cell cap) — O(1), coalesced.
-//   * y / z passes: s(y) = min(f+(y), f-(y)) with the one-sided f+(y) = min_{n>=0} max(n, g(y+n)).
-//     A CTA stages 32 adjacent columns x the whole line in shared memory (coalesced 32-byte row
-//     segments); warp 0 scans every column downwards for f+, warp 1 upwards for f-, one lane per
-//     column.  The scan keeps the classic "next smaller element" chain of candidates (farther
-//     candidates survive only with a strictly smaller g), doubly linked through two byte arrays,
-//     plus a pointer to the best candidate that only ever moves towards the scan position — O(1)
-//     amortised per cell instead of the reference's O(distance) search, and exact.  Lanes touch 32
-//     consecutive bytes per access, so shared memory is conflict-free.
-//     Lines longer than the shared-memory budget fall back to the capped search on global memory.
+//   * y / z passes: s(y) <= r iff the minimum of g over the window [y-r, y+r] is <= r — monotone in r — so
+//     each cell does an 8-step binary search on r against a sparse range-minimum table built in shared
+//     memory from the staged tile (32 adjacent columns x the whole line, coalesced 32-byte row segments).
+//     One thread per cell, no serial scan, ~25 conflict-free shared-memory operations per cell whatever
+//     the distances are.  Lines too long for shared memory use narrower tiles, then a global-memory search.
 //   * the anisotropic build shares the 2 x passes and 4 y passes between the 8 octant maps
 //     (same sharing as the reference's 14-dispatch schedule).
 // The maps are small (M bytes, L2-resident below ~100 MB); algorithmic bytes 6 B/block
@@ -248,75 +244,62 @@ __global__ void __launch_bounds__(256) minmax_pass_kernel(const uint8_t *__restr
 }
 
 
-// ---- y / z passes, O(1) amortised --------------------------------------------------------------
-// MODE 0: two-sided -> dst0 | MODE 1: f+ (towards +axis) -> dst0 | MODE 2: f- -> dst0 | MODE 3: f+ -> dst0 and f- -> dst1
-// One-sided scan for lane-private column `lane` of the staged tile.  Scan coordinate s runs from
-// L-1 down to 0 and "ahead" means larger s; UP maps s to the line position (s or L-1-s).
-template <bool UP, bool TO_SMEM>
-__device__ __forceinline__ void chain_scan(const uint8_t *__restrict__ g, uint8_t *__restrict__ nx, uint8_t *__restrict__ pv,
-                                           uint8_t *__restrict__ res_smem, uint8_t *__restrict__ res_gmem, size_t line_stride, int L, int lane,
-                                           bool store)
+// ---- y / z passes: range-minimum table + binary search on the radius --------------------------------
+// s(y) <= r  <=>  min of g over the window [y-r, y+r] (one-sided: [y, y+r] or [y-r, y]) is <= r, and that
+// predicate is monotone in r, so s(y) is found by an 8-step binary search whose window minimum is an O(1)
+// lookup in a sparse table M_k(y) = min g[y .. y+2^k) built in shared memory.  Every cell is an independent
+// thread (no serial scan along the line), shared-memory accesses are 32 consecutive bytes per warp, and the
+// cost per cell is ~25 shared-memory operations whatever the distances are (the reference's search costs
+// O(distance) per cell on top of being serial along the line).  Exact, so bit-identical.
+// MODE 0: two-sided -> dst0 | 1: towards +axis -> dst0 | 2: towards -axis -> dst0 | 3: both one-sided (+ -> dst0, - -> dst1)
+template <int SIDE>        // SIDE 0 two-sided, +1 / -1 one-sided
+__device__ __forceinline__ unsigned rmq_search(const uint8_t *__restrict__ T, int L, int TW, size_t level_stride, int y, int col, unsigned g0)
 {
-	auto pos = [&](int s) { return UP ? s : L - 1 - s; };        // line position of scan coordinate s
-	int  p   = -1;                                               // best candidate (scan coordinate), -1 = none
-	for (int s = L - 1; s >= 0; --s) {
-		const unsigned gs = g[pos(s) * 32 + lane];
-		// next strictly smaller element ahead, at most 255 cells away (farther ones saturate anyway)
-		int j = s + 1;
-		while (j < L && j - s <= 255 && g[pos(j) * 32 + lane] >= gs) {
-			const unsigned o = nx[j * 32 + lane];
-			j                = o ? j + (int) o : L;
-		}
-		const bool has_next = j < L && j - s <= 255;
-		nx[s * 32 + lane]   = has_next ? (uint8_t) (j - s) : 0;
-		pv[s * 32 + lane]   = 0;
-		if (has_next) pv[j * 32 + lane] = (uint8_t) (j - s);
-		if (!has_next || p < j) p = s;        // the old best was popped (or is out of reach): s dominates it
-		unsigned vp = max((unsigned) (p - s), (unsigned) g[pos(p) * 32 + lane]);
-		for (;;) {                             // slide towards s while the nearer neighbour on the chain is at least as good
-			const unsigned o = pv[p * 32 + lane];
-			if (!o) break;
-			const int      q  = p - (int) o;
-			const unsigned vq = max((unsigned) (q - s), (unsigned) g[pos(q) * 32 + lane]);
-			if (vq > vp) break;
-			p  = q;
-			vp = vq;
-		}
-		const uint8_t r = (uint8_t) min(vp, 255u);
-		if (TO_SMEM) res_smem[pos(s) * 32 + lane] = r;
-		else if (store) res_gmem[(size_t) pos(s) * line_stride] = r;
+	unsigned lo = 0, hi = min(g0, 255u);        // s(y) <= g(y): the n = 0 term
+	while (lo < hi) {
+		const int r   = (int) ((lo + hi) >> 1);
+		const int a   = SIDE > 0 ? y : max(y - r, 0);
+		const int b   = SIDE < 0 ? y : min(y + r, L - 1);
+		const int k   = 31 - __clz(b - a + 1);
+		const uint8_t *Tk = T + (size_t) k * level_stride;
+		const unsigned w  = min((unsigned) Tk[a * TW + col], (unsigned) Tk[(b - (1 << k) + 1) * TW + col]);
+		if (w <= (unsigned) r) hi = (unsigned) r;
+		else lo = (unsigned) r + 1;
 	}
+	return lo;
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(64) minmax_scan_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst0, uint8_t *__restrict__ dst1,
-                                                        uint32_t Wb, uint32_t L, size_t line_stride, size_t outer_stride)
+__global__ void __launch_bounds__(256) minmax_rmq_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst0, uint8_t *__restrict__ dst1,
+                                                       uint32_t Wb, uint32_t L, size_t line_stride, size_t outer_stride, int TW, int nlev)
 {
-	extern __shared__ uint8_t smem[];
-	const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t x    = blockIdx.x * 32 + lane;
+	extern __shared__ uint8_t T[];        // nlev levels of L x TW bytes
+	const int      col  = threadIdx.x % TW, sub = threadIdx.x / TW, nsub = blockDim.x / TW;
+	const uint32_t x    = blockIdx.x * TW + col;
 	const bool     in_x = x < Wb;
 	const size_t   base = (size_t) blockIdx.y * outer_stride + x;
-	const size_t   tile = (size_t) L * 32;
-	uint8_t       *g    = smem;                                 // staged input
-	uint8_t       *nxA = g + tile, *pvA = nxA + tile;            // chain links of the f+ scan (warp 0)
-	uint8_t       *nxB = pvA + tile, *pvB = nxB + tile;          // chain links of the f- scan (warp 1)
-	uint8_t       *A = pvB + tile, *B = A + tile;                // MODE 0 only: the two one-sided results
-	for (uint32_t p = warp; p < L; p += 2) g[p * 32 + lane] = in_x ? src[base + (size_t) p * line_stride] : (uint8_t) 255;
+	const size_t   lst  = (size_t) L * TW;
+	for (uint32_t p = sub; p < L; p += nsub) T[p * TW + col] = in_x ? src[base + (size_t) p * line_stride] : (uint8_t) 255;
 	__syncthreads();
-	if (MODE == 0) {
-		if (warp == 0) chain_scan<true, true>(g, nxA, pvA, A, nullptr, 0, (int) L, lane, false);
-		else chain_scan<false, true>(g, nxB, pvB, B, nullptr, 0, (int) L, lane, false);
+	for (int k = 1; k < nlev; ++k) {
+		const uint8_t *prev = T + (size_t) (k - 1) * lst;
+		uint8_t       *cur  = T + (size_t) k * lst;
+		const uint32_t half = 1u << (k - 1);
+		for (uint32_t p = sub; p < L; p += nsub) {
+			const unsigned a = prev[p * TW + col];
+			const unsigned b = p + half < L ? prev[(p + half) * TW + col] : 255u;
+			cur[p * TW + col] = (uint8_t) min(a, b);
+		}
 		__syncthreads();
-		if (in_x)
-			for (uint32_t p = warp; p < L; p += 2) dst0[base + (size_t) p * line_stride] = min(A[p * 32 + lane], B[p * 32 + lane]);
-	} else if (MODE == 3) {
-		if (warp == 0) chain_scan<true, false>(g, nxA, pvA, nullptr, dst0 + base, line_stride, (int) L, lane, in_x);
-		else chain_scan<false, false>(g, nxB, pvB, nullptr, dst1 + base, line_stride, (int) L, lane, in_x);
-	} else if (MODE == 1) {
-		if (warp == 0) chain_scan<true, false>(g, nxA, pvA, nullptr, dst0 + base, line_stride, (int) L, lane, in_x);
-	} else {
-		if (warp == 1) chain_scan<false, false>(g, nxA, pvA, nullptr, dst0 + base, line_stride, (int) L, lane, in_x);
+	}
+	if (!in_x) return;
+	for (uint32_t p = sub; p < L; p += nsub) {
+		const unsigned g0 = T[p * TW + col];
+		const size_t   o  = base + (size_t) p * line_stride;
+		if (MODE == 0) dst0[o] = (uint8_t) rmq_search<0>(T, (int) L, TW, lst, (int) p, col, g0);
+		if (MODE == 1 || MODE == 3) dst0[o] = (uint8_t) rmq_search<1>(T, (int) L, TW, lst, (int) p, col, g0);
+		if (MODE == 2) dst0[o] = (uint8_t) rmq_search<-1>(T, (int) L, TW, lst, (int) p, col, g0);
+		if (MODE == 3) dst1[o] = (uint8_t) rmq_search<-1>(T, (int) L, TW, lst, (int) p, col, g0);
 	}
 }
 
@@ -345,16 +328,22 @@ static int run_minmax(const vkv_volume *vol, int axis, const uint8_t *src, uint8
 	const size_t   line_stride  = axis == 1 ? (size_t) Wb : (size_t) Wb * Hb;
 	const size_t   outer_stride = axis == 1 ? (size_t) Wb * Hb : (size_t) Wb;
 	const dim3     grid((Wb + 31) / 32, axis == 1 ? Db : Hb);
-	constexpr int  MODE   = DIR == 0 ? 0 : (NOUT == 2 ? 3 : (DIR > 0 ? 1 : 2));
-	constexpr int  arrays = MODE == 0 ? 7 : (MODE == 3 ? 5 : 3);
-	const size_t   smem   = (size_t) arrays * L * 32;
+	constexpr int  MODE = DIR == 0 ? 0 : (NOUT == 2 ? 3 : (DIR > 0 ? 1 : 2));
+	// table levels: the largest window is min(2*255+1, L) cells (one-sided: min(256, L))
+	const uint32_t max_window = std::min<uint32_t>(DIR == 0 ? 511u : 256u, L);
+	int            nlev       = 1;
+	while ((2u << (nlev - 1)) <= max_window) ++nlev;        // nlev = floor(log2(max_window)) + 1
+	int TW = 32;
+	while (TW > 8 && (size_t) nlev * L * TW > (size_t) 200 * 1024) TW >>= 1;
+	const size_t smem = (size_t) nlev * L * TW;
 	if (smem <= (size_t) 200 * 1024) {
 		static bool configured = false;        // opt in to > 48 KB of dynamic shared memory once per instantiation
 		if (!configured) {
-			VKV_CUDA_CHECK(cudaFuncSetAttribute(minmax_scan_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+			VKV_CUDA_CHECK(cudaFuncSetAttribute(minmax_rmq_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 			configured = true;
 		}
-		minmax_scan_kernel<MODE><<<grid, 64, smem, s>>>(src, dst0, dst1, Wb, L, line_stride, outer_stride);
+		const dim3 grid_rmq((Wb + TW - 1) / TW, axis == 1 ? Db : Hb);
+		minmax_rmq_kernel<MODE><<<grid_rmq, 256, smem, s>>>(src, dst0, dst1, Wb, L, line_stride, outer_stride, TW, nlev);
 	} else if (L <= (uint32_t) kLineMax) {
 		minmax_pass_kernel<DIR, NOUT, true><<<grid, 256, (size_t) L * 32, s>>>(src, dst0, dst1, Wb, L, line_stride, outer_stride);
 	} else {

@@ -111,7 +111,23 @@ __global__ void __launch_bounds__(256) occupancy_fast_kernel(const uint8_t *__re
 		}
 		unsigned flags = 0;        // bit k: block k of this thread's 16-voxel run is occupied
 		unsigned cnt   = 0;
+		auto candidates = [&](unsigned vword, unsigned gword) -> unsigned {
+			unsigned c = 0x80808080u;
+			if (need_vlo) c &= v_ge.test(vword);
+			if (need_vhi) c &= v_le.test(~vword);
+			if (need_glo) c &= g_ge.test(gword);
+			if (need_ghi) c &= g_le.test(~gword);
+			return c;
+		};
+		// branch-free prefilter over all 16*BS voxels of this thread; the LUT path below is entered by few warps
+		unsigned any = 0;
 		if (!none) {
+#pragma unroll
+			for (int zz = 0; zz < BS; ++zz) {
+				any |= candidates(vv[zz].x, gg[zz].x) | candidates(vv[zz].y, gg[zz].y) | candidates(vv[zz].z, gg[zz].z) | candidates(vv[zz].w, gg[zz].w);
+			}
+		}
+		if (any) {
 #pragma unroll
 			for (int zz = 0; zz < BS; ++zz) {
 				const bool valid = in_xy && (bz * BS + zz) < D;
@@ -119,11 +135,7 @@ __global__ void __launch_bounds__(256) occupancy_fast_kernel(const uint8_t *__re
 				const unsigned gw[4] = {gg[zz].x, gg[zz].y, gg[zz].z, gg[zz].w};
 #pragma unroll
 				for (int k = 0; k < 4; ++k) {
-					unsigned cand = 0x80808080u;
-					if (need_vlo) cand &= v_ge.test(vw[k]);
-					if (need_vhi) cand &= v_le.test(~vw[k]);
-					if (need_glo) cand &= g_ge.test(gw[k]);
-					if (need_ghi) cand &= g_le.test(~gw[k]);
+					const unsigned cand = candidates(vw[k], gw[k]);
 					if (valid && cand) {
 						if (BS >= 4) {
 							bool hit = false;

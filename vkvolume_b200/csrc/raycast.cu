@@ -9,7 +9,8 @@
 //   * no geometry at all: each pixel computes its ray/box/clip-plane entry analytically in fp64
 //     from an affine pixel->direction basis built on the host;
 //   * one thread per pixel, a warp is an 8x4 pixel tile (coherent rays -> coherent texture and
-//     distance-map fetches), a CTA is a 16x8 tile;
+//     distance-map fetches), a CTA is just two warps (16x4 pixels) so that a few long rays do not pin
+//     a large slice of the register file;
 //   * V and G are cudaArray 3D textures sampled with hardware trilinear filtering
 //     (tex3D, normalised coordinates, clamp, UNORM->float); an EXACT variant does 8 point loads
 //     from the linear copies and fp32 lerps in the oracle's operation order;
@@ -86,11 +87,15 @@ __global__ void acorr_table_kernel(float *__restrict__ table, float voxel_alpha_
 	table[threadIdx.x] = clampf_(voxel_alpha_factor * (1.0f - powf(1.0f - a, sampling_factor_inv)), 0.0f, 1.0f);
 }
 
-template <int SKIP, bool EXACT>
-__global__ void __launch_bounds__(128) raycast_kernel(const __grid_constant__ RayParams P)
+#ifndef VKV_RC_MIN_CTAS
+#define VKV_RC_MIN_CTAS 20
+#endif
+// A CTA is two warps = a 16x4 pixel tile; small CTAs keep the register file busy while long rays finish.
+template <int SKIP, bool EXACT, bool COUNT>
+__global__ void __launch_bounds__(64, VKV_RC_MIN_CTAS) raycast_kernel(const __grid_constant__ RayParams P)
 {
 	__shared__ float s_acorr[256];        // opacity correction per TF alpha byte (volume_render.frag:283)
-	__shared__ unsigned long long s_cnt[4][4];
+	__shared__ unsigned long long s_cnt[2][4];
 	for (int k = threadIdx.x; k < 256; k += blockDim.x) s_acorr[k] = __ldg(P.acorr + k);
 	__syncthreads();
 
@@ -99,9 +104,9 @@ __global__ void __launch_bounds__(128) raycast_kernel(const __grid_constant__ Ra
 	const int local_tile = blockIdx.x / P.ctas_per_tile, in_tile = blockIdx.x % P.ctas_per_tile;
 	const int tile = P.tile_first + local_tile * P.tile_stride;
 	const int tx0 = (tile % P.tiles_x) * P.tile_w + (in_tile % P.ctas_per_tile_x) * 16;
-	const int ty0 = (tile / P.tiles_x) * P.tile_h + (in_tile / P.ctas_per_tile_x) * 8;
-	const int px = tx0 + (warp & 1) * 8 + (lane & 7);
-	const int py = ty0 + (warp >> 1) * 4 + (lane >> 3);
+	const int ty0 = (tile / P.tiles_x) * P.tile_h + (in_tile / P.ctas_per_tile_x) * 4;
+	const int px = tx0 + warp * 8 + (lane & 7);
+	const int py = ty0 + (lane >> 3);
 	const bool in_frame = px < P.width && py < P.height && px < (tile % P.tiles_x) * P.tile_w + P.tile_w &&
 	                      py < (tile / P.tiles_x) * P.tile_h + P.tile_h;
 
@@ -273,7 +278,7 @@ __global__ void __launch_bounds__(128) raycast_kernel(const __grid_constant__ Ra
 									break;
 								}
 							} else {
-								++n_empty;
+								if (COUNT) ++n_empty;
 							}
 							++i;
 							if (SKIP != VKV_SKIP_NONE) i_min = i;
@@ -307,7 +312,7 @@ __global__ void __launch_bounds__(128) raycast_kernel(const __grid_constant__ Ra
 		if (P.depth) P.depth[p] = frag_depth;
 	}
 
-	if (P.counts) {
+	if (COUNT) {
 		unsigned long long c[4] = {n_vol, n_dist, n_empty, covered};
 #pragma unroll
 		for (int k = 0; k < 4; ++k) {
@@ -317,7 +322,7 @@ __global__ void __launch_bounds__(128) raycast_kernel(const __grid_constant__ Ra
 		}
 		__syncthreads();
 		if (threadIdx.x < 4) {
-			const unsigned long long t = s_cnt[0][threadIdx.x] + s_cnt[1][threadIdx.x] + s_cnt[2][threadIdx.x] + s_cnt[3][threadIdx.x];
+			const unsigned long long t = s_cnt[0][threadIdx.x] + s_cnt[1][threadIdx.x];
 			if (t) atomicAdd(P.counts + threadIdx.x, t);
 		}
 	}
@@ -396,7 +401,7 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 	const int n_tiles = P.tiles_x * tiles_y;
 	P.tile_first = tile_first; P.tile_stride = tile_stride;
 	P.ctas_per_tile_x = tile_w / 16;
-	P.ctas_per_tile   = P.ctas_per_tile_x * (tile_h / 8);
+	P.ctas_per_tile   = P.ctas_per_tile_x * (tile_h / 4);
 	const int my_tiles = tile_first < n_tiles ? (n_tiles - tile_first + tile_stride - 1) / tile_stride : 0;
 	if (my_tiles == 0) return VKV_OK;
 	if (!vol->d_acorr) VKV_CUDA_CHECK(cudaMalloc(&vol->d_acorr, 256 * sizeof(float)));
@@ -418,10 +423,12 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 
 	const long long grid = (long long) my_tiles * P.ctas_per_tile;
 	const bool      exact = opt->filter == VKV_FILTER_EXACT;
-#define VKV_RC(SK)                                                                  \
-	do {                                                                            \
-		if (exact) raycast_kernel<SK, true><<<(unsigned) grid, 128, 0, s>>>(P);      \
-		else raycast_kernel<SK, false><<<(unsigned) grid, 128, 0, s>>>(P);           \
+#define VKV_RC(SK)                                                                                  \
+	do {                                                                                            \
+		if (exact && counts) raycast_kernel<SK, true, true><<<(unsigned) grid, 64, 0, s>>>(P);       \
+		else if (exact) raycast_kernel<SK, true, false><<<(unsigned) grid, 64, 0, s>>>(P);           \
+		else if (counts) raycast_kernel<SK, false, true><<<(unsigned) grid, 64, 0, s>>>(P);          \
+		else raycast_kernel<SK, false, false><<<(unsigned) grid, 64, 0, s>>>(P);                     \
 	} while (0)
 	switch (opt->skipping_type) {
 		case VKV_SKIP_NONE: VKV_RC(VKV_SKIP_NONE); break;
