@@ -39,7 +39,7 @@ struct RayParams {
 	int    use_gradient;
 	int    ert, test;
 	int    width, height;
-	int    tile_w, tile_h, tiles_x, tile_first, tile_stride, ctas_per_tile_x, ctas_per_tile;
+	int    tile_w, tile_h, tiles_x, tile_first, tile_stride, ctas_per_tile_x, ctas_per_tile, my_tiles;
 	cudaTextureObject_t tex_v, tex_g;
 	const uint8_t *V, *G;
 	const uchar4  *tf;
@@ -88,7 +88,7 @@ __global__ void acorr_table_kernel(float *__restrict__ table, float voxel_alpha_
 }
 
 #ifndef VKV_RC_MIN_CTAS
-#define VKV_RC_MIN_CTAS 20
+#define VKV_RC_MIN_CTAS 16
 #endif
 // A CTA is two warps = a 16x4 pixel tile; small CTAs keep the register file busy while long rays finish.
 template <int SKIP, bool EXACT, bool COUNT>
@@ -101,7 +101,10 @@ __global__ void __launch_bounds__(64, VKV_RC_MIN_CTAS) raycast_kernel(const __gr
 
 	// CTA -> tile -> pixel
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int local_tile = blockIdx.x / P.ctas_per_tile, in_tile = blockIdx.x % P.ctas_per_tile;
+	// Tiles are issued from the middle of this launch's tile list outwards (m, m-1, m+1, m-2, ...): the long rays sit
+	// near the image centre, so their latency chains start at t = 0 and the cheap border tiles fill the tail.
+	const int seq = blockIdx.x / P.ctas_per_tile, in_tile = blockIdx.x % P.ctas_per_tile;
+	const int local_tile = P.my_tiles / 2 + ((seq & 1) ? -((seq + 1) >> 1) : (seq >> 1));
 	const int tile = P.tile_first + local_tile * P.tile_stride;
 	const int tx0 = (tile % P.tiles_x) * P.tile_w + (in_tile % P.ctas_per_tile_x) * 16;
 	const int ty0 = (tile / P.tiles_x) * P.tile_h + (in_tile / P.ctas_per_tile_x) * 4;
@@ -215,6 +218,10 @@ __global__ void __launch_bounds__(64, VKV_RC_MIN_CTAS) raycast_kernel(const __gr
 					bool voxel_occupied = true;
 					int  i_first_hit    = n_steps;
 					const int back = (int) ceilf(P.sampling_factor);
+					// look-ahead cache of hardware-filtered samples i .. i+3: consecutive volume samples are the common case
+					// inside occupied regions, and one batch of independent fetches replaces four dependent round trips
+					int   pre_base = -0x40000000;
+					float pre_v0 = 0.0f, pre_v1 = 0.0f, pre_v2 = 0.0f, pre_v3 = 0.0f, pre_g0 = 1.0f, pre_g1 = 1.0f, pre_g2 = 1.0f, pre_g3 = 1.0f;
 					for (int i = 0; i < n_steps;) {
 						const float fi     = (float) i;
 						const float pos[3] = {entry[0] + fi * step[0], entry[1] + fi * step[1], entry[2] + fi * step[2]};
@@ -261,8 +268,27 @@ __global__ void __launch_bounds__(64, VKV_RC_MIN_CTAS) raycast_kernel(const __gr
 								intensity = sample_exact(P.V, P.dim, pos[0], pos[1], pos[2]);
 								if (P.use_gradient) gradient = sample_exact(P.G, P.dim, pos[0], pos[1], pos[2]);
 							} else {
-								intensity = tex3D<float>(P.tex_v, pos[0], pos[1], pos[2]);
-								if (P.use_gradient) gradient = tex3D<float>(P.tex_g, pos[0], pos[1], pos[2]);
+								int k = i - pre_base;
+								if ((unsigned) k >= 4u) {
+									pre_base = i;
+									k        = 0;
+									const float f1 = (float) (i + 1), f2 = (float) (i + 2), f3 = (float) (i + 3);
+									const float q1[3] = {entry[0] + f1 * step[0], entry[1] + f1 * step[1], entry[2] + f1 * step[2]};
+									const float q2[3] = {entry[0] + f2 * step[0], entry[1] + f2 * step[1], entry[2] + f2 * step[2]};
+									const float q3[3] = {entry[0] + f3 * step[0], entry[1] + f3 * step[1], entry[2] + f3 * step[2]};
+									pre_v0 = tex3D<float>(P.tex_v, pos[0], pos[1], pos[2]);
+									pre_v1 = tex3D<float>(P.tex_v, q1[0], q1[1], q1[2]);
+									pre_v2 = tex3D<float>(P.tex_v, q2[0], q2[1], q2[2]);
+									pre_v3 = tex3D<float>(P.tex_v, q3[0], q3[1], q3[2]);
+									if (P.use_gradient) {
+										pre_g0 = tex3D<float>(P.tex_g, pos[0], pos[1], pos[2]);
+										pre_g1 = tex3D<float>(P.tex_g, q1[0], q1[1], q1[2]);
+										pre_g2 = tex3D<float>(P.tex_g, q2[0], q2[1], q2[2]);
+										pre_g3 = tex3D<float>(P.tex_g, q3[0], q3[1], q3[2]);
+									}
+								}
+								intensity = k == 0 ? pre_v0 : (k == 1 ? pre_v1 : (k == 2 ? pre_v2 : pre_v3));
+								if (P.use_gradient) gradient = k == 0 ? pre_g0 : (k == 1 ? pre_g1 : (k == 2 ? pre_g2 : pre_g3));
 							}
 							const uchar4 tx = __ldg(P.tf + tf_texel(gradient) * 256 + tf_texel(intensity));
 							voxel_occupied  = tx.w > 0;
@@ -404,6 +430,7 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 	P.ctas_per_tile   = P.ctas_per_tile_x * (tile_h / 4);
 	const int my_tiles = tile_first < n_tiles ? (n_tiles - tile_first + tile_stride - 1) / tile_stride : 0;
 	if (my_tiles == 0) return VKV_OK;
+	P.my_tiles = my_tiles;
 	if (!vol->d_acorr) VKV_CUDA_CHECK(cudaMalloc(&vol->d_acorr, 256 * sizeof(float)));
 	if (vol->acorr_sampling != tfu->sampling_factor || vol->acorr_alpha != tfu->voxel_alpha_factor) {
 		acorr_table_kernel<<<1, 256, 0, s>>>(vol->d_acorr, tfu->voxel_alpha_factor, 1.0f / tfu->sampling_factor);

@@ -446,8 +446,8 @@ inline void VolumeRender::update_transfer_function(Volume &volume)
 			compute_submit(cmd);
 		}
 		const uint64_t n_occupied = compute_occupied_voxel_count.get_result(buffer);
-		const auto     ext        = volume.get_volume().extent;
-		const size_t   n_voxels   = (size_t) ext[0] * ext[1] * ext[2];
+		const Volume::Image vimg  = volume.get_volume();
+		const size_t   n_voxels   = (size_t) vimg.extent[0] * vimg.extent[1] * vimg.extent[2];
 		last_occupied_percent     = 100.0f * (float) n_occupied / (float) n_voxels;
 		const std::chrono::duration<float, std::milli> dur = std::chrono::system_clock::now() - start;
 		printf("[info] Occupied voxels: %g%% in %gms\n", last_occupied_percent, dur.count());
