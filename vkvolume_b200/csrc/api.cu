@@ -2,6 +2,7 @@
 // Each entry point names the reference interface it replaces in include/vkv.h.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -125,6 +126,11 @@ int vkv_volume_create(vkv_context *ctx, uint32_t width, uint32_t height, uint32_
 	}
 	vol->N = (size_t) width * height * depth;
 	vol->M = (size_t) vol->dim_b[0] * vol->dim_b[1] * vol->dim_b[2];
+	if (vol->M >= (1ull << 32)) {        // the ray caster addresses map cells with 32-bit block indices
+		set_error("vkv_volume_create: the distance map would have 2^32 or more blocks; use a larger block size");
+		delete vol;
+		return VKV_ERR_ARGUMENT;
+	}
 	vol->precomputed_gradient = use_precomputed_gradient != 0;
 	auto fail = [&](cudaError_t e, const char *what) {
 		set_error("vkv_volume_create: %s failed: %s", what, cudaGetErrorString(e));
@@ -142,6 +148,7 @@ int vkv_volume_create(vkv_context *ctx, uint32_t width, uint32_t height, uint32_
 		if ((e = cudaMalloc3DArray(&vol->a_G, &fd, ext)) != cudaSuccess) return fail(e, "cudaMalloc3DArray(G)");
 		if (make_texture(vol->a_G, &vol->t_G)) { vkv_volume_destroy(vol); return VKV_ERR_CUDA; }
 	}
+	make_volume_tensor_maps(vol);
 	if ((e = cudaMalloc(&vol->d_tf, 256 * 256 * 4)) != cudaSuccess) return fail(e, "cudaMalloc(tf)");
 	if ((e = cudaMalloc(&vol->d_mask2, kMaskWords * sizeof(uint2))) != cudaSuccess) return fail(e, "cudaMalloc(mask)");
 	if ((e = cudaMalloc(&vol->d_bounds, sizeof(TFBounds))) != cudaSuccess) return fail(e, "cudaMalloc(bounds)");
@@ -162,11 +169,16 @@ void vkv_volume_destroy(vkv_volume *vol)
 	if (vol->t_G) cudaDestroyTextureObject(vol->t_G);
 	if (vol->a_V) cudaFreeArray(vol->a_V);
 	if (vol->a_G) cudaFreeArray(vol->a_G);
-	cudaFree(vol->d_V); cudaFree(vol->d_G); cudaFree(vol->d_tf); cudaFree(vol->d_mask2); cudaFree(vol->d_bounds);
+	cudaFree(vol->d_V); cudaFree(vol->d_G); cudaFree(vol->d_tf); cudaFree(vol->d_mask2); cudaFree(vol->d_bounds); cudaFree(vol->d_tf_rows);
 	for (auto *m : vol->d_maps) cudaFree(m);
 	cudaFree(vol->d_swap); cudaFree(vol->d_tmp); cudaFree(vol->d_count); cudaFree(vol->d_counts_scratch);
 	cudaFree(vol->d_fb_scratch);
-	cudaFree(vol->d_acorr);
+	cudaFree(vol->d_ctab);
+	if (vol->copy_stream) {
+		cudaStreamDestroy(vol->copy_stream);
+		for (auto &e : vol->band_done) cudaEventDestroy(e);
+		cudaEventDestroy(vol->copies_done);
+	}
 	if (vol->h_count) cudaFreeHost(vol->h_count);
 	delete vol;
 }
@@ -263,10 +275,8 @@ int vkv_volume_update_transfer_function_texture(vkv_volume *vol, const vkv_volum
 	DeviceGuard  guard(vol->ctx->device);
 	cudaStream_t s = (cudaStream_t) stream;
 	int          rc;
-	if ((rc = launch_tf_texture(vol, opt, s))) return rc;
-	vkv_transfer_function_uniform u;
-	vkv_transfer_function_uniform_from_options(opt, &u);
-	return launch_tf_masks(vol, &u, s);
+	(void) rc;
+	return launch_tf_texture(vol, opt, s);        // texture, masks and bounds in one kernel
 }
 
 int vkv_volume_set_transfer_function_texture(vkv_volume *vol, const uint8_t *rgba, void *stream)
@@ -276,6 +286,7 @@ int vkv_volume_set_transfer_function_texture(vkv_volume *vol, const uint8_t *rgb
 	cudaStream_t s = (cudaStream_t) stream;
 	VKV_CUDA_CHECK(cudaMemcpyAsync(vol->d_tf, rgba, 256 * 256 * 4, cudaMemcpyHostToDevice, s));
 	vol->has_tf = true;
+	++vol->tf_version;
 	return launch_tf_masks(vol, nullptr, s);
 }
 
@@ -418,7 +429,7 @@ int vkv_render_tiles(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_r
 	int rc;
 	if ((rc = check_render(vol, tfu, opt, width, height, tile_w, tile_h, tile_stride))) return rc;
 	DeviceGuard guard(vol->ctx->device);
-	return launch_render(vol, cam, ray, tfu, opt, width, height, tile_w, tile_h, tile_first, tile_stride, rgba8_dev, depth_dev,
+	return launch_render(vol, cam, ray, tfu, opt, width, height, tile_w, tile_h, tile_first, tile_stride, -1, rgba8_dev, depth_dev,
 	                     counts_dev, (cudaStream_t) stream);
 }
 
@@ -433,24 +444,54 @@ int vkv_render_to_host(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv
                        const vkv_transfer_function_uniform *tfu, const vkv_render_options *opt, int width, int height,
                        uint8_t *rgba8_host, vkv_sample_counts *counts_host, void *stream)
 {
-	VKV_REQUIRE(vol && rgba8_host, VKV_ERR_ARGUMENT, "vkv_render_to_host: NULL argument");
+	VKV_REQUIRE(vol && cam && ray && tfu && opt && rgba8_host, VKV_ERR_ARGUMENT, "vkv_render_to_host: NULL argument");
+	constexpr int TW = 64, TH = 32, kBands = 6;
+	int rc;
+	if ((rc = check_render(vol, tfu, opt, width, height, TW, TH, 1))) return rc;
 	DeviceGuard  guard(vol->ctx->device);
 	cudaStream_t s     = (cudaStream_t) stream;
 	const size_t bytes = (size_t) width * height * 4;
 	if (vol->fb_scratch_bytes < bytes) {
 		cudaFree(vol->d_fb_scratch);
-	cudaFree(vol->d_acorr);
 		vol->d_fb_scratch     = nullptr;
 		vol->fb_scratch_bytes = 0;
 		VKV_CUDA_CHECK(cudaMalloc(&vol->d_fb_scratch, bytes));
 		vol->fb_scratch_bytes = bytes;
 	}
+	if (!vol->copy_stream) {
+		VKV_CUDA_CHECK(cudaStreamCreateWithFlags(&vol->copy_stream, cudaStreamNonBlocking));
+		for (auto &e : vol->band_done) VKV_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		VKV_CUDA_CHECK(cudaEventCreateWithFlags(&vol->copies_done, cudaEventDisableTiming));
+	}
+	vkv_sample_counts *counts_dev = counts_host ? vol->d_counts_scratch : nullptr;
 	if (counts_host) VKV_CUDA_CHECK(cudaMemsetAsync(vol->d_counts_scratch, 0, sizeof(vkv_sample_counts), s));
-	int rc = vkv_render(vol, cam, ray, tfu, opt, width, height, vol->d_fb_scratch, nullptr, counts_host ? vol->d_counts_scratch : nullptr, stream);
-	if (rc) return rc;
-	VKV_CUDA_CHECK(cudaMemcpyAsync(rgba8_host, vol->d_fb_scratch, bytes, cudaMemcpyDeviceToHost, s));
-	if (counts_host) VKV_CUDA_CHECK(cudaMemcpyAsync(counts_host, vol->d_counts_scratch, sizeof(vkv_sample_counts), cudaMemcpyDeviceToHost, s));
+	// The frame is rendered in bands of tile rows; the device-to-host copy of a finished band runs on a second
+	// stream while the next band renders, so the PCIe transfer overlaps the ray casting instead of following it.
+	const int tiles_x = (width + TW - 1) / TW, tiles_y = (height + TH - 1) / TH;
+	int       want    = kBands;
+	if (const char *e = getenv("VKV_E2E_BANDS")) want = atoi(e) > 0 && atoi(e) <= 8 ? atoi(e) : kBands;        // tuning knob
+	const int bands   = tiles_y < want ? tiles_y : want;
+	int       row0    = 0;
+	for (int b = 0; b < bands; ++b) {
+		const int row1 = (int) ((long long) tiles_y * (b + 1) / bands);
+		if ((rc = launch_render(vol, cam, ray, tfu, opt, width, height, TW, TH, row0 * tiles_x, 1, (row1 - row0) * tiles_x,
+		                        vol->d_fb_scratch, nullptr, counts_dev, s)))
+			return rc;
+		VKV_CUDA_CHECK(cudaEventRecord(vol->band_done[b], s));
+		VKV_CUDA_CHECK(cudaStreamWaitEvent(vol->copy_stream, vol->band_done[b], 0));
+		const size_t y0 = (size_t) row0 * TH, y1 = (size_t) (row1 * TH < height ? row1 * TH : height);
+		VKV_CUDA_CHECK(cudaMemcpyAsync(rgba8_host + y0 * width * 4, vol->d_fb_scratch + y0 * width * 4, (y1 - y0) * width * 4,
+		                               cudaMemcpyDeviceToHost, vol->copy_stream));
+		row0 = row1;
+	}
+	// counters go through the volume's pinned staging words (the caller's struct is usually pageable memory,
+	// and a pageable async copy would serialise against the band copies)
+	static_assert(sizeof(vkv_sample_counts) <= 8 * sizeof(unsigned long long), "pinned staging area too small");
+	if (counts_host) VKV_CUDA_CHECK(cudaMemcpyAsync(vol->h_count, vol->d_counts_scratch, sizeof(vkv_sample_counts), cudaMemcpyDeviceToHost, s));
+	VKV_CUDA_CHECK(cudaEventRecord(vol->copies_done, vol->copy_stream));
+	VKV_CUDA_CHECK(cudaStreamWaitEvent(s, vol->copies_done, 0));
 	VKV_CUDA_CHECK(cudaStreamSynchronize(s));
+	if (counts_host) memcpy(counts_host, vol->h_count, sizeof(vkv_sample_counts));
 	return VKV_OK;
 }
 

@@ -52,12 +52,16 @@ static inline uint32_t rnd_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; 
 // word index = gradient * 8 + (intensity >> 5), bit = intensity & 31.
 constexpr int kMaskWords = 256 * 256 / 32;
 
-// Conservative [lo, hi] byte ranges outside which no texel is visible; lets the
-// O(N) pass reject 4 voxels at a time with SIMD byte compares before touching the LUT.
+// What the O(N) pass knows about a visibility mask without looking texels up:
+//   [v_lo, v_hi] x [g_lo, g_hi]  conservative byte ranges outside which no texel is visible (v_lo > v_hi: nothing is);
+//   exact                        the visible set IS that rectangle, so a SIMD byte-range test classifies voxels exactly;
+//   v_sure, g_sure               every texel with v >= v_sure and g >= g_sure is visible (256: no such rectangle).
+struct TFRange {
+	uint32_t v_lo, v_hi, g_lo, g_hi, exact, v_sure, g_sure, pad;
+};
+// tex_*: TF-texture mask (occupancy); ana_*: analytic mask (voxel count); *_row255: gradient row 255 only (use_gradient == false)
 struct TFBounds {
-	// [0]: all rows, texture mask only; [1]: all rows, union of both masks;
-	// [2]: row 255 only (use_gradient == false), texture mask; [3]: row 255, union.
-	uint32_t v_lo[4], v_hi[4], g_lo[4], g_hi[4];
+	TFRange tex_all, ana_all, tex_row255, ana_row255;
 };
 
 }        // namespace vkv
@@ -86,9 +90,13 @@ struct vkv_volume {
 	uint8_t        *d_tf      = nullptr;        // 256*256 RGBA8
 	uint2          *d_mask2   = nullptr;        // kMaskWords x {texture, analytic}
 	vkv::TFBounds  *d_bounds  = nullptr;
+	void           *d_tf_rows = nullptr;        // per-row mask statistics + ticket (tf_masks_kernel scratch)
 	bool            has_tf    = false;
 	vkv_transfer_function_uniform mask_tfu{};   // tfu the analytic mask was built for
 	bool            mask_ana_valid = false;
+
+	alignas(64) unsigned char tmap_V[128]{}, tmap_G[128]{};        // CUtensorMap over d_V / d_G (TMA-staged occupancy kernel)
+	bool                      tmap_ok = false;
 
 	std::vector<uint8_t *> d_maps;        // distance maps (map n-1 doubles as the occupancy map)
 	uint8_t               *d_swap = nullptr;
@@ -100,8 +108,13 @@ struct vkv_volume {
 	vkv_sample_counts  *d_counts_scratch = nullptr;
 	uint8_t            *d_fb_scratch = nullptr;        // framebuffer for vkv_render_to_host
 	size_t              fb_scratch_bytes = 0;
-	float              *d_acorr = nullptr;             // ray caster: opacity-correction table + the key it was built for
-	float               acorr_sampling = -1.0f, acorr_alpha = -1.0f;
+	cudaStream_t        copy_stream = nullptr;         // vkv_render_to_host: D2H copies of finished bands overlap the next band
+	cudaEvent_t         band_done[8]{};
+	cudaEvent_t         copies_done = nullptr;
+	uint64_t            tf_version = 0;                // bumped by every TF-texture write
+	void               *d_ctab = nullptr;              // ray caster: 256x256 float4 premultiplied colour table + the key it was built for
+	uint64_t            ctab_tf_version = ~0ull;
+	float               ctab_sampling = -1.0f, ctab_alpha = -1.0f;
 };
 
 namespace vkv {
@@ -116,7 +129,8 @@ int launch_normalise(const void *raw_dev, size_t n, int kind, bool big_endian, f
                      cudaStream_t s);
 int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_cast_uniform *ray,
                   const vkv_transfer_function_uniform *tfu, const vkv_render_options *opt, int width, int height,
-                  int tile_w, int tile_h, int tile_first, int tile_stride, uint8_t *rgba8, float *depth,
+                  int tile_w, int tile_h, int tile_first, int tile_stride, int tile_limit, uint8_t *rgba8, float *depth,
                   vkv_sample_counts *counts, cudaStream_t s);
 int sync_arrays_from_linear(vkv_volume *vol, bool gradient, cudaStream_t s);
+int make_volume_tensor_maps(vkv_volume *vol);
 }        // namespace vkv

@@ -24,6 +24,8 @@
 //     (same sharing as the reference's 14-dispatch schedule).
 // The maps are small (M bytes, L2-resident below ~100 MB); algorithmic bytes 6 B/block
 // (isotropic) and 28 B/block (anisotropic) as in SURVEY §8(d).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vkv {
@@ -303,6 +305,159 @@ __global__ void __launch_bounds__(256) minmax_rmq_kernel(const uint8_t *__restri
 	}
 }
 
+// ---- y pass as a chamfer sweep ---------------------------------------------------------------------------
+// After the x pass g(x, y) is the distance to the nearest occupied cell of the SAME row.  The 2-D Chebyshev
+// distance within a slice then obeys the chamfer recurrence
+//     F(x, y) = min( g(x, y), 1 + min( F(x-1, y-1), F(x, y-1), F(x+1, y-1) ) )            (rows 0 .. y)
+// and the same from the other side, in place on F: one diagonal step towards a source lowers max(|dx|, |dy|) by
+// exactly one and no step can lower it by more, and the base term g already covers the sources of the row itself, so
+// there is NO dependency inside a row — a row is one parallel step.  Exact (the result is the closed form
+// min over sources of max(|dx|, |dy|), saturating at 255 because g <= 255), O(1) per cell, no search at all.
+// The octant-restricted maps use the one-sided x pass and only the neighbours {0, sx} (a step may not leave the
+// quadrant), and keep the two sweep directions as two outputs (sources at y' >= y -> dst0, y' <= y -> dst1).
+// One CTA per z slice; thread t owns cells t, t + T, ...; the previous row lives in shared memory (double-buffered,
+// one __syncthreads per row); the rows of the input are prefetched eight at a time.
+constexpr int kSweepMaxCells = 4;        // cells per thread: rows up to 4096 cells
+template <int XDIR, int NC>              // XDIR 0: isotropic (two-sided x, 3 neighbours, in-place second sweep); +-1: one-sided
+__global__ void __launch_bounds__(1024) ysweep_kernel(const uint8_t *__restrict__ g, uint8_t *__restrict__ dst0, uint8_t *__restrict__ dst1,
+                                                      uint32_t Wb, uint32_t Hb)
+{
+	extern __shared__ uint8_t s_rows[];        // 2 x (Wb + 2): previous / current row with a 255 border on both sides
+	const uint32_t T = blockDim.x, t = threadIdx.x;
+	const size_t   slice = (size_t) blockIdx.x * Wb * Hb;
+	uint8_t       *buf[2] = {s_rows + 1, s_rows + (Wb + 2) + 1};
+	constexpr int  P = 8;
+	for (int sweep = 0; sweep < 2; ++sweep) {
+		// sweep 0 walks y upwards (sources at y' <= y), sweep 1 downwards (sources at y' >= y)
+		const uint8_t *src = (XDIR == 0 && sweep == 1) ? dst0 : g;
+		uint8_t       *dst = XDIR == 0 ? dst0 : (sweep == 0 ? dst1 : dst0);
+		if (t == 0) { buf[0][-1] = 255; buf[1][-1] = 255; buf[0][Wb] = 255; buf[1][Wb] = 255; }
+		for (int c = 0; c < NC; ++c) {
+			const uint32_t x = t + c * T;
+			if (x < Wb) buf[0][x] = 255;        // "row -1": nothing behind the first row
+		}
+		__syncthreads();
+		unsigned nxt[NC][P];
+		auto row_of = [&](uint32_t i) { return sweep == 0 ? i : Hb - 1 - i; };
+		auto load_group = [&](uint32_t i0) {
+#pragma unroll
+			for (int k = 0; k < P; ++k)
+#pragma unroll
+				for (int c = 0; c < NC; ++c) {
+					const uint32_t x = t + c * T, i = i0 + k;
+					nxt[c][k] = (x < Wb && i < Hb) ? (unsigned) src[slice + (size_t) row_of(i) * Wb + x] : 255u;
+				}
+		};
+		load_group(0);
+		int pb = 0;
+		for (uint32_t i0 = 0; i0 < Hb; i0 += P) {
+			unsigned cur[NC][P];
+#pragma unroll
+			for (int k = 0; k < P; ++k)
+#pragma unroll
+				for (int c = 0; c < NC; ++c) cur[c][k] = nxt[c][k];
+			load_group(i0 + P);        // in flight while this group's rows are swept
+#pragma unroll
+			for (int k = 0; k < P; ++k) {
+				if (i0 + k < Hb) {
+					const uint8_t *prev = buf[pb];
+					uint8_t       *now  = buf[pb ^ 1];
+#pragma unroll
+					for (int c = 0; c < NC; ++c) {
+						const uint32_t x = t + c * T;
+						if (x < Wb) {
+							unsigned m = prev[x];
+							if (XDIR >= 0) m = min(m, (unsigned) prev[x + 1]);
+							if (XDIR <= 0) m = min(m, (unsigned) prev[(int) x - 1]);
+							const unsigned v = min(cur[c][k], m + 1u);
+							now[x] = (uint8_t) v;
+							dst[slice + (size_t) row_of(i0 + k) * Wb + x] = (uint8_t) v;
+						}
+					}
+					pb ^= 1;
+				}
+				__syncthreads();
+			}
+		}
+	}
+}
+
+// ---- z pass as a walk along the line --------------------------------------------------------------------------
+// One-sided result towards +z: F(z) = min_{j >= z} max(j - z, h(j)).  Stepping from z + 1 to z every candidate's cost
+// grows by at most one, so with r = F(z + 1):   F(z) = min( h(z), r      if some j in [z+1, z+r] has h(j) <= r
+//                                                                 r + 1  otherwise ),
+// i.e. ONE range-minimum query per cell instead of an 8-step binary search; the two-sided value is min(F, B) with B the
+// mirror image.  The sparse range-minimum table of the line is built in shared memory as before; a CTA owns TW adjacent
+// columns, walks them with 2 x TW threads (one per column and direction) and writes the result rows coalesced.
+// MODE 0: dst0 = min(F, B) | 3: dst0 = F (towards +z), dst1 = B (towards -z)
+template <int MODE>
+__global__ void __launch_bounds__(256) zwalk_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst0, uint8_t *__restrict__ dst1,
+                                                    uint32_t Wb, uint32_t L, size_t line_stride, size_t outer_stride, int TW, int nlev)
+{
+	extern __shared__ uint8_t T[];        // nlev levels of L x TW bytes, then the F and B lines (2 x L x TW)
+	const int      col  = threadIdx.x % TW, sub = threadIdx.x / TW, nsub = blockDim.x / TW;
+	const uint32_t x    = blockIdx.x * TW + col;
+	const bool     in_x = x < Wb;
+	const size_t   base = (size_t) blockIdx.y * outer_stride + x;
+	const size_t   lst  = (size_t) L * TW;
+	uint8_t       *Fl = T + (size_t) nlev * lst, *Bl = Fl + lst;
+	for (uint32_t p = sub; p < L; p += nsub) T[p * TW + col] = in_x ? src[base + (size_t) p * line_stride] : (uint8_t) 255;
+	__syncthreads();
+	for (int k = 1; k < nlev; ++k) {
+		const uint8_t *prev = T + (size_t) (k - 1) * lst;
+		uint8_t       *cur  = T + (size_t) k * lst;
+		const uint32_t half = 1u << (k - 1);
+		for (uint32_t p = sub; p < L; p += nsub) {
+			const unsigned a = prev[p * TW + col];
+			const unsigned b = p + half < L ? prev[(p + half) * TW + col] : 255u;
+			cur[p * TW + col] = (uint8_t) min(a, b);
+		}
+		__syncthreads();
+	}
+	if (sub < 2) {
+		const int Li = (int) L;
+		if (sub == 0) {        // F: towards +z, walking down from the last cell
+			unsigned r = T[(Li - 1) * TW + col];
+			Fl[(Li - 1) * TW + col] = (uint8_t) r;
+			for (int z = Li - 2; z >= 0; --z) {
+				unsigned cand = min(r + 1u, 255u);
+				if (r > 0u) {
+					const int a = z + 1, b = min(z + (int) r, Li - 1);
+					const int k = 31 - __clz(b - a + 1);
+					const uint8_t *Tk = T + (size_t) k * lst;
+					const unsigned w  = min((unsigned) Tk[a * TW + col], (unsigned) Tk[(b - (1 << k) + 1) * TW + col]);
+					if (w <= r) cand = r;
+				}
+				r = min((unsigned) T[z * TW + col], cand);
+				Fl[z * TW + col] = (uint8_t) r;
+			}
+		} else {               // B: towards -z, walking up from the first cell
+			unsigned r = T[col];
+			Bl[col] = (uint8_t) r;
+			for (int z = 1; z < Li; ++z) {
+				unsigned cand = min(r + 1u, 255u);
+				if (r > 0u) {
+					const int b = z - 1, a = max(z - (int) r, 0);
+					const int k = 31 - __clz(b - a + 1);
+					const uint8_t *Tk = T + (size_t) k * lst;
+					const unsigned w  = min((unsigned) Tk[a * TW + col], (unsigned) Tk[(b - (1 << k) + 1) * TW + col]);
+					if (w <= r) cand = r;
+				}
+				r = min((unsigned) T[z * TW + col], cand);
+				Bl[z * TW + col] = (uint8_t) r;
+			}
+		}
+	}
+	__syncthreads();
+	if (!in_x) return;
+	for (uint32_t p = sub; p < L; p += nsub) {
+		const size_t   o = base + (size_t) p * line_stride;
+		const unsigned f = Fl[p * TW + col], b = Bl[p * TW + col];
+		if (MODE == 0) dst0[o] = (uint8_t) min(f, b);
+		else { dst0[o] = (uint8_t) f; dst1[o] = (uint8_t) b; }
+	}
+}
+
 template <int DIR>
 static int run_xpass(const vkv_volume *vol, const uint8_t *O, uint8_t *out, cudaStream_t s)
 {
@@ -353,29 +508,104 @@ static int run_minmax(const vkv_volume *vol, int axis, const uint8_t *src, uint8
 	return VKV_OK;
 }
 
+template <int XDIR>
+static int run_ysweep(const vkv_volume *vol, const uint8_t *g, uint8_t *dst0, uint8_t *dst1, cudaStream_t s, bool *done)
+{
+	const uint32_t Wb = vol->dim_b[0], Hb = vol->dim_b[1], Db = vol->dim_b[2];
+	*done = false;
+	if (Wb > 1024u * kSweepMaxCells || Db > 65535u * 32768u) return VKV_OK;        // fall back to the search kernel
+	const int    threads = (int) std::min<uint32_t>(1024u, (Wb + 31u) / 32u * 32u);
+	const int    nc      = (int) ((Wb + threads - 1) / threads);
+	const size_t smem    = 2 * ((size_t) Wb + 2);
+	switch (nc) {
+		case 1: ysweep_kernel<XDIR, 1><<<Db, threads, smem, s>>>(g, dst0, dst1, Wb, Hb); break;
+		case 2: ysweep_kernel<XDIR, 2><<<Db, threads, smem, s>>>(g, dst0, dst1, Wb, Hb); break;
+		default: ysweep_kernel<XDIR, kSweepMaxCells><<<Db, threads, smem, s>>>(g, dst0, dst1, Wb, Hb); break;
+	}
+	VKV_LAUNCHED();
+	*done = true;
+	return VKV_OK;
+}
+
+// z lines (axis 2); MODE 0 two-sided -> dst0, MODE 3 both one-sided results
+template <int MODE>
+static int run_zwalk(const vkv_volume *vol, const uint8_t *src, uint8_t *dst0, uint8_t *dst1, cudaStream_t s, bool *done)
+{
+	const uint32_t Wb = vol->dim_b[0], Hb = vol->dim_b[1], L = vol->dim_b[2];
+	*done = false;
+	const uint32_t max_window = std::min<uint32_t>(255u, L);
+	int            nlev       = 1;
+	while ((2u << (nlev - 1)) <= max_window) ++nlev;
+	int TW = 64;
+	while (TW > 8 && (size_t) (nlev + 2) * L * TW > (size_t) 100 * 1024) TW >>= 1;
+	const size_t smem = (size_t) (nlev + 2) * L * TW;
+	if (smem > (size_t) 200 * 1024 || Hb > 65535u) return VKV_OK;
+	static bool configured = false;
+	if (!configured) {
+		VKV_CUDA_CHECK(cudaFuncSetAttribute(zwalk_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+		configured = true;
+	}
+	const dim3 grid((Wb + TW - 1) / TW, Hb);
+	zwalk_kernel<MODE><<<grid, 256, smem, s>>>(src, dst0, dst1, Wb, L, (size_t) Wb * Hb, (size_t) Wb, TW, nlev);
+	VKV_LAUNCHED();
+	*done = true;
+	return VKV_OK;
+}
+
 int launch_distance(vkv_volume *vol, int skipping_type, cudaStream_t s)
 {
 	int rc;
 	if (skipping_type == VKV_SKIP_DISTANCE) {
 		uint8_t *map = vol->d_maps[0];        // holds the occupancy map on entry, the distance map on exit
+		const bool legacy = getenv("VKV_DIST_SEARCH") != nullptr;        // A/B switch: the binary-search kernels for every pass
+		bool       done   = false;
 		if ((rc = run_xpass<0>(vol, map, vol->d_tmp, s))) return rc;
-		if ((rc = run_minmax<0, 1>(vol, 1, vol->d_tmp, vol->d_swap, nullptr, s))) return rc;
-		if ((rc = run_minmax<0, 1>(vol, 2, vol->d_swap, map, nullptr, s))) return rc;
+		if (!legacy && (rc = run_ysweep<0>(vol, vol->d_tmp, vol->d_swap, nullptr, s, &done))) return rc;
+		if (!done && (rc = run_minmax<0, 1>(vol, 1, vol->d_tmp, vol->d_swap, nullptr, s))) return rc;
+		done = false;
+		if (!legacy && (rc = run_zwalk<0>(vol, vol->d_swap, map, nullptr, s, &done))) return rc;
+		if (!done && (rc = run_minmax<0, 1>(vol, 2, vol->d_swap, map, nullptr, s))) return rc;
 	} else if (skipping_type == VKV_SKIP_ANISOTROPIC_DISTANCE) {
 		// map index i = 4[x-] + 2[y-] + [z-]  (compute_distance_map.cpp:228-252); occupancy lives in map 7
 		uint8_t *const *m = vol->d_maps.data();
-		// x+ half: maps 0..3
+		const bool legacy = getenv("VKV_DIST_SEARCH") != nullptr;
+		bool       ok_y = false, ok_z = false;
+		// x+ half: maps 0..3.  The y sweep gives both y directions of the same x pass (y+ -> swap, y- -> map 3, which the
+		// last z walk of this half then overwrites in place: a CTA stages its columns before it writes them).
 		if ((rc = run_xpass<1>(vol, m[7], vol->d_tmp, s))) return rc;
-		if ((rc = run_minmax<1, 1>(vol, 1, vol->d_tmp, vol->d_swap, nullptr, s))) return rc;
-		if ((rc = run_minmax<1, 2>(vol, 2, vol->d_swap, m[0], m[1], s))) return rc;
-		if ((rc = run_minmax<-1, 1>(vol, 1, vol->d_tmp, vol->d_swap, nullptr, s))) return rc;
-		if ((rc = run_minmax<1, 2>(vol, 2, vol->d_swap, m[2], m[3], s))) return rc;
-		// x- half: maps 4..7 (map 7 — the occupancy — is overwritten last, as in the reference)
+		if (!legacy && (rc = run_ysweep<1>(vol, vol->d_tmp, vol->d_swap, m[3], s, &ok_y))) return rc;
+		if (ok_y) {
+			if ((rc = run_zwalk<3>(vol, vol->d_swap, m[0], m[1], s, &ok_z))) return rc;
+			if (!ok_z && (rc = run_minmax<1, 2>(vol, 2, vol->d_swap, m[0], m[1], s))) return rc;
+			if (ok_z) { if ((rc = run_zwalk<3>(vol, m[3], m[2], m[3], s, &ok_z))) return rc; }
+			else {
+				VKV_CUDA_CHECK(cudaMemcpyAsync(vol->d_swap, m[3], vol->M, cudaMemcpyDeviceToDevice, s));
+				if ((rc = run_minmax<1, 2>(vol, 2, vol->d_swap, m[2], m[3], s))) return rc;
+			}
+		} else {
+			if ((rc = run_minmax<1, 1>(vol, 1, vol->d_tmp, vol->d_swap, nullptr, s))) return rc;
+			if ((rc = run_minmax<1, 2>(vol, 2, vol->d_swap, m[0], m[1], s))) return rc;
+			if ((rc = run_minmax<-1, 1>(vol, 1, vol->d_tmp, vol->d_swap, nullptr, s))) return rc;
+			if ((rc = run_minmax<1, 2>(vol, 2, vol->d_swap, m[2], m[3], s))) return rc;
+		}
+		// x- half: maps 4..7 (map 7 — the occupancy — is consumed by the x pass and overwritten last, as in the reference)
 		if ((rc = run_xpass<-1>(vol, m[7], vol->d_tmp, s))) return rc;
-		if ((rc = run_minmax<1, 1>(vol, 1, vol->d_tmp, vol->d_swap, nullptr, s))) return rc;
-		if ((rc = run_minmax<1, 2>(vol, 2, vol->d_swap, m[4], m[5], s))) return rc;
-		if ((rc = run_minmax<-1, 1>(vol, 1, vol->d_tmp, vol->d_swap, nullptr, s))) return rc;
-		if ((rc = run_minmax<1, 2>(vol, 2, vol->d_swap, m[6], m[7], s))) return rc;
+		ok_y = ok_z = false;
+		if (!legacy && (rc = run_ysweep<-1>(vol, vol->d_tmp, vol->d_swap, m[7], s, &ok_y))) return rc;
+		if (ok_y) {
+			if ((rc = run_zwalk<3>(vol, vol->d_swap, m[4], m[5], s, &ok_z))) return rc;
+			if (!ok_z && (rc = run_minmax<1, 2>(vol, 2, vol->d_swap, m[4], m[5], s))) return rc;
+			if (ok_z) { if ((rc = run_zwalk<3>(vol, m[7], m[6], m[7], s, &ok_z))) return rc; }
+			else {
+				VKV_CUDA_CHECK(cudaMemcpyAsync(vol->d_swap, m[7], vol->M, cudaMemcpyDeviceToDevice, s));
+				if ((rc = run_minmax<1, 2>(vol, 2, vol->d_swap, m[6], m[7], s))) return rc;
+			}
+		} else {
+			if ((rc = run_minmax<1, 1>(vol, 1, vol->d_tmp, vol->d_swap, nullptr, s))) return rc;
+			if ((rc = run_minmax<1, 2>(vol, 2, vol->d_swap, m[4], m[5], s))) return rc;
+			if ((rc = run_minmax<-1, 1>(vol, 1, vol->d_tmp, vol->d_swap, nullptr, s))) return rc;
+			if ((rc = run_minmax<1, 2>(vol, 2, vol->d_swap, m[6], m[7], s))) return rc;
+		}
 	}
 	// NONE / BLOCK: the occupancy map itself is what the ray caster reads (compute_distance_map.cpp:96-99)
 	return VKV_OK;

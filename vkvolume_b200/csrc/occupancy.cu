@@ -14,6 +14,11 @@
 // block, and a persistent grid (a multiple of the SM count) so the count needs one
 // atomicAdd per CTA.  Algorithmic bytes: 2 B/voxel + 1 B/block (1 B/voxel when the gradient
 // is unused).
+#include <cuda.h>
+
+#include <cstdlib>
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace vkv {
@@ -41,6 +46,24 @@ struct ByteGE {
 	{
 		const unsigned m = (x & 0x7f7f7f7fu) + add;
 		return (m & x) | ((m | x) & or_sel);        // caller masks with 0x80808080
+	}
+};
+
+// The candidate rectangle of a pass: the texture mask's ranges, widened by the analytic mask's when the count is fused.
+struct Prefilter {
+	unsigned vlo, vhi, glo, ghi;
+	bool     none;
+	__device__ __forceinline__ void load(const TFBounds *b, bool use_g, bool count)
+	{
+		const TFRange &t = use_g ? b->tex_all : b->tex_row255;
+		const TFRange &a = use_g ? b->ana_all : b->ana_row255;
+		vlo = t.v_lo; vhi = t.v_hi; glo = t.g_lo; ghi = t.g_hi;
+		bool empty = t.v_lo > t.v_hi;
+		if (count && a.v_lo <= a.v_hi) {
+			if (empty) { vlo = a.v_lo; vhi = a.v_hi; glo = a.g_lo; ghi = a.g_hi; empty = false; }
+			else { vlo = min(vlo, a.v_lo); vhi = max(vhi, a.v_hi); glo = min(glo, a.g_lo); ghi = max(ghi, a.g_hi); }
+		}
+		none = empty;
 	}
 };
 
@@ -77,10 +100,10 @@ __global__ void __launch_bounds__(256) occupancy_fast_kernel(const uint8_t *__re
 	constexpr int BPT = 16 / BS;        // blocks per thread
 	__shared__ uint2    s_mask[kMaskWords];
 	for (int i = threadIdx.x; i < kMaskWords; i += blockDim.x) s_mask[i] = mask2[i];
-	const int      bsel = (USE_G ? 0 : 2) + (COUNT ? 1 : 0);
-	const unsigned vlo = bounds->v_lo[bsel], vhi = bounds->v_hi[bsel];
-	const unsigned glo = bounds->g_lo[bsel], ghi = bounds->g_hi[bsel];
-	const bool     none = vlo > vhi;        // nothing visible anywhere
+	Prefilter pf;
+	pf.load(bounds, USE_G, COUNT);
+	const unsigned vlo = pf.vlo, vhi = pf.vhi, glo = pf.glo, ghi = pf.ghi;
+	const bool     none = pf.none;        // nothing visible anywhere
 	ByteGE         v_ge, v_le, g_ge, g_le;
 	v_ge.set(vlo); v_le.set(255u - vhi); g_ge.set(glo); g_le.set(255u - ghi);
 	const bool need_vlo = vlo > 0u, need_vhi = vhi < 255u, need_glo = USE_G && glo > 0u, need_ghi = USE_G && ghi < 255u;
@@ -184,6 +207,264 @@ __global__ void __launch_bounds__(256) occupancy_fast_kernel(const uint8_t *__re
 	}
 }
 
+// Byte-range membership of the 4 voxels of a (V, G) word pair: bit 7 of every byte of the result is set iff
+// v_lo <= v <= v_hi (and g_lo <= g <= g_hi).  HI = false drops the upper tests (the built-in ramp transfer function
+// never needs them: everything above the threshold is visible).  Branch-free; the caller ANDs with 0x80808080.
+struct RangeTest {
+	ByteGE vge, vle, gge, gle;
+	bool   empty;
+	__device__ __forceinline__ void set(unsigned vlo, unsigned vhi, unsigned glo, unsigned ghi)
+	{
+		empty = vlo > vhi;
+		vge.set(empty ? 0u : vlo); vle.set(empty ? 0u : 255u - vhi); gge.set(empty ? 0u : glo); gle.set(empty ? 0u : 255u - ghi);
+	}
+	template <bool USE_G, bool HI>
+	__device__ __forceinline__ unsigned bits(unsigned v, unsigned g) const
+	{
+		unsigned c = vge.test(v);
+		if (HI) c &= vle.test(~v);
+		if (USE_G) {
+			c &= gge.test(g);
+			if (HI) c &= gle.test(~g);
+		}
+		return c;
+	}
+};
+
+// ---- TMA-staged streaming variant (BS = 4) ------------------------------------------------------------------
+// The register-staged kernel above keeps only 64-128 B per thread in flight and alternates "load" and
+// "classify" phases inside every warp, which leaves HBM at ~40 % of its bandwidth.  Here the loads are taken
+// out of the compute warps entirely: one producer warp streams the 4x4 rows of a block row (1024 voxels of x
+// per task, V and — if used — G) into a ring of shared-memory stages with 1-D bulk TMA copies
+// (cp.async.bulk, completion on an mbarrier), 128-160 KB in flight per SM, and two groups of 256 consumer threads
+// alternate over the stages: each thread owns one 4-voxel word column = exactly one block of the map, reads its
+// 16 (+16) words conflict-free from shared memory, runs the SWAR prefilter + bit-mask lookup and stores one map byte.
+// Persistent grid: one CTA per SM.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+	unsigned ok, spins = 0;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(ok)
+		             : "r"(smem_u32(bar)), "r"(parity)
+		             : "memory");
+		if (!ok && ++spins > (1u << 26)) __trap();        // a lost arrival must surface as an error, never as a hung GPU
+	} while (!ok);
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+	             "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+	             : "memory");
+}
+
+// 3-D tiled TMA: one instruction moves a whole (256 words x 4 rows x 4 slices) box = 16 KB; rows or columns
+// outside the volume are zero-filled by the hardware and still count towards the transaction bytes.
+__device__ __forceinline__ void tma_load_box(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+	                 smem_u32(smem_dst)),
+	             "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+	             : "memory");
+}
+
+constexpr int kTmaXC       = 1024;                   // voxels of x per task
+constexpr int kTmaRows     = 16;                     // 4 x 4 rows of a block row
+constexpr int kTmaConsumers = 512;                   // two groups of 256
+constexpr int kTmaThreads  = kTmaConsumers + 32;     // + one producer warp
+template <bool USE_G> struct TmaCfg {
+	static constexpr int    kStages     = USE_G ? 5 : 10;
+	static constexpr int    kStageBytes = kTmaRows * kTmaXC * (USE_G ? 2 : 1);
+	static constexpr size_t kSmemBytes  = (size_t) kStages * kStageBytes + 2 * kStages * sizeof(uint64_t) + 16;
+};
+
+template <bool USE_G, bool COUNT>
+__global__ void __launch_bounds__(kTmaThreads, 1) occupancy_tma_kernel(const __grid_constant__ CUtensorMap map_v,
+                                                                      const __grid_constant__ CUtensorMap map_g,
+                                                                      const uint2 *__restrict__ mask2, const TFBounds *__restrict__ bounds,
+                                                                      uint32_t W, uint32_t H, uint32_t D, uint32_t Wb, uint32_t Hb,
+                                                                      uint32_t zb_first, uint32_t zb_count, uint8_t *__restrict__ O,
+                                                                      unsigned long long *__restrict__ count)
+{
+	constexpr int BS = 4, S = TmaCfg<USE_G>::kStages;
+	constexpr int kStageBytes = TmaCfg<USE_G>::kStageBytes;
+	extern __shared__ __align__(128) uint8_t s_dyn[];
+	__shared__ uint2              s_mask[kMaskWords];
+	__shared__ unsigned long long s_c[kTmaConsumers / 32];
+	__shared__ uint4              meta[TmaCfg<USE_G>::kStages];
+	uint8_t  *stage_base = s_dyn;
+	uint64_t *full  = reinterpret_cast<uint64_t *>(s_dyn + (size_t) S * kStageBytes);
+	uint64_t *empty = full + S;
+
+	if (threadIdx.x == 0) {
+		for (int i = 0; i < S; ++i) {
+			mbar_init(&full[i], 1);                  // the producer's arrive.expect_tx (+ the bytes)
+			mbar_init(&empty[i], 256 / 32);          // one arrival per consumer warp of the group that read the stage
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	for (int i = threadIdx.x; i < kMaskWords; i += blockDim.x) s_mask[i] = mask2[i];
+	__syncthreads();
+
+	const uint32_t xchunks = (W + kTmaXC - 1) / kTmaXC;
+	const uint32_t ntasks  = xchunks * Hb * zb_count;        // < 2^32 (checked by the launcher)
+	const int      warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+	if (warp == kTmaConsumers / 32) {
+		// ---- producer: one lane issues one box load per array per task ----
+		if (lane == 0) {
+			uint32_t n = 0;
+			for (uint32_t task = blockIdx.x; task < ntasks; task += gridDim.x, ++n) {
+				const int      st = (int) (n % S);
+				const unsigned ph = (n / S) & 1u;
+				if (n >= (uint32_t) S) mbar_wait(&empty[st], ph ^ 1u);        // the consumers released this slot
+				const uint32_t r  = task / xchunks, xc = task - r * xchunks;
+				const uint32_t bq = r / Hb, by = r - bq * Hb, bz = zb_first + bq;
+				uint8_t       *dst = stage_base + (size_t) st * kStageBytes;
+				meta[st] = make_uint4(xc, by, bz, 0u);
+				mbar_arrive_expect_tx(&full[st], (unsigned) kStageBytes);
+				tma_load_box(dst, &map_v, (int) (xc * (kTmaXC / 4)), (int) (by * BS), (int) (bz * BS), &full[st]);
+				if (USE_G) tma_load_box(dst + kTmaRows * kTmaXC, &map_g, (int) (xc * (kTmaXC / 4)), (int) (by * BS), (int) (bz * BS), &full[st]);
+			}
+		}
+		return;
+	}
+
+	// ---- consumers ----
+	const int group = warp >> 3;                 // 0 / 1: stages n with n % 2 == group
+	const int t     = threadIdx.x & 255;         // word column inside the task = block inside the chunk
+	const TFRange tex = USE_G ? bounds->tex_all : bounds->tex_row255;
+	const TFRange ana = USE_G ? bounds->ana_all : bounds->ana_row255;
+	RangeTest rt_tex, rt_sure, rt_ana;
+	rt_tex.set(tex.v_lo, tex.v_hi, tex.g_lo, tex.g_hi);
+	rt_sure.set(tex.v_sure, tex.v_sure < 256u ? 255u : 0u, USE_G ? tex.g_sure : 0u, 255u);
+	rt_ana.set(ana.v_lo, ana.v_hi, ana.g_lo, ana.g_hi);
+	const bool tex_exact = tex.exact != 0u, ana_exact = ana.exact != 0u;
+	// upper tests are only needed when some range stops below 255 (never with the built-in ramp transfer function)
+	const bool need_hi = (!rt_tex.empty && (tex.v_hi < 255u || (USE_G && tex.g_hi < 255u))) ||
+	                     (COUNT && !rt_ana.empty && (ana.v_hi < 255u || (USE_G && ana.g_hi < 255u)));
+
+	unsigned long long local_count = 0;
+	int      st = group;
+	unsigned ph = 0;
+	for (uint32_t task = blockIdx.x + (uint32_t) group * gridDim.x; task < ntasks; task += 2 * gridDim.x) {
+		mbar_wait(&full[st], ph);
+		const uint4    m  = meta[st];        // written by the producer before it armed the barrier: x chunk, block row, block slice
+		const uint32_t by = m.y, bz = m.z;
+		const uint32_t x  = m.x * kTmaXC + (uint32_t) t * 4;
+		const unsigned *sv = reinterpret_cast<const unsigned *>(stage_base + (size_t) st * kStageBytes) + t;
+		const unsigned *sg = sv + kTmaRows * kTmaXC / 4;
+		// words are read straight from the stage (conflict-free: consecutive threads, consecutive words); the slot goes back
+		// to the producer once this warp has classified its columns
+		auto vw = [&](int row) { return sv[row * (kTmaXC / 4)]; };
+		auto gw = [&](int row) { return USE_G ? sg[row * (kTmaXC / 4)] : 0u; };
+		const int      st_used = st;
+		st += 2;
+		if (st >= S) { st -= S; ph ^= 1u; }
+		if (x >= W) {
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&empty[st_used]);
+			continue;
+		}
+		// rows beyond the volume (zero-filled by the TMA) must not be classified: bit r of `rows` = row r exists
+		const uint32_t ny = min((uint32_t) BS, H - by * BS), nz = min((uint32_t) BS, D - bz * BS);
+		const unsigned rows = (ny == BS && nz == BS) ? 0xffffu : (((1u << ny) - 1u) * 0x1111u) & ((1u << (4 * nz)) - 1u);
+		bool     hit = false;
+		unsigned cnt = 0;
+		auto classify = [&](auto hi_tag, auto edge_tag) {
+			constexpr bool HI = decltype(hi_tag)::value, EDGE = decltype(edge_tag)::value;
+			unsigned acc_t = 0, acc_s = 0;
+#pragma unroll
+			for (int row = 0; row < kTmaRows; ++row) {
+				if (EDGE && !((rows >> row) & 1u)) continue;
+				acc_t |= rt_tex.bits<USE_G, HI>(vw(row), gw(row));
+				if (!tex_exact) acc_s |= rt_sure.bits<USE_G, false>(vw(row), gw(row));
+			}
+			acc_t &= 0x80808080u; acc_s &= 0x80808080u;
+			if (rt_tex.empty) acc_t = 0u;
+			if (tex_exact) hit = acc_t != 0u;
+			else {
+				hit = acc_s != 0u && !rt_sure.empty;
+				if (!hit && acc_t) {        // candidates only in the sliver between the sure and the outer rectangle: look them up
+					unsigned dummy = 0;
+#pragma unroll
+					for (int row = 0; row < kTmaRows; ++row) {
+						if (EDGE && !((rows >> row) & 1u)) continue;
+						const unsigned cand = rt_tex.bits<USE_G, HI>(vw(row), gw(row)) & 0x80808080u;
+						if (cand && !hit) classify_word<USE_G, false>(vw(row), gw(row), cand, s_mask, hit, dummy);
+					}
+				}
+			}
+			if (COUNT && !rt_ana.empty) {
+#pragma unroll
+				for (int row = 0; row < kTmaRows; ++row) {
+					if (EDGE && !((rows >> row) & 1u)) continue;
+					const unsigned cand = rt_ana.bits<USE_G, HI>(vw(row), gw(row)) & 0x80808080u;
+					if (ana_exact) cnt += __popc(cand);
+					else if (cand) {
+						bool h = false;
+						classify_word<USE_G, true>(vw(row), gw(row), cand, s_mask, h, cnt);
+					}
+				}
+			}
+		};
+		if (rows == 0xffffu) {
+			if (need_hi) classify(std::true_type{}, std::false_type{});
+			else classify(std::false_type{}, std::false_type{});
+		} else {
+			classify(std::true_type{}, std::true_type{});
+		}
+		__syncwarp();
+		if (lane == 0) mbar_arrive(&empty[st_used]);
+		if (O) O[((size_t) bz * Hb + by) * Wb + (x >> 2)] = hit ? 0 : 255;
+		if (COUNT) local_count += cnt;
+	}
+
+	if (COUNT) {
+		unsigned long long c = local_count;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+		if (lane == 0) s_c[warp] = c;
+		// consumers only (the producer warp has left): named barrier 1 over the 512 consumer threads
+		asm volatile("bar.sync 1, %0;" ::"n"(kTmaConsumers) : "memory");
+		if (threadIdx.x == 0) {
+			unsigned long long tsum = 0;
+			for (int i = 0; i < kTmaConsumers / 32; ++i) tsum += s_c[i];
+			if (tsum) atomicAdd(count, tsum);
+		}
+	}
+}
+
+template <bool USE_G, bool COUNT>
+static int launch_tma_inst(vkv_volume *vol, uint8_t *O, uint32_t zb_first, uint32_t zb_count, unsigned long long *count_dev, cudaStream_t s)
+{
+	static bool configured = false;
+	if (!configured) {
+		VKV_CUDA_CHECK(cudaFuncSetAttribute(occupancy_tma_kernel<USE_G, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		                                    (int) TmaCfg<USE_G>::kSmemBytes));
+		configured = true;
+	}
+	occupancy_tma_kernel<USE_G, COUNT><<<vol->ctx->sm_count, kTmaThreads, TmaCfg<USE_G>::kSmemBytes, s>>>(
+	    *reinterpret_cast<const CUtensorMap *>(vol->tmap_V), *reinterpret_cast<const CUtensorMap *>(USE_G ? vol->tmap_G : vol->tmap_V), vol->d_mask2,
+	    vol->d_bounds, vol->dim[0], vol->dim[1], vol->dim[2], vol->dim_b[0], vol->dim_b[1], zb_first, zb_count, O,
+	    count_dev);
+	VKV_LAUNCHED();
+	return VKV_OK;
+}
+
 // Generic path: any per-axis effective block size, any extents.  One CTA per
 // (block row, block slice, x segment of whole blocks); coalesced byte loads; shared flag array.
 template <bool USE_G, bool COUNT>
@@ -270,6 +551,41 @@ static int launch_fast(vkv_volume *vol, bool use_g, bool count, uint8_t *O, uint
 	return launch_fast_inst<BS, false, false>(vol, O, zb_first, zb_count, count_dev, s);
 }
 
+// Tensor maps over the linear V / G copies viewed as (W/4) x H x D 32-bit words, box 256 x 4 x 4 (SWIZZLE_NONE):
+// the TMA-staged occupancy kernel's loads.  Needs W % 16 == 0; failure just leaves tmap_ok false (register path).
+int make_volume_tensor_maps(vkv_volume *vol)
+{
+	vol->tmap_ok = false;
+	static_assert(sizeof(CUtensorMap) == sizeof(vol->tmap_V), "CUtensorMap size");
+	if (vol->dim[0] % 16 != 0) return VKV_OK;
+	typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+	                              const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+	static encode_fn encode = nullptr;
+	if (!encode) {
+		void                            *fn = nullptr;
+		cudaDriverEntryPointQueryResult  q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+			cudaGetLastError();
+			return VKV_OK;
+		}
+		encode = reinterpret_cast<encode_fn>(fn);
+	}
+	const cuuint64_t gdim[3]    = {vol->dim[0] / 4, vol->dim[1], vol->dim[2]};
+	const cuuint64_t gstride[2] = {(cuuint64_t) vol->dim[0], (cuuint64_t) vol->dim[0] * vol->dim[1]};
+	const cuuint32_t box[3]     = {kTmaXC / 4, 4, 4};
+	const cuuint32_t estr[3]    = {1, 1, 1};
+	uint8_t *bases[2] = {vol->d_V, vol->d_G};
+	unsigned char *maps[2] = {vol->tmap_V, vol->tmap_G};
+	for (int i = 0; i < 2; ++i) {
+		if (!bases[i]) continue;
+		if (encode(reinterpret_cast<CUtensorMap *>(maps[i]), CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, bases[i], gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+		           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+			return VKV_OK;
+	}
+	vol->tmap_ok = true;
+	return VKV_OK;
+}
+
 int launch_occupancy(vkv_volume *vol, bool use_gradient, bool count, uint8_t *O, uint32_t zb_first, uint32_t zb_count,
                      unsigned long long *count_dev, cudaStream_t s)
 {
@@ -281,6 +597,12 @@ int launch_occupancy(vkv_volume *vol, bool use_gradient, bool count, uint8_t *O,
 	const uint64_t fast_tasks = (uint64_t) ((vol->dim[0] + 63) / 64) * vol->dim_b[1] * zb_count;        // upper bound over BS
 	const bool fast  = fast_tasks < (1ull << 32) && cubic && (vol->bs[0] == 2 || vol->bs[0] == 4 || vol->bs[0] == 8) && vol->dim[0] % 16 == 0 &&
 	                  vol->dim_b[0] * vol->bs[0] == vol->dim[0] && (reinterpret_cast<uintptr_t>(vol->d_V) % 16 == 0);
+	if (fast && vol->bs[0] == 4 && vol->tmap_ok && !getenv("VKV_OCC_NO_TMA")) {
+		if (use_g && count) return launch_tma_inst<true, true>(vol, O, zb_first, zb_count, count_dev, s);
+		if (use_g) return launch_tma_inst<true, false>(vol, O, zb_first, zb_count, count_dev, s);
+		if (count) return launch_tma_inst<false, true>(vol, O, zb_first, zb_count, count_dev, s);
+		return launch_tma_inst<false, false>(vol, O, zb_first, zb_count, count_dev, s);
+	}
 	if (fast) {
 		switch (vol->bs[0]) {
 			case 2: return launch_fast<2>(vol, use_g, count, O, zb_first, zb_count, count_dev, grid, s);

@@ -20,6 +20,8 @@
 //   * blend-with-clear, sRGB encode and the RGBA8 store happen in the epilogue; the store
 //     target may be a peer-mapped framebuffer (multi-GPU tile gather fused into the kernel).
 // The march loop is the fragment shader's, statement for statement, in fp32 without contraction.
+#include <cmath>
+
 #include "common.cuh"
 
 namespace vkv {
@@ -29,6 +31,9 @@ struct RayParams {
 	double d0[3], ddx[3], ddy[3];   // far-plane direction of pixel (px,py): d0 + px*ddx + py*ddy
 	double plane[4];                // clip plane, texture space
 	double pvm_z[4], pvm_w[4];      // rows z and w of proj*view*model (depth output)
+	double s0;                      // plane . (o, 1)
+	float  fd0[3], fddx[3], fddy[3], fo[3], fplane[3], fs0;        // fp32 copies for the conservative rejection test
+	float  vol_to_map[3];           // dim / block_size per axis
 	float  cam_pos_tex[3];
 	float  dimf[3];
 	float  block_size[3];
@@ -39,13 +44,14 @@ struct RayParams {
 	int    use_gradient;
 	int    ert, test;
 	int    width, height;
-	int    tile_w, tile_h, tiles_x, tile_first, tile_stride, ctas_per_tile_x, ctas_per_tile, my_tiles;
+	int    tile_w, tile_h, tiles_x, tile_first, tile_stride, my_tiles, seq_base;
+	int    bbox[4];                 // conservative screen bounds (inclusive) of the unit cube: x0, y0, x1, y1
 	cudaTextureObject_t tex_v, tex_g;
 	const uint8_t *V, *G;
 	const uchar4  *tf;
+	const float4  *ctab;            // per TF texel: premultiplied colour + corrected opacity (w < 0: texel alpha byte is 0)
 	const uint8_t *maps;            // map 0; map i at maps_stride * i (anisotropic)
 	const uint8_t *map_ptrs[8];
-	const float   *acorr;           // 256-entry opacity-correction table (built once per (sampling, alpha factor))
 	uint8_t       *rgba8;
 	float         *depth;
 	unsigned long long *counts;     // vkv_sample_counts or null
@@ -79,62 +85,80 @@ __device__ __forceinline__ float srgb_encode(float c) { return c <= 0.0031308f ?
 __device__ __forceinline__ unsigned unorm8(float c) { return (unsigned) (clampf_(c, 0.0f, 1.0f) * 255.0f + 0.5f); }
 
 
-// color.a = clamp(voxel_alpha_factor * (1 - pow(1 - a, 1/sampling_factor)), 0, 1) for the 256 possible TF alpha bytes
-// (volume_render.frag:283).  Built once per (sampling_factor, voxel_alpha_factor) and cached in the volume.
-__global__ void acorr_table_kernel(float *__restrict__ table, float voxel_alpha_factor, float sampling_factor_inv)
+// Per TF texel: the fragment shader's `color` after opacity correction and premultiplication
+// (volume_render.frag:279-285): ca = clamp(voxel_alpha_factor * (1 - pow(1 - a, 1/sampling_factor)), 0, 1),
+// rgb = (byte / 255) * ca.  w = -1 marks texels whose alpha byte is 0 (voxel_occupied = false).
+// Built once per (TF texture, sampling_factor, voxel_alpha_factor) and cached in the volume: one 16-byte
+// read-only load replaces the RGBA8 load, four UNORM decodes, the pow() and three multiplies per sample.
+__global__ void __launch_bounds__(256) ctab_kernel(const uchar4 *__restrict__ tf, float4 *__restrict__ ctab, float voxel_alpha_factor,
+                                                   float sampling_factor_inv)
 {
-	const float a      = (float) threadIdx.x / 255.0f;
-	table[threadIdx.x] = clampf_(voxel_alpha_factor * (1.0f - powf(1.0f - a, sampling_factor_inv)), 0.0f, 1.0f);
+	const int    idx = blockIdx.x * blockDim.x + threadIdx.x;
+	const uchar4 tx  = tf[idx];
+	float4       e   = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
+	if (tx.w > 0) {
+		const float a  = (float) tx.w / 255.0f;
+		const float ca = clampf_(voxel_alpha_factor * (1.0f - powf(1.0f - a, sampling_factor_inv)), 0.0f, 1.0f);
+		e = make_float4(((float) tx.x / 255.0f) * ca, ((float) tx.y / 255.0f) * ca, ((float) tx.z / 255.0f) * ca, ca);
+	}
+	ctab[idx] = e;
 }
 
 #ifndef VKV_RC_MIN_CTAS
 #define VKV_RC_MIN_CTAS 16
 #endif
 // A CTA is two warps = a 16x4 pixel tile; small CTAs keep the register file busy while long rays finish.
+// grid = (CTAs per tile in x, CTAs per tile in y, tiles of this launch).
 template <int SKIP, bool EXACT, bool COUNT>
 __global__ void __launch_bounds__(64, VKV_RC_MIN_CTAS) raycast_kernel(const __grid_constant__ RayParams P)
 {
-	__shared__ float s_acorr[256];        // opacity correction per TF alpha byte (volume_render.frag:283)
 	__shared__ unsigned long long s_cnt[2][4];
-	for (int k = threadIdx.x; k < 256; k += blockDim.x) s_acorr[k] = __ldg(P.acorr + k);
-	__syncthreads();
 
 	// CTA -> tile -> pixel
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	// Tiles are issued from the middle of this launch's tile list outwards (m, m-1, m+1, m-2, ...): the long rays sit
 	// near the image centre, so their latency chains start at t = 0 and the cheap border tiles fill the tail.
-	const int seq = blockIdx.x / P.ctas_per_tile, in_tile = blockIdx.x % P.ctas_per_tile;
+	const int seq        = P.seq_base + (int) blockIdx.z;
 	const int local_tile = P.my_tiles / 2 + ((seq & 1) ? -((seq + 1) >> 1) : (seq >> 1));
-	const int tile = P.tile_first + local_tile * P.tile_stride;
-	const int tx0 = (tile % P.tiles_x) * P.tile_w + (in_tile % P.ctas_per_tile_x) * 16;
-	const int ty0 = (tile / P.tiles_x) * P.tile_h + (in_tile / P.ctas_per_tile_x) * 4;
+	const int tile       = P.tile_first + local_tile * P.tile_stride;
+	const int tile_y = tile / P.tiles_x, tile_x = tile - tile_y * P.tiles_x;
+	const int tx0 = tile_x * P.tile_w + (int) blockIdx.x * 16;
+	const int ty0 = tile_y * P.tile_h + (int) blockIdx.y * 4;
 	const int px = tx0 + warp * 8 + (lane & 7);
 	const int py = ty0 + (lane >> 3);
-	const bool in_frame = px < P.width && py < P.height && px < (tile % P.tiles_x) * P.tile_w + P.tile_w &&
-	                      py < (tile / P.tiles_x) * P.tile_h + P.tile_h;
+	const bool   in_frame = px < P.width && py < P.height;
+	const size_t p        = (size_t) py * P.width + px;
+
+	// CTA-uniform rejection against the projected bounds of the unit cube: such pixels keep the clear colour
+	// (0,0,0,1) (render_pipeline.cpp:38) and depth 0.
+	if (tx0 > P.bbox[2] || tx0 + 15 < P.bbox[0] || ty0 > P.bbox[3] || ty0 + 3 < P.bbox[1]) {
+		if (in_frame) {
+			reinterpret_cast<unsigned *>(P.rgba8)[p] = 0xff000000u;
+			if (P.depth) P.depth[p] = 0.0f;
+		}
+		return;
+	}
 
 	unsigned n_vol = 0, n_dist = 0, n_empty = 0, covered = 0;
 	float    out[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 	float    frag_depth = 0.0f;
-	float    r = 0.0f, g = 0.0f, b = 0.0f, a = 1.0f;        // clear colour (0,0,0,1)  (render_pipeline.cpp:38)
 
 	if (in_frame) {
 		// ---- analytic ray entry (replaces both vertex shaders + rasteriser) ----
-		// (1) conservative fp32 rejection: two thirds of a typical frame miss the box, skip the fp64 work there
-		bool maybe = true;
-		{
+		// (1) conservative fp32 rejection (approximate divisions; only ever used to say "certainly misses")
+		bool maybe = px >= P.bbox[0] && px <= P.bbox[2] && py >= P.bbox[1] && py <= P.bbox[3];
+		if (maybe) {
 			float tnf = -INFINITY, tff = INFINITY, sdf = 0.0f;
 #pragma unroll
 			for (int k = 0; k < 3; ++k) {
-				const float dk = (float) P.d0[k] + (float) px * (float) P.ddx[k] + (float) py * (float) P.ddy[k];
-				const float ok = (float) P.o[k];
-				const float a0 = (0.0f - ok) / dk, a1 = (1.0f - ok) / dk;
+				const float dk = P.fd0[k] + (float) px * P.fddx[k] + (float) py * P.fddy[k];
+				const float rk = __fdividef(1.0f, dk);
+				const float a0 = (0.0f - P.fo[k]) * rk, a1 = (1.0f - P.fo[k]) * rk;
 				tnf = fmaxf(tnf, fminf(a0, a1));
 				tff = fminf(tff, fmaxf(a0, a1));
-				sdf += (float) P.plane[k] * dk;
+				sdf += P.fplane[k] * dk;
 			}
-			const float s0f = (float) P.plane[0] * (float) P.o[0] + (float) P.plane[1] * (float) P.o[1] + (float) P.plane[2] * (float) P.o[2] + (float) P.plane[3];
-			const float t0f = fmaxf(fmaxf(tnf, -s0f / sdf), 0.0f);
+			const float t0f = fmaxf(fmaxf(tnf, __fdividef(-P.fs0, sdf)), 0.0f);
 			// reject only when the miss is far outside fp32 rounding (relative 1e-3); NaNs fall through to fp64
 			if (t0f > tff + 1e-3f * (fabsf(tff) + fabsf(t0f)) + 1e-6f) maybe = false;
 		}
@@ -155,10 +179,9 @@ __global__ void __launch_bounds__(64, VKV_RC_MIN_CTAS) raycast_kernel(const __gr
 					if (t1 < tf) tf = t1;
 				}
 			}
-			const double s0 = P.plane[0] * P.o[0] + P.plane[1] * P.o[1] + P.plane[2] * P.o[2] + P.plane[3];
 			const double sd = P.plane[0] * d[0] + P.plane[1] * d[1] + P.plane[2] * d[2];
 			if (hit && sd > 0.0) {
-				const double t_clip = -s0 / sd;
+				const double t_clip = -P.s0 / sd;
 				double       t0     = tn > t_clip ? tn : t_clip;
 				if (t0 < 0.0) t0 = 0.0;
 				if (t0 < tf) {
@@ -202,21 +225,21 @@ __global__ void __launch_bounds__(64, VKV_RC_MIN_CTAS) raycast_kernel(const __gr
 					if (!(t > 0.0f && t < 1.0f)) inside = false;        // lessThanEqual 0 / greaterThanEqual 1 / NaN
 				}
 				if (inside) {
-					float vol_to_map[3], sdt_inv[3];
-					int   dim_map_1[3];
+					float sdt_inv[3];
 #pragma unroll
 					for (int k = 0; k < 3; ++k) {
-						vol_to_map[k]   = P.dimf[k] / P.block_size[k];
-						dim_map_1[k]    = P.dim_b[k] - 1;
 						const float sdt = step[k] * P.dimf[k] / P.block_size[k];
 						sdt_inv[k]      = 1.0f / sdt;
 					}
 					const uint8_t *__restrict__ Dm = P.map_ptrs[0];
 					if (SKIP == VKV_SKIP_ANISOTROPIC_DISTANCE)
 						Dm = P.map_ptrs[(dir[2] < 0 ? 1 : 0) + (dir[1] < 0 ? 2 : 0) + (dir[0] < 0 ? 4 : 0)];
-					int  i_min = 0, u_last[3] = {0, 0, 0};
-					bool voxel_occupied = true;
-					int  i_first_hit    = n_steps;
+					// u_last of the shader, kept as the linear index of the block (the map has < 2^32 blocks, so the
+					// index identifies the block); it starts at block (0,0,0) (volume_render.frag:197)
+					unsigned idx_last = 0u;
+					int      i_min    = 0;
+					bool     voxel_occupied = true;
+					int      i_first_hit    = n_steps;
 					const int back = (int) ceilf(P.sampling_factor);
 					// look-ahead cache of hardware-filtered samples i .. i+3: consecutive volume samples are the common case
 					// inside occupied regions, and one batch of independent fetches replaces four dependent round trips
@@ -225,20 +248,22 @@ __global__ void __launch_bounds__(64, VKV_RC_MIN_CTAS) raycast_kernel(const __gr
 					for (int i = 0; i < n_steps;) {
 						const float fi     = (float) i;
 						const float pos[3] = {entry[0] + fi * step[0], entry[1] + fi * step[1], entry[2] + fi * step[2]};
-						float u[3];
-						int   u_i[3] = {0, 0, 0};
-						bool  do_skip = false;
+						float    u[3];
+						int      u_i[3] = {0, 0, 0};
+						unsigned idx    = 0u;
+						bool     do_skip = false;
 						if (SKIP != VKV_SKIP_NONE) {
 #pragma unroll
 							for (int k = 0; k < 3; ++k) {
-								u[k]   = vol_to_map[k] * pos[k];
-								u_i[k] = clampi_((int) u[k], 0, dim_map_1[k]);
+								u[k]   = P.vol_to_map[k] * pos[k];
+								u_i[k] = clampi_((int) u[k], 0, P.dim_b[k] - 1);
 							}
-							do_skip = !voxel_occupied && (u_i[0] != u_last[0] || u_i[1] != u_last[1] || u_i[2] != u_last[2]);
+							idx     = ((unsigned) u_i[2] * (unsigned) P.dim_b[1] + (unsigned) u_i[1]) * (unsigned) P.dim_b[0] + (unsigned) u_i[0];
+							do_skip = !voxel_occupied && idx != idx_last;
 						}
 						if (SKIP != VKV_SKIP_NONE && do_skip) {
 							++n_dist;
-							const unsigned dist = __ldg(Dm + ((size_t) u_i[2] * P.dim_b[1] + (size_t) u_i[1]) * P.dim_b[0] + (size_t) u_i[0]);
+							const unsigned dist = __ldg(Dm + idx);
 							if (dist > 0u) {
 								float dxyz[3];
 #pragma unroll
@@ -258,8 +283,8 @@ __global__ void __launch_bounds__(64, VKV_RC_MIN_CTAS) raycast_kernel(const __gr
 								i += i_delta;
 							} else {
 								voxel_occupied = true;
-								u_last[0] = u_i[0]; u_last[1] = u_i[1]; u_last[2] = u_i[2];
-								i = max(i - back, i_min);
+								idx_last       = idx;
+								i              = max(i - back, i_min);
 							}
 						} else {
 							++n_vol;
@@ -290,15 +315,13 @@ __global__ void __launch_bounds__(64, VKV_RC_MIN_CTAS) raycast_kernel(const __gr
 								intensity = k == 0 ? pre_v0 : (k == 1 ? pre_v1 : (k == 2 ? pre_v2 : pre_v3));
 								if (P.use_gradient) gradient = k == 0 ? pre_g0 : (k == 1 ? pre_g1 : (k == 2 ? pre_g2 : pre_g3));
 							}
-							const uchar4 tx = __ldg(P.tf + tf_texel(gradient) * 256 + tf_texel(intensity));
-							voxel_occupied  = tx.w > 0;
+							const float4 c = __ldg(P.ctab + tf_texel(gradient) * 256 + tf_texel(intensity));
+							voxel_occupied = c.w >= 0.0f;
 							if (voxel_occupied) {
-								if (SKIP != VKV_SKIP_NONE) { u_last[0] = u_i[0]; u_last[1] = u_i[1]; u_last[2] = u_i[2]; }
-								const float ca = s_acorr[tx.w];
-								const float c0 = ((float) tx.x / 255.0f) * ca, c1 = ((float) tx.y / 255.0f) * ca, c2 = ((float) tx.z / 255.0f) * ca;
-								const float w  = 1.0f - out[3];
-								out[0] = out[0] + w * c0; out[1] = out[1] + w * c1; out[2] = out[2] + w * c2; out[3] = out[3] + w * ca;
-								if (ca > 0.0f) i_first_hit = i;
+								if (SKIP != VKV_SKIP_NONE) idx_last = idx;
+								const float w = 1.0f - out[3];
+								out[0] = out[0] + w * c.x; out[1] = out[1] + w * c.y; out[2] = out[2] + w * c.z; out[3] = out[3] + w * c.w;
+								if (c.w > 0.0f) i_first_hit = i;
 								if (out[3] > 0.99f && P.ert) {
 									out[3] = 1.0f;
 									break;
@@ -326,14 +349,13 @@ __global__ void __launch_bounds__(64, VKV_RC_MIN_CTAS) raycast_kernel(const __gr
 					}
 				}
 			}
-			// blend with the clear colour: rgb = src.rgb + dst.rgb*(1-src.a), a = src.a*(1-src.a) + dst.a*0
-			r = out[0]; g = out[1]; b = out[2];
-			a = out[3] * (1.0f - out[3]);
 		}
-		// R8G8B8A8_SRGB store
-		const unsigned packed = unorm8(srgb_encode(clampf_(r, 0.0f, 1.0f))) | (unorm8(srgb_encode(clampf_(g, 0.0f, 1.0f))) << 8) |
-		                        (unorm8(srgb_encode(clampf_(b, 0.0f, 1.0f))) << 16) | (unorm8(a) << 24);
-		const size_t p = (size_t) py * P.width + px;
+		// blend with the clear colour (0,0,0,1): rgb = src.rgb + dst.rgb*(1-src.a), a = src.a*(1-src.a) + dst.a*0;
+		// R8G8B8A8_SRGB store.  Uncovered pixels keep the clear colour.
+		unsigned packed = 0xff000000u;
+		if (covered)
+			packed = unorm8(srgb_encode(clampf_(out[0], 0.0f, 1.0f))) | (unorm8(srgb_encode(clampf_(out[1], 0.0f, 1.0f))) << 8) |
+			         (unorm8(srgb_encode(clampf_(out[2], 0.0f, 1.0f))) << 16) | (unorm8(out[3] * (1.0f - out[3])) << 24);
 		reinterpret_cast<unsigned *>(P.rgba8)[p] = packed;
 		if (P.depth) P.depth[p] = frag_depth;
 	}
@@ -384,10 +406,46 @@ static void far_dir(const vkv_camera_uniform *cam, const vkv_ray_cast_uniform *r
 	for (int k = 0; k < 3; ++k) d[k] = mp[k] + 0.5 - (double) ray->cam_pos_tex[k];
 }
 
+// Conservative screen-space bounds (pixel indices, inclusive) of the unit cube [0,1]^3 in texture space.
+// A pixel (px, py) looks along d0 + px*ddx + py*ddy; corner c is seen at the pixel solving
+// [ddx ddy d0] (l*px, l*py, l)^T = c - o with l > 0.  Any corner at or behind the camera plane, a camera
+// inside the cube or a degenerate basis fall back to the whole frame.
+static void screen_bbox(const RayParams &P, int width, int height, int out[4])
+{
+	out[0] = 0; out[1] = 0; out[2] = width - 1; out[3] = height - 1;
+	const double eps = 1e-6;
+	if (P.o[0] >= -eps && P.o[0] <= 1 + eps && P.o[1] >= -eps && P.o[1] <= 1 + eps && P.o[2] >= -eps && P.o[2] <= 1 + eps) return;
+	const double a[3] = {P.ddx[0], P.ddx[1], P.ddx[2]}, b[3] = {P.ddy[0], P.ddy[1], P.ddy[2]}, c[3] = {P.d0[0], P.d0[1], P.d0[2]};
+	const double bc[3] = {b[1] * c[2] - b[2] * c[1], b[2] * c[0] - b[0] * c[2], b[0] * c[1] - b[1] * c[0]};
+	const double ca[3] = {c[1] * a[2] - c[2] * a[1], c[2] * a[0] - c[0] * a[2], c[0] * a[1] - c[1] * a[0]};
+	const double ab[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+	const double det   = a[0] * bc[0] + a[1] * bc[1] + a[2] * bc[2];
+	const double scale = (std::fabs(a[0]) + std::fabs(a[1]) + std::fabs(a[2])) * (std::fabs(b[0]) + std::fabs(b[1]) + std::fabs(b[2])) *
+	                     (std::fabs(c[0]) + std::fabs(c[1]) + std::fabs(c[2]));
+	if (!(std::fabs(det) > 1e-12 * scale)) return;
+	double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+	for (int corner = 0; corner < 8; ++corner) {
+		const double r[3] = {(corner & 1 ? 1.0 : 0.0) - P.o[0], (corner & 2 ? 1.0 : 0.0) - P.o[1], (corner & 4 ? 1.0 : 0.0) - P.o[2]};
+		const double lx = (r[0] * bc[0] + r[1] * bc[1] + r[2] * bc[2]) / det;
+		const double ly = (r[0] * ca[0] + r[1] * ca[1] + r[2] * ca[2]) / det;
+		const double l  = (r[0] * ab[0] + r[1] * ab[1] + r[2] * ab[2]) / det;
+		if (!(l > 1e-9)) return;        // corner not strictly in front of the camera: no finite bound
+		const double x = lx / l, y = ly / l;
+		xmin = std::fmin(xmin, x); xmax = std::fmax(xmax, x);
+		ymin = std::fmin(ymin, y); ymax = std::fmax(ymax, y);
+	}
+	if (!(std::isfinite(xmin) && std::isfinite(xmax) && std::isfinite(ymin) && std::isfinite(ymax))) return;
+	// one pixel of slack on every side for rounding; an off-screen cube gives an empty rectangle
+	const double x0 = std::floor(xmin) - 1.0, x1 = std::ceil(xmax) + 1.0, y0 = std::floor(ymin) - 1.0, y1 = std::ceil(ymax) + 1.0;
+	out[0] = (int) std::fmax(x0, 0.0); out[2] = (int) std::fmin(x1, (double) width - 1.0);
+	out[1] = (int) std::fmax(y0, 0.0); out[3] = (int) std::fmin(y1, (double) height - 1.0);
+	if (x1 < 0.0 || y1 < 0.0 || x0 > width - 1.0 || y0 > height - 1.0) { out[0] = 1; out[2] = 0; out[1] = 1; out[3] = 0; }
+}
+
 int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_cast_uniform *ray,
                   const vkv_transfer_function_uniform *tfu, const vkv_render_options *opt, int width, int height, int tile_w,
-                  int tile_h, int tile_first, int tile_stride, uint8_t *rgba8, float *depth, vkv_sample_counts *counts,
-                  cudaStream_t s)
+                  int tile_h, int tile_first, int tile_stride, int tile_limit, uint8_t *rgba8, float *depth,
+                  vkv_sample_counts *counts, cudaStream_t s)
 {
 	RayParams P{};
 	double    dx1[3], dy1[3];
@@ -403,8 +461,21 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 		P.dim[k]         = (int) vol->dim[k];
 		P.dim_b[k]       = (int) vol->dim_b[k];
 		P.block_size[k]  = ray->block_size[k];
+		P.vol_to_map[k]  = P.dimf[k] / P.block_size[k];
+		P.fd0[k] = (float) P.d0[k]; P.fddx[k] = (float) P.ddx[k]; P.fddy[k] = (float) P.ddy[k];
+		P.fo[k]  = (float) P.o[k];
+		P.fplane[k] = ray->plane_tex[k];
 	}
 	for (int k = 0; k < 4; ++k) P.plane[k] = ray->plane_tex[k];
+	{
+		// same operation order as the per-pixel evaluation used to have (no contraction)
+		volatile double t = P.plane[0] * P.o[0];
+		t = t + P.plane[1] * P.o[1];
+		t = t + P.plane[2] * P.o[2];
+		t = t + P.plane[3];
+		P.s0  = t;
+		P.fs0 = P.fplane[0] * P.fo[0] + P.fplane[1] * P.fo[1] + P.fplane[2] * P.fo[2] + ray->plane_tex[3];
+	}
 	{
 		double pr[16], vw[16], md[16], pv[16], pvm[16];
 		for (int i = 0; i < 16; ++i) { pr[i] = cam->proj[i]; vw[i] = cam->view[i]; md[i] = cam->model[i]; }
@@ -426,19 +497,22 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 	const int tiles_y = (height + tile_h - 1) / tile_h;
 	const int n_tiles = P.tiles_x * tiles_y;
 	P.tile_first = tile_first; P.tile_stride = tile_stride;
-	P.ctas_per_tile_x = tile_w / 16;
-	P.ctas_per_tile   = P.ctas_per_tile_x * (tile_h / 4);
-	const int my_tiles = tile_first < n_tiles ? (n_tiles - tile_first + tile_stride - 1) / tile_stride : 0;
+	int my_tiles = tile_first < n_tiles ? (n_tiles - tile_first + tile_stride - 1) / tile_stride : 0;
+	if (tile_limit >= 0 && my_tiles > tile_limit) my_tiles = tile_limit;
 	if (my_tiles == 0) return VKV_OK;
 	P.my_tiles = my_tiles;
-	if (!vol->d_acorr) VKV_CUDA_CHECK(cudaMalloc(&vol->d_acorr, 256 * sizeof(float)));
-	if (vol->acorr_sampling != tfu->sampling_factor || vol->acorr_alpha != tfu->voxel_alpha_factor) {
-		acorr_table_kernel<<<1, 256, 0, s>>>(vol->d_acorr, tfu->voxel_alpha_factor, 1.0f / tfu->sampling_factor);
+	screen_bbox(P, width, height, P.bbox);
+	// premultiplied colour table: rebuilt when the TF texture, the sampling factor or the alpha factor changed
+	if (!vol->d_ctab) VKV_CUDA_CHECK(cudaMalloc(&vol->d_ctab, 256 * 256 * sizeof(float4)));
+	if (vol->ctab_tf_version != vol->tf_version || vol->ctab_sampling != tfu->sampling_factor || vol->ctab_alpha != tfu->voxel_alpha_factor) {
+		ctab_kernel<<<256, 256, 0, s>>>(reinterpret_cast<const uchar4 *>(vol->d_tf), reinterpret_cast<float4 *>(vol->d_ctab),
+		                                tfu->voxel_alpha_factor, 1.0f / tfu->sampling_factor);
 		VKV_LAUNCHED();
-		vol->acorr_sampling = tfu->sampling_factor;
-		vol->acorr_alpha    = tfu->voxel_alpha_factor;
+		vol->ctab_tf_version = vol->tf_version;
+		vol->ctab_sampling   = tfu->sampling_factor;
+		vol->ctab_alpha      = tfu->voxel_alpha_factor;
 	}
-	P.acorr = vol->d_acorr;
+	P.ctab  = reinterpret_cast<const float4 *>(vol->d_ctab);
 	P.tex_v = vol->t_V; P.tex_g = vol->t_G;
 	P.V = vol->d_V; P.G = vol->d_G;
 	P.tf = reinterpret_cast<const uchar4 *>(vol->d_tf);
@@ -448,23 +522,27 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 	P.depth  = depth;
 	P.counts = reinterpret_cast<unsigned long long *>(counts);
 
-	const long long grid = (long long) my_tiles * P.ctas_per_tile;
-	const bool      exact = opt->filter == VKV_FILTER_EXACT;
-#define VKV_RC(SK)                                                                                  \
-	do {                                                                                            \
-		if (exact && counts) raycast_kernel<SK, true, true><<<(unsigned) grid, 64, 0, s>>>(P);       \
-		else if (exact) raycast_kernel<SK, true, false><<<(unsigned) grid, 64, 0, s>>>(P);           \
-		else if (counts) raycast_kernel<SK, false, true><<<(unsigned) grid, 64, 0, s>>>(P);          \
-		else raycast_kernel<SK, false, false><<<(unsigned) grid, 64, 0, s>>>(P);                     \
+	const bool exact = opt->filter == VKV_FILTER_EXACT;
+	// gridDim.z is limited to 65535: launch the tile list in chunks (one chunk up to 134 Mpixel with 64x32 tiles)
+	for (int base = 0; base < my_tiles; base += 65535) {
+		P.seq_base = base;
+		const dim3 grid((unsigned) (tile_w / 16), (unsigned) (tile_h / 4), (unsigned) std::min(65535, my_tiles - base));
+#define VKV_RC(SK)                                                                      \
+	do {                                                                                \
+		if (exact && counts) raycast_kernel<SK, true, true><<<grid, 64, 0, s>>>(P);      \
+		else if (exact) raycast_kernel<SK, true, false><<<grid, 64, 0, s>>>(P);          \
+		else if (counts) raycast_kernel<SK, false, true><<<grid, 64, 0, s>>>(P);         \
+		else raycast_kernel<SK, false, false><<<grid, 64, 0, s>>>(P);                    \
 	} while (0)
-	switch (opt->skipping_type) {
-		case VKV_SKIP_NONE: VKV_RC(VKV_SKIP_NONE); break;
-		case VKV_SKIP_BLOCK: VKV_RC(VKV_SKIP_BLOCK); break;
-		case VKV_SKIP_DISTANCE: VKV_RC(VKV_SKIP_DISTANCE); break;
-		default: VKV_RC(VKV_SKIP_ANISOTROPIC_DISTANCE); break;
-	}
+		switch (opt->skipping_type) {
+			case VKV_SKIP_NONE: VKV_RC(VKV_SKIP_NONE); break;
+			case VKV_SKIP_BLOCK: VKV_RC(VKV_SKIP_BLOCK); break;
+			case VKV_SKIP_DISTANCE: VKV_RC(VKV_SKIP_DISTANCE); break;
+			default: VKV_RC(VKV_SKIP_ANISOTROPIC_DISTANCE); break;
+		}
 #undef VKV_RC
-	VKV_LAUNCHED();
+		VKV_LAUNCHED();
+	}
 	return VKV_OK;
 }
 
