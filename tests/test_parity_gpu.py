@@ -112,6 +112,26 @@ def test_gradient_byte_exact(ctx, shape):
     vol.close()
 
 
+@pytest.mark.parametrize("kind", ["noise", "smooth_ties", "low_noise"])
+def test_gradient_integer_path_byte_exact(ctx, kind):
+    """The integer (dp4a) gradient kernel against the oracle on inputs that stress its tie handling: full-range noise,
+    a smooth ramp whose gradients sit exactly on rounding boundaries, and +-2 noise (many S == (4n+2)^2 ties)."""
+    D, H, W = 37, 45, 160        # W % 16 == 0 -> the vectorised integer kernel
+    rng = np.random.default_rng(123)
+    if kind == "noise":
+        V = rng.integers(0, 256, size=(D, H, W), dtype=np.uint8)
+    elif kind == "smooth_ties":
+        z, y, x = np.meshgrid(np.arange(D), np.arange(H), np.arange(W), indexing="ij")
+        V = ((2 * x + 4 * y + 6 * z) % 256).astype(np.uint8)
+    else:
+        V = (128 + rng.integers(-2, 3, size=(D, H, W))).astype(np.uint8)
+    vol = capi.Volume(ctx, W, H, D)
+    vol.upload(V)
+    vol.compute_gradient_map(capi.transfer_function_uniform(VolumeOptions(gradient_min=0.0, gradient_max=0.2)))
+    assert np.array_equal(vol.download_gradient(), orc.gradient_map(V))
+    vol.close()
+
+
 # ---- K2a / K2b -----------------------------------------------------------------------------------------
 @pytest.mark.parametrize("shape,bs", [((16, 16, 32), 4), ((9, 10, 13), 4), ((24, 20, 48), 4), ((12, 12, 32), 2), ((16, 24, 64), 8),
                                       ((7, 9, 10), 3), ((15, 11, 48), 5), ((10, 10, 10), 1), ((6, 6, 6), 8), ((33, 17, 80), 4),

@@ -145,8 +145,14 @@ int vkv_volume_create(vkv_context *ctx, uint32_t width, uint32_t height, uint32_
 	if (make_texture(vol->a_V, &vol->t_V)) { vkv_volume_destroy(vol); return VKV_ERR_CUDA; }
 	if (vol->precomputed_gradient) {
 		if ((e = cudaMalloc(&vol->d_G, vol->N)) != cudaSuccess) return fail(e, "cudaMalloc(G)");
-		if ((e = cudaMalloc3DArray(&vol->a_G, &fd, ext)) != cudaSuccess) return fail(e, "cudaMalloc3DArray(G)");
+		if ((e = cudaMalloc3DArray(&vol->a_G, &fd, ext, cudaArraySurfaceLoadStore)) != cudaSuccess) return fail(e, "cudaMalloc3DArray(G)");
 		if (make_texture(vol->a_G, &vol->t_G)) { vkv_volume_destroy(vol); return VKV_ERR_CUDA; }
+		{
+			cudaResourceDesc rd{};
+			rd.resType         = cudaResourceTypeArray;
+			rd.res.array.array = vol->a_G;
+			if ((e = cudaCreateSurfaceObject(&vol->s_G, &rd)) != cudaSuccess) return fail(e, "cudaCreateSurfaceObject(G)");
+		}
 	}
 	make_volume_tensor_maps(vol);
 	if ((e = cudaMalloc(&vol->d_tf, 256 * 256 * 4)) != cudaSuccess) return fail(e, "cudaMalloc(tf)");
@@ -167,6 +173,7 @@ void vkv_volume_destroy(vkv_volume *vol)
 	DeviceGuard guard(vol->ctx->device);
 	if (vol->t_V) cudaDestroyTextureObject(vol->t_V);
 	if (vol->t_G) cudaDestroyTextureObject(vol->t_G);
+	if (vol->s_G) cudaDestroySurfaceObject(vol->s_G);
 	if (vol->a_V) cudaFreeArray(vol->a_V);
 	if (vol->a_G) cudaFreeArray(vol->a_G);
 	cudaFree(vol->d_V); cudaFree(vol->d_G); cudaFree(vol->d_tf); cudaFree(vol->d_mask2); cudaFree(vol->d_bounds); cudaFree(vol->d_tf_rows);
@@ -300,7 +307,7 @@ int vkv_compute_gradient_map(vkv_volume *vol, const vkv_transfer_function_unifor
 	int          rc;
 	// quirk A.8.1: the map is all 1.0 when use_gradient is false at this moment
 	if ((rc = launch_gradient(vol, tfu->use_gradient != 0, tfu->grad_magnitude_modifier, s))) return rc;
-	return sync_arrays_from_linear(vol, true, s);
+	return vol->G_array_synced ? VKV_OK : sync_arrays_from_linear(vol, true, s);
 }
 
 static int ensure_analytic_mask(vkv_volume *vol, const vkv_transfer_function_uniform *tfu, cudaStream_t s)
@@ -445,7 +452,7 @@ int vkv_render_to_host(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv
                        uint8_t *rgba8_host, vkv_sample_counts *counts_host, void *stream)
 {
 	VKV_REQUIRE(vol && cam && ray && tfu && opt && rgba8_host, VKV_ERR_ARGUMENT, "vkv_render_to_host: NULL argument");
-	constexpr int TW = 64, TH = 32, kBands = 6;
+	constexpr int TW = 64, TH = 32, kBands = 1;        // measured on B200: cross-stream band overlap costs more than it hides (scripts/e2e_probe.py)
 	int rc;
 	if ((rc = check_render(vol, tfu, opt, width, height, TW, TH, 1))) return rc;
 	DeviceGuard  guard(vol->ctx->device);

@@ -85,6 +85,8 @@ struct vkv_volume {
 	uint8_t *d_G = nullptr;        // linear gradient
 	cudaArray_t         a_V = nullptr, a_G = nullptr;        // 3D arrays (K4 samples these)
 	cudaTextureObject_t t_V = 0, t_G = 0;
+	cudaSurfaceObject_t s_G = 0;                     // surface over a_G: the gradient kernel stores into the array directly
+	bool                G_array_synced = false;      // set by launch_gradient when the array needs no copy from d_G
 	bool     has_V = false, has_G = false;
 
 	uint8_t        *d_tf      = nullptr;        // 256*256 RGBA8

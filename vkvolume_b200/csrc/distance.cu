@@ -317,68 +317,115 @@ __global__ void __launch_bounds__(256) minmax_rmq_kernel(const uint8_t *__restri
 // quadrant), and keep the two sweep directions as two outputs (sources at y' >= y -> dst0, y' <= y -> dst1).
 // One CTA per z slice; thread t owns cells t, t + T, ...; the previous row lives in shared memory (double-buffered,
 // one __syncthreads per row); the rows of the input are prefetched eight at a time.
-constexpr int kSweepMaxCells = 4;        // cells per thread: rows up to 4096 cells
-template <int XDIR, int NC>              // XDIR 0: isotropic (two-sided x, 3 neighbours, in-place second sweep); +-1: one-sided
+__device__ __forceinline__ uint32_t d_smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void d_mbar_init(uint64_t *bar, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(d_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void d_mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(d_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void d_mbar_wait(uint64_t *bar, unsigned parity)
+{
+	unsigned ok, spins = 0;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(ok)
+		             : "r"(d_smem_u32(bar)), "r"(parity)
+		             : "memory");
+		if (!ok && ++spins > (1u << 26)) __trap();        // a lost arrival must surface as an error, never as a hung GPU
+	} while (!ok);
+}
+__device__ __forceinline__ void d_tma_load_1d(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d_smem_u32(smem_dst)),
+	             "l"(gmem_src), "r"(bytes), "r"(d_smem_u32(bar))
+	             : "memory");
+}
+
+// The input rows arrive by 1-D bulk TMA copies, kSweepRows rows (one contiguous block of the slice) per copy,
+// double-buffered on two mbarriers: the serial row recurrence never waits on a global load, it reads shared memory.
+constexpr int kSweepRows = 32;
+template <int XDIR>        // XDIR 0: isotropic (two-sided x, 3 neighbours, in-place second sweep); +-1: one-sided
 __global__ void __launch_bounds__(1024) ysweep_kernel(const uint8_t *__restrict__ g, uint8_t *__restrict__ dst0, uint8_t *__restrict__ dst1,
                                                       uint32_t Wb, uint32_t Hb)
 {
-	extern __shared__ uint8_t s_rows[];        // 2 x (Wb + 2): previous / current row with a 255 border on both sides
-	const uint32_t T = blockDim.x, t = threadIdx.x;
-	const size_t   slice = (size_t) blockIdx.x * Wb * Hb;
-	uint8_t       *buf[2] = {s_rows + 1, s_rows + (Wb + 2) + 1};
-	constexpr int  P = 8;
+	extern __shared__ __align__(128) uint8_t s_dyn[];        // 2 chunks of kSweepRows x Wb | 2 x (Wb + 2) row buffers
+	__shared__ __align__(8) uint64_t s_bar[2];
+	const uint32_t x      = threadIdx.x;
+	const bool     active = x < Wb;
+	const size_t   slice  = (size_t) blockIdx.x * Wb * Hb;
+	const uint32_t chunk_bytes = kSweepRows * Wb;
+	uint8_t       *ring = s_dyn;
+	uint8_t       *buf0 = s_dyn + 2 * (size_t) chunk_bytes + 16 + 1, *buf1 = buf0 + (Wb + 2);
+	const uint32_t nchunks = (Hb + kSweepRows - 1) / kSweepRows;
+	if (x == 0) {
+		d_mbar_init(&s_bar[0], 1);
+		d_mbar_init(&s_bar[1], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	unsigned issued = 0;        // copies issued so far (thread 0): copy n lands in ring buffer n & 1, phase (n >> 1) & 1
 	for (int sweep = 0; sweep < 2; ++sweep) {
 		// sweep 0 walks y upwards (sources at y' <= y), sweep 1 downwards (sources at y' >= y)
-		const uint8_t *src = (XDIR == 0 && sweep == 1) ? dst0 : g;
-		uint8_t       *dst = XDIR == 0 ? dst0 : (sweep == 0 ? dst1 : dst0);
-		if (t == 0) { buf[0][-1] = 255; buf[1][-1] = 255; buf[0][Wb] = 255; buf[1][Wb] = 255; }
-		for (int c = 0; c < NC; ++c) {
-			const uint32_t x = t + c * T;
-			if (x < Wb) buf[0][x] = 255;        // "row -1": nothing behind the first row
-		}
-		__syncthreads();
-		unsigned nxt[NC][P];
-		auto row_of = [&](uint32_t i) { return sweep == 0 ? i : Hb - 1 - i; };
-		auto load_group = [&](uint32_t i0) {
-#pragma unroll
-			for (int k = 0; k < P; ++k)
-#pragma unroll
-				for (int c = 0; c < NC; ++c) {
-					const uint32_t x = t + c * T, i = i0 + k;
-					nxt[c][k] = (x < Wb && i < Hb) ? (unsigned) src[slice + (size_t) row_of(i) * Wb + x] : 255u;
-				}
+		const uint8_t  *src  = (XDIR == 0 && sweep == 1) ? dst0 : g;
+		uint8_t        *dst  = XDIR == 0 ? dst0 : (sweep == 0 ? dst1 : dst0);
+		const ptrdiff_t step = sweep == 0 ? (ptrdiff_t) Wb : -(ptrdiff_t) Wb;
+		uint8_t        *dp   = dst + slice + (sweep == 0 ? 0 : (size_t) (Hb - 1) * Wb) + x;
+		// chunk c of this sweep = rows [lo, lo + n) of the slice, consumed upwards (sweep 0) or downwards (sweep 1)
+		auto issue = [&](uint32_t c) {
+			const uint32_t i0 = c * kSweepRows, n = min((uint32_t) kSweepRows, Hb - i0);
+			const uint32_t lo = sweep == 0 ? i0 : Hb - i0 - n;
+			uint64_t      *bar = &s_bar[issued & 1u];
+			d_mbar_expect_tx(bar, n * Wb);
+			d_tma_load_1d(ring + (size_t) (issued & 1u) * chunk_bytes, src + slice + (size_t) lo * Wb, n * Wb, bar);
+			++issued;
 		};
-		load_group(0);
-		int pb = 0;
-		for (uint32_t i0 = 0; i0 < Hb; i0 += P) {
-			unsigned cur[NC][P];
-#pragma unroll
-			for (int k = 0; k < P; ++k)
-#pragma unroll
-				for (int c = 0; c < NC; ++c) cur[c][k] = nxt[c][k];
-			load_group(i0 + P);        // in flight while this group's rows are swept
-#pragma unroll
-			for (int k = 0; k < P; ++k) {
-				if (i0 + k < Hb) {
-					const uint8_t *prev = buf[pb];
-					uint8_t       *now  = buf[pb ^ 1];
-#pragma unroll
-					for (int c = 0; c < NC; ++c) {
-						const uint32_t x = t + c * T;
-						if (x < Wb) {
-							unsigned m = prev[x];
-							if (XDIR >= 0) m = min(m, (unsigned) prev[x + 1]);
-							if (XDIR <= 0) m = min(m, (unsigned) prev[(int) x - 1]);
-							const unsigned v = min(cur[c][k], m + 1u);
-							now[x] = (uint8_t) v;
-							dst[slice + (size_t) row_of(i0 + k) * Wb + x] = (uint8_t) v;
-						}
-					}
-					pb ^= 1;
+		if (XDIR == 0 && sweep == 1) {
+			// the second sweep re-reads what this CTA just wrote with ordinary stores: order them before the async-proxy reads
+			__threadfence();
+			asm volatile("fence.proxy.async;" ::: "memory");
+		}
+		if (x == 0) { buf0[-1] = 255; buf1[-1] = 255; buf0[Wb] = 255; buf1[Wb] = 255; }
+		if (active) buf0[x] = 255;        // "row -1": nothing behind the first row
+		__syncthreads();
+		unsigned consumed = issued;       // uniform bookkeeping of the copy sequence number (every thread tracks it)
+		if (x == 0) {
+			issue(0);
+			if (nchunks > 1) issue(1);
+		}
+		for (uint32_t c = 0; c < nchunks; ++c) {
+			const unsigned seq = consumed + c;
+			d_mbar_wait(&s_bar[seq & 1u], (seq >> 1) & 1u);
+			const uint32_t n  = min((uint32_t) kSweepRows, Hb - c * kSweepRows);
+			const uint8_t *cb = ring + (size_t) (seq & 1u) * chunk_bytes;
+			// rows alternate between the two row buffers; a chunk has an even number of rows unless it is the last one, so the
+			// buffer roles are compile-time constants of the 2-row unrolled loop
+			const uint8_t *cp = cb + (sweep == 0 ? 0 : (size_t) (n - 1) * Wb) + x;        // this thread's cell in the chunk's first row
+			auto row_step = [&](const uint8_t *prev, uint8_t *now) {
+				if (active) {
+					unsigned m = prev[x];
+					if (XDIR >= 0) m = min(m, (unsigned) prev[x + 1]);
+					if (XDIR <= 0) m = min(m, (unsigned) prev[(int) x - 1]);
+					const unsigned val = min((unsigned) *cp, m + 1u);
+					now[x] = (uint8_t) val;
+					*dp    = (uint8_t) val;
+					dp += step;
+					cp += step;
 				}
 				__syncthreads();
+			};
+			uint32_t k = 0;
+			for (; k + 2 <= n; k += 2) {
+				row_step(buf0, buf1);
+				row_step(buf1, buf0);
 			}
+			if (k < n) row_step(buf0, buf1);        // odd tail: only ever in the last chunk of a sweep
+			// every thread is past the chunk: its ring buffer may be refilled
+			if (x == 0 && c + 2 < nchunks) issue(c + 2);
 		}
+		issued = consumed + nchunks;        // keep every thread's view of the sequence number in step with thread 0's
 	}
 }
 
@@ -387,74 +434,88 @@ __global__ void __launch_bounds__(1024) ysweep_kernel(const uint8_t *__restrict_
 // grows by at most one, so with r = F(z + 1):   F(z) = min( h(z), r      if some j in [z+1, z+r] has h(j) <= r
 //                                                                 r + 1  otherwise ),
 // i.e. ONE range-minimum query per cell instead of an 8-step binary search; the two-sided value is min(F, B) with B the
-// mirror image.  The sparse range-minimum table of the line is built in shared memory as before; a CTA owns TW adjacent
-// columns, walks them with 2 x TW threads (one per column and direction) and writes the result rows coalesced.
-// MODE 0: dst0 = min(F, B) | 3: dst0 = F (towards +z), dst1 = B (towards -z)
+// mirror image.  A CTA owns TW adjacent columns: it stages them and builds the sparse range-minimum table four columns
+// per thread (32-bit shared-memory accesses, packed byte minimum), walks them with 2 x TW threads — one per column and
+// direction, every thread of the CTA — and writes the result rows as 32-bit words.
+// MODE 0: dst0 = min(F, B) | 3: dst0 = F (towards +z), dst1 = B (towards -z).   Needs Wb % 4 == 0 and TW % 4 == 0.
 template <int MODE>
 __global__ void __launch_bounds__(256) zwalk_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst0, uint8_t *__restrict__ dst1,
                                                     uint32_t Wb, uint32_t L, size_t line_stride, size_t outer_stride, int TW, int nlev)
 {
-	extern __shared__ uint8_t T[];        // nlev levels of L x TW bytes, then the F and B lines (2 x L x TW)
-	const int      col  = threadIdx.x % TW, sub = threadIdx.x / TW, nsub = blockDim.x / TW;
-	const uint32_t x    = blockIdx.x * TW + col;
-	const bool     in_x = x < Wb;
-	const size_t   base = (size_t) blockIdx.y * outer_stride + x;
+	extern __shared__ __align__(16) uint8_t T[];        // nlev levels of L x TW bytes, then the F and B lines (2 x L x TW)
+	const int      nthreads = blockDim.x;               // = 2 * TW
+	const int      TW4 = TW >> 2;                       // words per row
+	const uint32_t x0  = blockIdx.x * TW;
+	const size_t   base = (size_t) blockIdx.y * outer_stride + x0;
 	const size_t   lst  = (size_t) L * TW;
 	uint8_t       *Fl = T + (size_t) nlev * lst, *Bl = Fl + lst;
-	for (uint32_t p = sub; p < L; p += nsub) T[p * TW + col] = in_x ? src[base + (size_t) p * line_stride] : (uint8_t) 255;
+	// stage: word w of row p = columns 4w .. 4w+3
+	const int nwords = (int) L * TW4;
+	for (int i = threadIdx.x; i < nwords; i += nthreads) {
+		const int p = i / TW4, w = i - p * TW4;
+		unsigned  v = 0xffffffffu;
+		if (x0 + 4u * w < Wb) v = __ldg(reinterpret_cast<const unsigned *>(src + base + (size_t) p * line_stride) + w);
+		reinterpret_cast<unsigned *>(T)[i] = v;
+	}
 	__syncthreads();
 	for (int k = 1; k < nlev; ++k) {
-		const uint8_t *prev = T + (size_t) (k - 1) * lst;
-		uint8_t       *cur  = T + (size_t) k * lst;
-		const uint32_t half = 1u << (k - 1);
-		for (uint32_t p = sub; p < L; p += nsub) {
-			const unsigned a = prev[p * TW + col];
-			const unsigned b = p + half < L ? prev[(p + half) * TW + col] : 255u;
-			cur[p * TW + col] = (uint8_t) min(a, b);
+		const unsigned *prev = reinterpret_cast<const unsigned *>(T + (size_t) (k - 1) * lst);
+		unsigned       *cur  = reinterpret_cast<unsigned *>(T + (size_t) k * lst);
+		const int       half = (1 << (k - 1)) * TW4;        // in words
+		for (int i = threadIdx.x; i < nwords; i += nthreads) {
+			const unsigned a = prev[i];
+			const unsigned b = i + half < nwords ? prev[i + half] : 0xffffffffu;
+			cur[i] = __vminu4(a, b);
 		}
 		__syncthreads();
 	}
-	if (sub < 2) {
-		const int Li = (int) L;
-		if (sub == 0) {        // F: towards +z, walking down from the last cell
+	{
+		const int col = threadIdx.x % TW, Li = (int) L;
+		if (threadIdx.x < TW) {        // F: towards +z, walking down from the last cell
 			unsigned r = T[(Li - 1) * TW + col];
 			Fl[(Li - 1) * TW + col] = (uint8_t) r;
 			for (int z = Li - 2; z >= 0; --z) {
+				const unsigned hz = T[z * TW + col];
 				unsigned cand = min(r + 1u, 255u);
-				if (r > 0u) {
+				if (r > 0u && hz > r) {        // h(z) <= r decides F(z) = h(z) whatever the window holds
 					const int a = z + 1, b = min(z + (int) r, Li - 1);
 					const int k = 31 - __clz(b - a + 1);
 					const uint8_t *Tk = T + (size_t) k * lst;
 					const unsigned w  = min((unsigned) Tk[a * TW + col], (unsigned) Tk[(b - (1 << k) + 1) * TW + col]);
 					if (w <= r) cand = r;
 				}
-				r = min((unsigned) T[z * TW + col], cand);
+				r = min(hz, cand);
 				Fl[z * TW + col] = (uint8_t) r;
 			}
-		} else {               // B: towards -z, walking up from the first cell
+		} else {                       // B: towards -z, walking up from the first cell
 			unsigned r = T[col];
 			Bl[col] = (uint8_t) r;
 			for (int z = 1; z < Li; ++z) {
+				const unsigned hz = T[z * TW + col];
 				unsigned cand = min(r + 1u, 255u);
-				if (r > 0u) {
+				if (r > 0u && hz > r) {
 					const int b = z - 1, a = max(z - (int) r, 0);
 					const int k = 31 - __clz(b - a + 1);
 					const uint8_t *Tk = T + (size_t) k * lst;
 					const unsigned w  = min((unsigned) Tk[a * TW + col], (unsigned) Tk[(b - (1 << k) + 1) * TW + col]);
 					if (w <= r) cand = r;
 				}
-				r = min((unsigned) T[z * TW + col], cand);
+				r = min(hz, cand);
 				Bl[z * TW + col] = (uint8_t) r;
 			}
 		}
 	}
 	__syncthreads();
-	if (!in_x) return;
-	for (uint32_t p = sub; p < L; p += nsub) {
+	for (int i = threadIdx.x; i < nwords; i += nthreads) {
+		const int p = i / TW4, w = i - p * TW4;
+		if (x0 + 4u * w >= Wb) continue;
+		const unsigned f = reinterpret_cast<const unsigned *>(Fl)[i], b = reinterpret_cast<const unsigned *>(Bl)[i];
 		const size_t   o = base + (size_t) p * line_stride;
-		const unsigned f = Fl[p * TW + col], b = Bl[p * TW + col];
-		if (MODE == 0) dst0[o] = (uint8_t) min(f, b);
-		else { dst0[o] = (uint8_t) f; dst1[o] = (uint8_t) b; }
+		if (MODE == 0) reinterpret_cast<unsigned *>(dst0 + o)[w] = __vminu4(f, b);
+		else {
+			reinterpret_cast<unsigned *>(dst0 + o)[w] = f;
+			reinterpret_cast<unsigned *>(dst1 + o)[w] = b;
+		}
 	}
 }
 
@@ -513,15 +574,18 @@ static int run_ysweep(const vkv_volume *vol, const uint8_t *g, uint8_t *dst0, ui
 {
 	const uint32_t Wb = vol->dim_b[0], Hb = vol->dim_b[1], Db = vol->dim_b[2];
 	*done = false;
-	if (Wb > 1024u * kSweepMaxCells || Db > 65535u * 32768u) return VKV_OK;        // fall back to the search kernel
-	const int    threads = (int) std::min<uint32_t>(1024u, (Wb + 31u) / 32u * 32u);
-	const int    nc      = (int) ((Wb + threads - 1) / threads);
-	const size_t smem    = 2 * ((size_t) Wb + 2);
-	switch (nc) {
-		case 1: ysweep_kernel<XDIR, 1><<<Db, threads, smem, s>>>(g, dst0, dst1, Wb, Hb); break;
-		case 2: ysweep_kernel<XDIR, 2><<<Db, threads, smem, s>>>(g, dst0, dst1, Wb, Hb); break;
-		default: ysweep_kernel<XDIR, kSweepMaxCells><<<Db, threads, smem, s>>>(g, dst0, dst1, Wb, Hb); break;
+	// one cell per thread; bulk copies need 16-byte aligned row blocks (slice size, hence every block start and length)
+	if (Wb > 1024u || ((size_t) Wb * Hb) % 16 != 0 || ((size_t) kSweepRows * Wb) % 16 != 0 || (reinterpret_cast<uintptr_t>(g) % 16) != 0 ||
+	    (reinterpret_cast<uintptr_t>(dst0) % 16) != 0)
+		return VKV_OK;        // otherwise the search kernel
+	const int    threads = (int) ((Wb + 31u) / 32u * 32u);
+	const size_t smem    = 2 * (size_t) kSweepRows * Wb + 16 + 2 * ((size_t) Wb + 2);
+	static bool configured = false;
+	if (!configured) {
+		VKV_CUDA_CHECK(cudaFuncSetAttribute(ysweep_kernel<XDIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+		configured = true;
 	}
+	ysweep_kernel<XDIR><<<Db, threads, smem, s>>>(g, dst0, dst1, Wb, Hb);
 	VKV_LAUNCHED();
 	*done = true;
 	return VKV_OK;
@@ -533,20 +597,21 @@ static int run_zwalk(const vkv_volume *vol, const uint8_t *src, uint8_t *dst0, u
 {
 	const uint32_t Wb = vol->dim_b[0], Hb = vol->dim_b[1], L = vol->dim_b[2];
 	*done = false;
+	if (Wb % 4 != 0 || Hb > 65535u) return VKV_OK;        // 32-bit column groups; otherwise the search kernel
 	const uint32_t max_window = std::min<uint32_t>(255u, L);
 	int            nlev       = 1;
 	while ((2u << (nlev - 1)) <= max_window) ++nlev;
 	int TW = 64;
-	while (TW > 8 && (size_t) (nlev + 2) * L * TW > (size_t) 100 * 1024) TW >>= 1;
+	while (TW > 8 && (size_t) (nlev + 2) * L * TW > (size_t) 72 * 1024) TW >>= 1;
 	const size_t smem = (size_t) (nlev + 2) * L * TW;
-	if (smem > (size_t) 200 * 1024 || Hb > 65535u) return VKV_OK;
+	if (smem > (size_t) 200 * 1024) return VKV_OK;
 	static bool configured = false;
 	if (!configured) {
 		VKV_CUDA_CHECK(cudaFuncSetAttribute(zwalk_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 		configured = true;
 	}
 	const dim3 grid((Wb + TW - 1) / TW, Hb);
-	zwalk_kernel<MODE><<<grid, 256, smem, s>>>(src, dst0, dst1, Wb, L, (size_t) Wb * Hb, (size_t) Wb, TW, nlev);
+	zwalk_kernel<MODE><<<grid, 2 * TW, smem, s>>>(src, dst0, dst1, Wb, L, (size_t) Wb * Hb, (size_t) Wb, TW, nlev);
 	VKV_LAUNCHED();
 	*done = true;
 	return VKV_OK;

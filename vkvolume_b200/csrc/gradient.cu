@@ -12,6 +12,8 @@
 // identical to the CPU oracle's (the byte feeds the occupancy LUT).  UNORM decode b/255 is
 // served from a 256-entry shared-memory table built with a true division.
 // Algorithmic bytes: read N + write N = 2 B/voxel.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vkv {
@@ -93,6 +95,141 @@ __global__ void __launch_bounds__(256) gradient_vec16_kernel(const uint8_t *__re
 	}
 }
 
+// ---- integer formulation (grad_magnitude_modifier == 1, the only value the reference ever passes) -------------
+// With A, B, C, D the four tap bytes, 255 * |g| = sqrt(S) / 4 where S = sx^2 + sy^2 + sz^2 is an INTEGER:
+//     (sx, sy, sz) = M (A, B, C, D),  M^T M = 4 I - J   =>   S = 4 (A^2 + B^2 + C^2 + D^2) - (A + B + C + D)^2,
+// two dp4a instructions on the packed taps.  The stored byte is rint(sqrt(S) / 4); the reference's fp32 chain
+// (UNORM decode, three adds, 0.25, length, * 255, round) carries an absolute error below 1.5e-4 in 255 |g|, so whenever
+// sqrt(S) / 4 is further than 1e-3 from a rounding boundary n + 1/2 the byte is decided by S alone.  The remaining
+// voxels — in practice only exact ties S = (4n + 2)^2, 3-5 % of a volume — are queued per warp in shared memory and
+// evaluated by all 32 lanes with the shader's exact fp32 operation order (the old path), then patched into the
+// staged output row.  Byte-identical to the fp32 kernel (and to the CPU oracle) at a quarter of the instructions.
+__device__ __forceinline__ unsigned prmt_(unsigned a, unsigned b, unsigned sel)
+{
+	unsigned r;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+	return r;
+}
+
+constexpr int kGradQueue = 512;        // worst case: every voxel of a warp iteration is a tie
+
+// Work decomposition: a task is one row (y, z) x one group of 32 chunks (512 voxels of x), numbered with the chunk
+// group fastest; warp w of CTA b takes task 8 b + w, so at any moment the grid reads and writes a compact window of the
+// volume (DRAM pages stay open, the (y +- 1, z +- 1) rows are shared through L2) and the (group, y, z) decode is two
+// 32-bit divisions per warp task instead of 64-bit ones per thread.
+// SURF: also write the 16 result bytes into the cudaArray the ray caster samples (the map exists twice: linear for the
+// occupancy pass, array for the texture unit) — one surface store instead of a second pass over the map.
+template <bool SURF>
+__global__ void __launch_bounds__(256) gradient_int_kernel(const uint8_t *__restrict__ V, uint8_t *__restrict__ G, cudaSurfaceObject_t surf,
+                                                          uint32_t W, uint32_t H, uint32_t D)
+{
+	__shared__ float          s_lut[256];
+	__shared__ __align__(16) unsigned s_w[8][4][32 * 4];        // taps (A | B << 8 | C << 16 | D << 24) of the warp's 512 voxels: [j][lane][i]
+	__shared__ unsigned short s_qp[8][kGradQueue];              // queued voxels: lane * 16 + j * 4 + i
+	__shared__ __align__(16) unsigned char s_out[8][32 * 16];
+	__shared__ unsigned       s_qn[8];
+	s_lut[threadIdx.x] = (float) threadIdx.x / 255.0f;        // UNORM decode, exactly as imageLoad
+	if (threadIdx.x < 8) s_qn[threadIdx.x] = 0u;
+	__syncthreads();
+	const uint32_t nchunks = W / 16, ngroups = (nchunks + 31) / 32;
+	const uint32_t ntasks  = ngroups * H * D;        // < 2^32 (checked by the launcher)
+	const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t task = blockIdx.x * 8u + warp;
+	if (task >= ntasks) return;
+	const uint32_t row = task / ngroups, grp = task - row * ngroups;
+	const uint32_t z = row / H, y = row - z * H;
+	{
+		const uint32_t chunk  = grp * 32 + lane;
+		const bool     active = chunk < nchunks;
+		const uint32_t cch    = active ? chunk : nchunks - 1;        // idle lanes mirror the last chunk (their loads stay in bounds)
+		const uint32_t ym = y > 0 ? y - 1 : 0, yp = y + 1 < H ? y + 1 : H - 1;
+		const uint32_t zm = z > 0 ? z - 1 : 0, zp = z + 1 < D ? z + 1 : D - 1;
+		const uint32_t x = cch * 16;
+		const size_t   r_mm = ((size_t) zm * H + ym) * W, r_pm = ((size_t) zp * H + ym) * W, r_mp = ((size_t) zm * H + yp) * W,
+		               r_pp = ((size_t) zp * H + yp) * W;
+		// rows: A = (y-1, z-1) read at x+1 | B = (y-1, z+1) at x-1 | C = (y+1, z-1) at x-1 | E = (y+1, z+1) at x+1
+		const uint8_t *rowp[4] = {V + r_mm + x, V + r_pm + x, V + r_mp + x, V + r_pp + x};
+		const bool     first = cch == 0, last = cch == nchunks - 1;
+		unsigned win[4][4];        // the 16-byte window of each row, already shifted by its x offset
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			const uint4    q    = __ldg(reinterpret_cast<const uint4 *>(rowp[k]));
+			const unsigned w[4] = {q.x, q.y, q.z, q.w};
+			const bool     plus = (k == 0 || k == 3);        // tap at x+1 (else x-1)
+			if (plus) {
+				// byte x+16 (clamped to W-1) in bits 0..7: from the next lane, from memory for the group's last lane
+				const unsigned down = __shfl_down_sync(0xffffffffu, w[0], 1);
+				unsigned       edge = 0;
+				if (lane == 31 && !last) edge = rowp[k][16];
+				const unsigned right = last ? (w[3] >> 24) : (lane == 31 ? edge : down);
+				win[k][0] = __funnelshift_r(w[0], w[1], 8);
+				win[k][1] = __funnelshift_r(w[1], w[2], 8);
+				win[k][2] = __funnelshift_r(w[2], w[3], 8);
+				win[k][3] = __funnelshift_r(w[3], right, 8);
+			} else {
+				// byte x-1 (clamped to 0) in bits 24..31
+				const unsigned up   = __shfl_up_sync(0xffffffffu, w[3], 1);
+				unsigned       edge = 0;
+				if (lane == 0 && !first) edge = ((unsigned) *(rowp[k] - 1)) << 24;
+				const unsigned left = first ? (w[0] << 24) : (lane == 0 ? edge : up);
+				win[k][0] = __funnelshift_r(left, w[0], 24);
+				win[k][1] = __funnelshift_r(w[0], w[1], 24);
+				win[k][2] = __funnelshift_r(w[1], w[2], 24);
+				win[k][3] = __funnelshift_r(w[2], w[3], 24);
+			}
+		}
+		unsigned out[4], flags = 0;
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			// 4x4 byte transpose: taps of voxel i of this word group -> one word (A, B, C, D)
+			const unsigned t0 = prmt_(win[0][j], win[1][j], 0x5140u), t1 = prmt_(win[0][j], win[1][j], 0x7362u);
+			const unsigned u0 = prmt_(win[2][j], win[3][j], 0x5140u), u1 = prmt_(win[2][j], win[3][j], 0x7362u);
+			const unsigned wv[4] = {prmt_(t0, u0, 0x5410u), prmt_(t0, u0, 0x7632u), prmt_(t1, u1, 0x5410u), prmt_(t1, u1, 0x7632u)};
+			*reinterpret_cast<uint4 *>(&s_w[warp][j][lane * 4]) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+			float yv[4];
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				const unsigned q  = __dp4a(wv[i], wv[i], 0u);                // A^2 + B^2 + C^2 + D^2
+				const unsigned sm = __dp4a(wv[i], 0x01010101u, 0u);          // A + B + C + D
+				const unsigned S  = 4u * q - sm * sm;                        // < 2^20
+				const float    f  = __uint_as_float(S | 0x4b000000u) - 8388608.0f;        // exact int -> float
+				float rt;
+				asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rt) : "f"(f));
+				const float yy = __fmaf_rn(rt, 0.25f, 8388608.0f);           // low mantissa bits = rint(sqrt(S) / 4)
+				const float dd = __fmaf_rn(rt, 0.25f, -(yy - 8388608.0f));   // distance from that integer, in [-1/2, 1/2]
+				yv[i]          = yy;
+				// too close to n + 1/2 (the sign bit of 0.499 - |dd|): decided by the fp32 chain.  Bit 15 - (4 j + i) of flags.
+				flags = __funnelshift_l(__float_as_uint(0.499f - fabsf(dd)), flags, 1);
+			}
+			const unsigned p01 = prmt_(__float_as_uint(yv[0]), __float_as_uint(yv[1]), 0x0040u);
+			const unsigned p23 = prmt_(__float_as_uint(yv[2]), __float_as_uint(yv[3]), 0x0040u);
+			out[j]             = prmt_(p01, p23, 0x5410u);
+		}
+		*reinterpret_cast<uint4 *>(&s_out[warp][lane * 16]) = make_uint4(out[0], out[1], out[2], out[3]);
+		flags &= 0xffffu;
+		while (flags) {
+			const unsigned i    = 15u - (unsigned) (__ffs(flags) - 1);
+			const unsigned slot = atomicAdd(&s_qn[warp], 1u);
+			s_qp[warp][slot]    = (unsigned short) (lane * 16 + i);
+			flags &= flags - 1;
+		}
+		__syncwarp();
+		const unsigned nq = s_qn[warp];
+		for (unsigned e = lane; e < nq; e += 32) {
+			const unsigned p  = s_qp[warp][e];
+			const unsigned ln = p >> 4, ji = p & 15u;
+			const unsigned w  = s_w[warp][ji >> 2][ln * 4 + (ji & 3u)];
+			s_out[warp][p]    = gradient_byte(s_lut[w & 0xffu], s_lut[(w >> 8) & 0xffu], s_lut[(w >> 16) & 0xffu], s_lut[w >> 24], 1.0f);
+		}
+		__syncwarp();
+		const uint4 o = *reinterpret_cast<const uint4 *>(&s_out[warp][lane * 16]);
+		if (active) {
+			*reinterpret_cast<uint4 *>(G + ((size_t) z * H + y) * W + x) = o;
+			if (SURF) surf3Dwrite(o, surf, (int) x, (int) y, (int) z);        // x in bytes
+		}
+	}
+}
+
 // Any extents: one thread per voxel, clamped byte loads through L1.
 __global__ void __launch_bounds__(256) gradient_scalar_kernel(const uint8_t *__restrict__ V, uint8_t *__restrict__ G, uint32_t W,
                                                              uint32_t H, uint32_t D, float modifier)
@@ -121,9 +258,21 @@ __global__ void __launch_bounds__(256) fill_u32_kernel(uint32_t *__restrict__ p,
 int launch_gradient(vkv_volume *vol, bool use_gradient, float modifier, cudaStream_t s)
 {
 	const int grid = vol->ctx->sm_count * 8;
+	vol->G_array_synced = false;
 	if (!use_gradient) {
 		// get_gradient returns 1.0 for every voxel (get_gradient_compute.glsl:6-7) -> byte 255
 		VKV_CUDA_CHECK(cudaMemsetAsync(vol->d_G, 255, vol->N, s));
+	} else if (vol->dim[0] % 16 == 0 && reinterpret_cast<uintptr_t>(vol->d_V) % 16 == 0 && modifier == 1.0f && !getenv("VKV_GRAD_FP32") &&
+	           (uint64_t) ((vol->dim[0] / 16 + 31) / 32) * vol->dim[1] * vol->dim[2] < (1ull << 31)) {
+		const unsigned ntasks = ((vol->dim[0] / 16 + 31) / 32) * vol->dim[1] * vol->dim[2];
+		const unsigned grid   = (ntasks + 7) / 8;
+		if (vol->s_G && !getenv("VKV_GRAD_NOSURF")) {
+			gradient_int_kernel<true><<<grid, 256, 0, s>>>(vol->d_V, vol->d_G, vol->s_G, vol->dim[0], vol->dim[1], vol->dim[2]);
+			vol->G_array_synced = true;        // the kernel wrote the array itself
+		} else {
+			gradient_int_kernel<false><<<grid, 256, 0, s>>>(vol->d_V, vol->d_G, 0, vol->dim[0], vol->dim[1], vol->dim[2]);
+		}
+		VKV_LAUNCHED();
 	} else if (vol->dim[0] % 16 == 0 && reinterpret_cast<uintptr_t>(vol->d_V) % 16 == 0) {
 		gradient_vec16_kernel<<<grid, 256, 0, s>>>(vol->d_V, vol->d_G, vol->dim[0], vol->dim[1], vol->dim[2], modifier);
 		VKV_LAUNCHED();
