@@ -190,7 +190,8 @@ def run_native(args):
     def rebuild_single(count=False, o=opt):
         return vol.update_transfer_function(o, skip, count=count, stream=stream)
 
-    slab = (vol.map_extent[2] + world - 1) // world
+    from vkvolume_b200 import sharding
+    slab = sharding.slab_size(vol.map_extent[2], world)
     if world > 1:
         Wb, Hb, Db = vol.map_extent
         map_idx = 7 if skip == 3 else 0
@@ -203,20 +204,12 @@ def run_native(args):
         Wb, Hb, Db = vol.map_extent
         vol.update_transfer_function_texture(o, stream)
         u = capi.transfer_function_uniform(o)
-        z0 = min(rank * slab, Db)
-        zc = max(0, min(slab, Db - z0))
+        z0, zc = sharding.slab_range(rank, world, Db)
         count_t.zero_()
         vol.compute_occupancy_slab(u, skip, z0, zc, count_dev=count_t.data_ptr(), stream=stream)
         full = torch.as_tensor(_DevPtr(vol.device_distance_map(map_idx), Wb * Hb * Db), device=dev)
-        mine = torch.zeros(slab * Wb * Hb, dtype=torch.uint8, device=dev)
-        mine[: zc * Wb * Hb] = full[z0 * Wb * Hb:(z0 + zc) * Wb * Hb]
-        dist.all_gather_into_tensor(gather_buf, mine)
-        for r in range(world):
-            rz0 = min(r * slab, Db)
-            rzc = max(0, min(slab, Db - rz0))
-            if rzc and r != rank:
-                full[rz0 * Wb * Hb:(rz0 + rzc) * Wb * Hb] = gather_buf[r * slab * Wb * Hb: r * slab * Wb * Hb + rzc * Wb * Hb]
-        dist.all_reduce(count_t)
+        sharding.all_gather_occupancy(full, rank, world, (Wb, Hb, Db), gather_buf)
+        sharding.all_reduce_count(count_t)
         vol.compute_distance_from_occupancy(skip, stream)
 
     rebuild = rebuild_sharded if world > 1 else rebuild_single

@@ -1,0 +1,99 @@
+"""CPU-only coverage of the N > 1 host logic: slab / tile arithmetic, and a world_size-2 gloo run of the z-slab occupancy
+exchange (per-rank slab computed with the oracle, slab rows all-gathered, count all-reduced, distance transform on the
+gathered map) checked against the single-rank result."""
+import os
+import socket
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from vkvolume_b200 import sharding
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.mark.parametrize("Db,world", [(7, 2), (8, 2), (1, 2), (3, 4), (124, 8), (512, 8), (5, 8)])
+def test_slabs_partition_the_map(Db, world):
+    covered = []
+    for r in range(world):
+        z0, zc = sharding.slab_range(r, world, Db)
+        assert 0 <= z0 <= Db and 0 <= zc <= sharding.slab_size(Db, world)
+        covered += list(range(z0, z0 + zc))
+    assert covered == list(range(Db))
+
+
+@pytest.mark.parametrize("frame,world", [((1920, 1080), 2), ((7680, 4320), 8), ((160, 120), 4), ((64, 32), 8)])
+def test_tiles_are_dealt_exactly_once(frame, world):
+    n = sharding.n_tiles(*frame, 64, 32)
+    seen = sorted(t for r in range(world) for t in sharding.tiles_of_rank(r, world, n))
+    assert seen == list(range(n))
+    sizes = [len(sharding.tiles_of_rank(r, world, n)) for r in range(world)]
+    assert max(sizes) - min(sizes) <= 1
+
+
+WORKER = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, os.environ["VKV_ROOT"]); sys.path.insert(0, os.path.join(os.environ["VKV_ROOT"], "tests"))
+import oracle_api as orc
+from vkvolume_b200 import scene, sharding
+from vkvolume_b200.capi import VolumeOptions
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+shape = (26, 20, 24)        # D, H, W: 7 block slices of 4 (ragged last block), 2 ranks -> slabs of 4 and 3
+V = scene.blobs_volume(shape, seed=5, n_blobs=6)
+opt = VolumeOptions(intensity_min=0.1, intensity_max=1.0, gradient_min=0.0, gradient_max=0.2)
+tfu = orc.transfer_function_uniform(opt); tf = orc.transfer_function_texture(opt)
+G = orc.gradient_map(V)
+D, H, W = shape
+(Wb, Hb, Db), _ = orc.map_extent((W, H, D), 4)
+O_full = orc.occupancy_map(V, G, tf, 4, True)
+z0, zc = sharding.slab_range(rank, world, Db)
+# this rank's slab only: the voxel slices [4 z0, 4 (z0 + zc)) of the volume
+vz0, vz1 = 4 * z0, min(D, 4 * (z0 + zc))
+mine = orc.occupancy_map(V[vz0:vz1], G[vz0:vz1], tf, 4, True) if zc else np.zeros((0, Hb, Wb), np.uint8)
+full = torch.full((Wb * Hb * Db,), 77, dtype=torch.uint8)        # poison: every cell must be overwritten
+full[z0 * Wb * Hb:(z0 + zc) * Wb * Hb] = torch.from_numpy(mine.reshape(-1).copy())
+sharding.all_gather_occupancy(full, rank, world, (Wb, Hb, Db))
+cnt = torch.tensor([orc.occupied_voxel_count(V[vz0:vz1], G[vz0:vz1], tfu) if zc else 0], dtype=torch.int64)
+sharding.all_reduce_count(cnt)
+got = full.numpy().reshape(Db, Hb, Wb)
+assert np.array_equal(got, O_full), "gathered occupancy map differs from the single-rank map"
+assert int(cnt.item()) == orc.occupied_voxel_count(V, G, tfu), "all-reduced voxel count differs"
+assert np.array_equal(orc.distance_map(got.copy()), orc.distance_map(O_full.copy()))
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_zslab_exchange_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    port = _free_port()
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), VKV_ROOT=str(ROOT),
+                   OMP_NUM_THREADS="2")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = []
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=240)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        outs.append(out)
+    for rank, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, f"rank {rank} failed:\n{out}"
+        assert f"rank {rank} ok" in out

@@ -1,0 +1,62 @@
+"""Host-side logic of the multi-GPU decomposition: pure index arithmetic plus the two
+torch.distributed exchanges.  Works on CPU tensors with the gloo backend (how tests/test_sharding_gloo.py runs it)
+and on CUDA tensors with NCCL (how bench.py runs it) — there is no compute here.
+
+* Ray casting shards by image tiles: tile t of the row-major tile list goes to rank t % world (round-robin, because
+  ESS/ERT make per-pixel cost wildly non-uniform); every rank holds a full replica and stores its tiles straight into
+  rank 0's framebuffer (peer mapping), so that path has no collective at all.
+* The TF-change rebuild shards the O(N) occupancy pass by z-slabs of blocks; the slab rows of the occupancy map are
+  all-gathered, the voxel count is all-reduced, and every rank then runs the distance transform on the full map.
+"""
+from __future__ import annotations
+
+
+def slab_size(depth_blocks: int, world: int) -> int:
+    """Block slices per rank (the last ranks may get fewer, or none)."""
+    return (depth_blocks + world - 1) // world
+
+
+def slab_range(rank: int, world: int, depth_blocks: int) -> tuple[int, int]:
+    """(first block slice, number of block slices) of `rank`; count is 0 for ranks beyond the map."""
+    s = slab_size(depth_blocks, world)
+    z0 = min(rank * s, depth_blocks)
+    return z0, max(0, min(s, depth_blocks - z0))
+
+
+def tiles_of_rank(rank: int, world: int, n_tiles: int) -> range:
+    """Tiles rendered by `rank` — what vkv_render_tiles(tile_first=rank, tile_stride=world) covers."""
+    return range(rank, n_tiles, world)
+
+
+def n_tiles(width: int, height: int, tile_w: int, tile_h: int) -> int:
+    return ((width + tile_w - 1) // tile_w) * ((height + tile_h - 1) // tile_h)
+
+
+def all_gather_occupancy(full, rank: int, world: int, map_extent, gather_buf=None, group=None):
+    """In place: `full` (flat uint8 tensor of Wb*Hb*Db cells, this rank's slab rows already written) receives every other
+    rank's slab rows.  Slabs are padded to the common slab size for all_gather_into_tensor."""
+    import torch
+    import torch.distributed as dist
+
+    Wb, Hb, Db = map_extent
+    plane = Wb * Hb
+    s = slab_size(Db, world)
+    z0, zc = slab_range(rank, world, Db)
+    if gather_buf is None:
+        gather_buf = torch.empty(world * s * plane, dtype=torch.uint8, device=full.device)
+    mine = torch.zeros(s * plane, dtype=torch.uint8, device=full.device)
+    mine[: zc * plane] = full[z0 * plane:(z0 + zc) * plane]
+    dist.all_gather_into_tensor(gather_buf, mine, group=group)
+    for r in range(world):
+        rz0, rzc = slab_range(r, world, Db)
+        if rzc and r != rank:
+            full[rz0 * plane:(rz0 + rzc) * plane] = gather_buf[r * s * plane: r * s * plane + rzc * plane]
+    return full
+
+
+def all_reduce_count(count_tensor, group=None):
+    """Sum of the per-slab occupied-voxel counts (int64 tensor of one element), in place."""
+    import torch.distributed as dist
+
+    dist.all_reduce(count_tensor, group=group)
+    return count_tensor
