@@ -262,9 +262,10 @@ def run_native(args):
             fb_ptr = peer_ptr
     counts_t = torch.zeros(4, dtype=torch.int64, device=dev)
 
+    cams = [scene.look_at_camera(orbit_eye(k, 72, wl), aspect=FW / FH) for k in range(72)]        # synthetic inputs: the camera path
+
     def uniforms(step):
-        cam = scene.look_at_camera(orbit_eye(step, 72, wl), aspect=FW / FH)
-        return vol.make_uniforms(cam, it, wl["clip"])
+        return vol.make_uniforms(cams[step % 72], it, wl["clip"])        # host maths of VolumeRenderSubpass::draw (C ABI call)
 
     def render_step(step, counts_ptr):
         cu, ru = uniforms(step)
@@ -393,8 +394,12 @@ def run_native(args):
         peak_fetch = tex_peak.get("l2_resident_256") if isinstance(tex_peak, dict) else None
         achieved = texel_bytes_per_step / (ms_per_step * 1e-3) / 1e9
         peak = peak_fetch * 8 / 1e9 if peak_fetch else None
+        traffic = None
+        tj = ROOT / "profiles" / "traffic.json"
+        if tj.exists() and args.workload == "c2" and world == 1:
+            traffic = json.loads(tj.read_text()).get("raycast_kernel")        # dram bytes per launch from the committed ncu --set full capture
         roofline = {"kernel": "raycast_kernel", "bound": "texture", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": (achieved / peak) if peak else None, "traffic": None,
+                    "frac": (achieved / peak) if peak else None, "traffic": traffic,
                     "peak_source": "vkv_bench_tex3d measured live: coherent trilinear u8 tex3D fetches/s on an L2-resident 256^3 array x 8 texel bytes per fetch",
                     "algorithmic_bytes_per_launch": texel_bytes_per_step,
                     "definition": "n_vol*(8*(1+gamma)+4)+n_dist texel bytes per frame (SURVEY 8(d))"}
@@ -404,10 +409,13 @@ def run_native(args):
             ach = bytes_ / (ms * 1e-3) / 1e9
             return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                     "algorithmic_bytes_per_launch": bytes_, "ms": ms, "peak_source": peak_src}
-        hbm_rooflines["gradient_vec16_kernel"] = rl(2 * N_vox, float(np.median(t_grad)))
-        hbm_rooflines["occupancy_fast_kernel"] = rl((2 if use_g else 1) * N_vox + M_blk, stage_ms["occupancy"])
-        hbm_rooflines["occupancy_fast_kernel+count"] = rl((2 if use_g else 1) * N_vox, float(np.median(count_ms)))
+        hbm_rooflines["gradient_int_kernel"] = rl(2 * N_vox, float(np.median(t_grad)))
+        hbm_rooflines["gradient_int_kernel"]["note"] = "2 B/voxel algorithmic; the kernel also writes the map into the texture array (+1 B/voxel)"
+        hbm_rooflines["occupancy_tma_kernel"] = rl((2 if use_g else 1) * N_vox + M_blk, stage_ms["occupancy"])
+        hbm_rooflines["occupancy_tma_kernel+count"] = rl((2 if use_g else 1) * N_vox, float(np.median(count_ms)))
+        hbm_rooflines["occupancy_tma_kernel+count"]["note"] = "vkv_compute_occupied_voxel_count: memset + kernel + 8-byte D2H + stream sync inside the timed region"
         hbm_rooflines["distance_map_passes"] = rl((28 if skip == 3 else 6) * M_blk, stage_ms["distance"])
+        hbm_rooflines["distance_map_passes"]["note"] = f"{M_blk} blocks: the map is L2-resident, the HBM fraction is not the meaningful figure (DESIGN.md)"
 
     # ---- CPU baseline (oracle port on the host cores; bounded sample) ------------------------------------------------------
     cpu_baseline = None

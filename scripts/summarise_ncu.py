@@ -54,6 +54,32 @@ for rep in sorted(src.glob(f"{tag}_*.ncu-rep")):
                 i = hdr.index(w)
                 lines.append(f"- {w}: {r[i]} {units[i]}")
         lines.append("")
+# dram traffic per launch of every captured kernel -> profiles/traffic.json (bench.py's roofline.traffic)
+import json
+import re
+traffic = {}
+for rep in sorted(src.glob(f"{tag}_*.ncu-rep")):
+    p = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True)
+    rows = list(csv.reader(p.stdout.splitlines()))
+    if len(rows) < 3 or "dram__bytes_read.sum" not in rows[0]:
+        continue
+    hdr, units = rows[0], rows[1]
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    vals = []
+    for r in rows[2:]:
+        tot = 0.0
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(m)
+            tot += float(r[i].replace(",", "")) * scale.get(units[i], 1)
+        vals.append(tot)
+    name = re.sub(r"^void |<.*$|\(.*$", "", rows[2][hdr.index("Kernel Name")]).split("::")[-1]
+    traffic[name] = sum(vals) / len(vals)
+if traffic:
+    tj = Path("profiles") / "traffic.json"
+    old = json.loads(tj.read_text()) if tj.exists() else {}
+    old.update(traffic)
+    old["_source"] = f"ncu --set full captures of round tag {tag} (scripts/gpu_profile.sh), dram__bytes_read.sum + dram__bytes_write.sum per launch"
+    tj.write_text(json.dumps(old, indent=1))
 out.parent.mkdir(exist_ok=True)
 out.write_text("\n".join(lines))
 print("wrote", out)
