@@ -284,6 +284,22 @@ def run_native(args):
     for s in range(Wm):
         render_step(s, 0)
     barrier()
+    # untimed self-check of the fused gather (N > 1): the frame the ranks assembled in rank 0's HBM through their peer
+    # stores must equal rank 0's own full-frame render of the same view, byte for byte
+    tiles_match = None
+    if world > 1:
+        fb.zero_() if rank == 0 else None
+        barrier()
+        render_step(0, 0)
+        barrier()
+        if rank == 0:
+            full = torch.zeros_like(fb)
+            cu0, ru0 = uniforms(0)
+            vol.render(cu0, ru0, tfu, ropt, FW, FH, full.data_ptr(), 0, 0, stream)
+            torch.cuda.synchronize()
+            tiles_match = bool(torch.equal(full, fb))
+            del full
+        barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = capi.kernel_launch_count()
@@ -436,7 +452,7 @@ def run_native(args):
             "ess_rebuild_ms": {"median": float(np.median(rebuild_ms)), "mean": float(np.mean(rebuild_ms)), "p95": float(np.percentile(rebuild_ms, 95)),
                                "changes": n_changes, "stages": stage_ms, "sharded_z_slabs": world > 1},
             "occupied_voxels": occupied, "occupied_percent": 100.0 * occupied / N_vox,
-            "modes": modes, "e2e": e2e, "gpu_launches": int(launches), "wall_s_timed_region": wall,
+            "modes": modes, "tiles_match_single_gpu_frame": tiles_match, "e2e": e2e, "gpu_launches": int(launches), "wall_s_timed_region": wall,
             "clocks": sampler.summary(), "roofline": roofline, "rooflines_hbm": hbm_rooflines, "tex3d_fetch_per_s": tex_peak,
             "cpu_baseline": cpu_baseline,
         }

@@ -298,8 +298,10 @@ VKV_API int vkv_compute_occupancy_slab(vkv_volume *vol, const vkv_transfer_funct
                                        uint32_t zb_first, uint32_t zb_count, uint64_t *count_dev, void *stream);
 VKV_API int vkv_compute_distance_from_occupancy(vkv_volume *vol, int skipping_type, void *stream);
 
-/* ---- cross-process peer mapping (CUDA IPC) for the fused tile gather -------- */
-#define VKV_IPC_HANDLE_BYTES 64
+/* ---- cross-process peer mapping (CUDA IPC) for the fused tile gather --------
+ * The blob is the CUDA IPC handle of the allocation containing dev_ptr plus dev_ptr's byte offset inside it, so
+ * interior pointers (sub-allocations of a framework's caching allocator) map to the same bytes in the peer. */
+#define VKV_IPC_HANDLE_BYTES 72
 VKV_API int vkv_ipc_export(void *dev_ptr, uint8_t handle_out[VKV_IPC_HANDLE_BYTES]);
 VKV_API int vkv_ipc_open(const uint8_t handle[VKV_IPC_HANDLE_BYTES], void **dev_ptr_out);
 VKV_API int vkv_ipc_close(void *dev_ptr);

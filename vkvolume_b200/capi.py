@@ -16,7 +16,7 @@ LIB_PATH = Path(__file__).resolve().parent / "lib" / "libvkv.so"
 SKIP_NONE, SKIP_BLOCK, SKIP_DISTANCE, SKIP_ANISOTROPIC_DISTANCE = 0, 1, 2, 3
 TEST_NONE, TEST_RAY_ENTRY, TEST_RAY_EXIT, TEST_NUM_TEXTURE_SAMPLES = 0, 1, 2, 3
 FILTER_HARDWARE, FILTER_EXACT = 0, 1
-IPC_HANDLE_BYTES = 64
+IPC_HANDLE_BYTES = 72
 
 
 class VkvError(RuntimeError):

@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <new>
 
 #include "common.cuh"
@@ -544,27 +546,62 @@ int vkv_volume_download_distance_map(vkv_volume *vol, size_t idx, uint8_t *out, 
 }
 int vkv_volume_download_transfer_function(vkv_volume *vol, uint8_t *out, size_t n) { return download(vol, vol ? vol->d_tf : nullptr, 256 * 256 * 4, out, n); }
 
+// The handle blob is the cudaIpcMemHandle_t of the ALLOCATION that contains dev_ptr followed by dev_ptr's byte offset
+// inside it: framework allocators (torch's caching allocator) hand out interior pointers of larger cudaMalloc blocks,
+// and cudaIpcOpenMemHandle always maps the block's base.
+static std::mutex                 g_ipc_mutex;
+static std::map<void *, void *>   g_ipc_bases;        // pointer returned by vkv_ipc_open -> mapped base
+
 int vkv_ipc_export(void *dev_ptr, uint8_t handle_out[VKV_IPC_HANDLE_BYTES])
 {
-	static_assert(sizeof(cudaIpcMemHandle_t) == VKV_IPC_HANDLE_BYTES, "IPC handle size");
+	static_assert(sizeof(cudaIpcMemHandle_t) + sizeof(uint64_t) == VKV_IPC_HANDLE_BYTES, "IPC handle size");
 	VKV_REQUIRE(dev_ptr && handle_out, VKV_ERR_ARGUMENT, "NULL argument");
+	typedef int (*range_fn)(unsigned long long *, size_t *, unsigned long long);        // cuMemGetAddressRange
+	static range_fn get_range = nullptr;
+	if (!get_range) {
+		void                           *fn = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		VKV_CUDA_CHECK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q));
+		VKV_REQUIRE(q == cudaDriverEntryPointSuccess && fn, VKV_ERR_CUDA, "cuMemGetAddressRange is not available");
+		get_range = reinterpret_cast<range_fn>(fn);
+	}
+	unsigned long long base = 0;
+	size_t             size = 0;
+	VKV_REQUIRE(get_range(&base, &size, (unsigned long long) (uintptr_t) dev_ptr) == 0 && base, VKV_ERR_CUDA,
+	            "cuMemGetAddressRange failed: not a device allocation");
 	cudaIpcMemHandle_t h;
-	VKV_CUDA_CHECK(cudaIpcGetMemHandle(&h, dev_ptr));
+	VKV_CUDA_CHECK(cudaIpcGetMemHandle(&h, reinterpret_cast<void *>((uintptr_t) base)));
+	const uint64_t offset = (uint64_t) ((uintptr_t) dev_ptr - (uintptr_t) base);
 	memcpy(handle_out, &h, sizeof h);
+	memcpy(handle_out + sizeof h, &offset, sizeof offset);
 	return VKV_OK;
 }
 int vkv_ipc_open(const uint8_t handle[VKV_IPC_HANDLE_BYTES], void **dev_ptr_out)
 {
 	VKV_REQUIRE(handle && dev_ptr_out, VKV_ERR_ARGUMENT, "NULL argument");
 	cudaIpcMemHandle_t h;
+	uint64_t           offset = 0;
 	memcpy(&h, handle, sizeof h);
-	VKV_CUDA_CHECK(cudaIpcOpenMemHandle(dev_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+	memcpy(&offset, handle + sizeof h, sizeof offset);
+	void *base = nullptr;
+	VKV_CUDA_CHECK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+	*dev_ptr_out = static_cast<uint8_t *>(base) + offset;
+	std::lock_guard<std::mutex> lock(g_ipc_mutex);
+	g_ipc_bases[*dev_ptr_out] = base;
 	return VKV_OK;
 }
 int vkv_ipc_close(void *dev_ptr)
 {
 	VKV_REQUIRE(dev_ptr, VKV_ERR_ARGUMENT, "NULL argument");
-	VKV_CUDA_CHECK(cudaIpcCloseMemHandle(dev_ptr));
+	void *base = nullptr;
+	{
+		std::lock_guard<std::mutex> lock(g_ipc_mutex);
+		auto it = g_ipc_bases.find(dev_ptr);
+		VKV_REQUIRE(it != g_ipc_bases.end(), VKV_ERR_ARGUMENT, "pointer was not returned by vkv_ipc_open");
+		base = it->second;
+		g_ipc_bases.erase(it);
+	}
+	VKV_CUDA_CHECK(cudaIpcCloseMemHandle(base));
 	return VKV_OK;
 }
 
