@@ -193,7 +193,11 @@ def _volume_with_occupancy(ctx, O):
 
 @pytest.mark.parametrize("shape,p", [((8, 9, 10), 0.05), ((16, 12, 20), 0.01), ((5, 24, 7), 0.1), ((1, 1, 30), 0.1), ((3, 1, 1), 0.5),
                                      ((20, 40, 70), 0.002), ((33, 65, 129), 0.0005), ((4, 4, 300), 0.003), ((300, 3, 5), 0.003),
-                                     ((2, 1100, 3), 0.002), ((6, 6, 6), 0.0)])
+                                     ((2, 1100, 3), 0.002), ((6, 6, 6), 0.0),
+                                     # long lines through the fast paths (Wb % 4 == 0): segment-parallel z walk with saturation
+                                     # beyond 255, chamfer y sweep over several TMA chunks, 64-word x rows, sparse sources
+                                     ((300, 8, 16), 0.002), ((40, 300, 32), 0.001), ((70, 36, 128), 0.0005), ((520, 4, 8), 0.001),
+                                     ((4, 8, 2048), 0.0005), ((2, 4, 2052), 0.0008), ((130, 50, 64), 0.00005), ((33, 17, 1024), 0.0002)])
 def test_distance_maps_bit_exact(ctx, shape, p):
     rng = np.random.default_rng(abs(hash(shape)) % 1000)
     O = np.where(rng.random(shape) < p, 0, 255).astype(np.uint8)
@@ -204,6 +208,25 @@ def test_distance_maps_bit_exact(ctx, shape, p):
     assert np.array_equal(vol.download_distance_map(0), orc.distance_map(O))
     vol.compute_distance_map(tfu, SKIP_ANISOTROPIC_DISTANCE)
     assert vol.map_extent == O.shape[::-1]
+    want = orc.distance_map_anisotropic(O)
+    for i in range(8):
+        assert np.array_equal(vol.download_distance_map(i), want[i]), f"octant map {i}"
+    vol.close()
+
+
+@pytest.mark.parametrize("shape,cells", [((600, 8, 16), [(0, 0, 0)]), ((600, 8, 16), [(599, 7, 15), (300, 0, 8)]),
+                                         ((8, 600, 16), [(7, 0, 3)]), ((4, 8, 1024), [(0, 0, 1023)]), ((290, 12, 36), [(289, 0, 0), (0, 11, 35)]),
+                                         ((64, 64, 64), []), ((512, 4, 32), [(255, 1, 16)])])
+def test_distance_maps_saturation_and_far_sources(ctx, shape, cells):
+    """Single far sources: every line saturates at 255 somewhere (the cap of distance_map.comp:77,96) and the segment heads
+    of the z walk / the chunk boundaries of the y sweep sit in empty space."""
+    O = np.full(shape, 255, np.uint8)
+    for c in cells:
+        O[c] = 0
+    vol, tfu = _volume_with_occupancy(ctx, O)
+    vol.compute_distance_map(tfu, SKIP_DISTANCE)
+    assert np.array_equal(vol.download_distance_map(0), orc.distance_map(O))
+    vol.compute_distance_map(tfu, SKIP_ANISOTROPIC_DISTANCE)
     want = orc.distance_map_anisotropic(O)
     for i in range(8):
         assert np.array_equal(vol.download_distance_map(i), want[i]), f"octant map {i}"

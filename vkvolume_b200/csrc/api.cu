@@ -460,6 +460,25 @@ int vkv_render_to_host(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv
 	DeviceGuard  guard(vol->ctx->device);
 	cudaStream_t s     = (cudaStream_t) stream;
 	const size_t bytes = (size_t) width * height * 4;
+	// Page-locked destination (cudaHostAlloc / cudaHostRegister / torch pin_memory): the ray caster's epilogue stores
+	// the RGBA8 pixels straight into it over PCIe, so the transfer of finished pixels overlaps the rays still marching
+	// and no staging frame or copy follows the kernel.  Pageable destinations take the staged copy below.
+	{
+		cudaPointerAttributes attr{};
+		const char           *knob = getenv("VKV_E2E_ZEROCOPY");
+		const bool            want = knob && atoi(knob) != 0;        // opt-in: measured on B200 (scripts/e2e_probe.py) the 32-byte PCIe writes of the 8x4-pixel warp tiles cost more (0.35 ms) than kernel + bulk copy (0.31 ms)
+		if (want && cudaPointerGetAttributes(&attr, rgba8_host) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
+			vkv_sample_counts *cd = counts_host ? vol->d_counts_scratch : nullptr;
+			if (counts_host) VKV_CUDA_CHECK(cudaMemsetAsync(vol->d_counts_scratch, 0, sizeof(vkv_sample_counts), s));
+			if ((rc = launch_render(vol, cam, ray, tfu, opt, width, height, TW, TH, 0, 1, -1, static_cast<uint8_t *>(attr.devicePointer), nullptr, cd, s)))
+				return rc;
+			if (counts_host) VKV_CUDA_CHECK(cudaMemcpyAsync(vol->h_count, vol->d_counts_scratch, sizeof(vkv_sample_counts), cudaMemcpyDeviceToHost, s));
+			VKV_CUDA_CHECK(cudaStreamSynchronize(s));
+			if (counts_host) memcpy(counts_host, vol->h_count, sizeof(vkv_sample_counts));
+			return VKV_OK;
+		}
+		cudaGetLastError();        // a pageable pointer makes cudaPointerGetAttributes fail on old drivers: not an error here
+	}
 	if (vol->fb_scratch_bytes < bytes) {
 		cudaFree(vol->d_fb_scratch);
 		vol->d_fb_scratch     = nullptr;

@@ -88,44 +88,43 @@ __global__ void __launch_bounds__(256) xpass_ballot_kernel(const uint8_t *__rest
 
 // Same, four cells per lane: a warp handles 128 cells per step with one 32-bit load and one 32-bit
 // store per lane; the 4-bit occupancy nibbles are merged into mask words with three xor-shuffles.
-// Needs Wb % 4 == 0 (rows then start 4-byte aligned).
-template <int DIR>
-__device__ __forceinline__ unsigned nearest_occupied(const unsigned *words, int w, int b)
-{
-	unsigned d = 255;
-	if (DIR >= 0) {
-		const unsigned m = words[w] >> b;
-		if (m) d = min(d, (unsigned) (__ffs(m) - 1));
-		else {
-#pragma unroll
-			for (int k = 1; k <= 8; ++k) {
-				const unsigned mk = words[w + k];
-				if (mk) { d = min(d, (unsigned) (k * 32 - b + __ffs(mk) - 1)); break; }
-			}
-		}
+// The search for the nearest set bit is O(1) whatever the distance: a 64-bit mask of the row's NON-ZERO words
+// (two ballots) names the word that holds it, so an empty stretch costs two bit scans instead of a loop over
+// up to eight words per side; only the outer cells of a lane's four are searched, the inner ones follow from
+// d(x) = occupied ? 0 : d(x +- 1) + 1.   Needs Wb % 4 == 0 (rows then start 4-byte aligned).
+struct RowBits {
+	const unsigned    *words;
+	unsigned long long nz;        // bit w: words[w] != 0
+	// distance from bit `bit` of word w to the nearest set bit at or after it (255: none within 254)
+	__device__ __forceinline__ unsigned right(int w, int bit) const
+	{
+		const unsigned m = words[w] >> bit;
+		if (m) return (unsigned) (__ffs(m) - 1);
+		const unsigned long long rest = w < 63 ? nz >> (w + 1) : 0ull;
+		if (!rest) return 255u;
+		const int k = __ffsll((long long) rest);        // the set bit is in word w + k
+		return min((unsigned) (k * 32 - bit + __ffs(words[w + k]) - 1), 255u);
 	}
-	if (DIR <= 0) {
-		const unsigned m = words[w] << (31 - b);
-		if (m) d = min(d, (unsigned) __clz(m));
-		else {
-#pragma unroll
-			for (int k = 1; k <= 8; ++k) {
-				const unsigned mk = words[w - k];
-				if (mk) { d = min(d, (unsigned) (b + 1 + (k - 1) * 32 + __clz(mk))); break; }
-			}
-		}
+	// ... at or before it
+	__device__ __forceinline__ unsigned left(int w, int bit) const
+	{
+		const unsigned m = words[w] << (31 - bit);
+		if (m) return (unsigned) __clz(m);
+		const unsigned long long rest = nz & ((1ull << w) - 1ull);
+		if (!rest) return 255u;
+		const int w2 = 63 - __clzll((long long) rest);
+		return min((unsigned) (bit + 1 + (w - 1 - w2) * 32 + __clz(words[w2])), 255u);
 	}
-	return d;
-}
+};
 
 template <int DIR>
 __global__ void __launch_bounds__(256) xpass_vec4_kernel(const uint8_t *__restrict__ O, uint8_t *__restrict__ out, uint32_t Wb, uint64_t nrows)
 {
-	__shared__ unsigned s_words[8][kRowWordsMax + 16];
+	__shared__ unsigned s_words[8][kRowWordsMax];
 	const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	unsigned      *words = &s_words[warp][8];
+	unsigned      *words = s_words[warp];
 	const uint32_t nseg  = (Wb + 127) / 128;
-	for (int i = lane; i < kRowWordsMax + 16; i += 32) s_words[warp][i] = 0;
+	for (int i = lane; i < kRowWordsMax; i += 32) words[i] = 0;
 	__syncwarp();
 	for (uint64_t row = (uint64_t) blockIdx.x * 8 + warp; row < nrows; row += (uint64_t) gridDim.x * 8) {
 		const uint8_t *src = O + row * Wb;
@@ -142,14 +141,35 @@ __global__ void __launch_bounds__(256) xpass_vec4_kernel(const uint8_t *__restri
 			if ((lane & 7) == 0) words[sgm * 4 + (lane >> 3)] = v;
 		}
 		__syncwarp();
+		RowBits rb;
+		rb.words = words;
+		rb.nz    = (unsigned long long) __ballot_sync(0xffffffffu, words[lane] != 0u) |
+		        ((unsigned long long) __ballot_sync(0xffffffffu, words[32 + lane] != 0u) << 32);
 		for (uint32_t sgm = 0; sgm < nseg; ++sgm) {
 			const uint32_t x = sgm * 128 + lane * 4;
 			if (x < Wb) {
-				const int w = (int) (x >> 5), b = (int) (x & 31);
-				unsigned  r = 0;
+				const int      w = (int) (x >> 5), b = (int) (x & 31);
+				const unsigned occ = (words[w] >> b) & 0xfu;
+				unsigned       d[4] = {255u, 255u, 255u, 255u};
+				if (DIR >= 0) {
+					unsigned r = rb.right(w, b + 3);
+					d[3]       = r;
 #pragma unroll
-				for (int k = 0; k < 4; ++k) r |= nearest_occupied<DIR>(words, w, b + k) << (8 * k);
-				*reinterpret_cast<unsigned *>(out + row * Wb + x) = r;
+					for (int k = 2; k >= 0; --k) {
+						r    = ((occ >> k) & 1u) ? 0u : min(r + 1u, 255u);
+						d[k] = r;
+					}
+				}
+				if (DIR <= 0) {
+					unsigned l = rb.left(w, b);
+					d[0]       = min(d[0], l);
+#pragma unroll
+					for (int k = 1; k < 4; ++k) {
+						l    = ((occ >> k) & 1u) ? 0u : min(l + 1u, 255u);
+						d[k] = min(d[k], l);
+					}
+				}
+				*reinterpret_cast<unsigned *>(out + row * Wb + x) = d[0] | (d[1] << 8) | (d[2] << 16) | (d[3] << 24);
 			}
 		}
 		__syncwarp();
@@ -344,42 +364,57 @@ __device__ __forceinline__ void d_tma_load_1d(void *smem_dst, const void *gmem_s
 	             : "memory");
 }
 
-// The input rows arrive by 1-D bulk TMA copies, kSweepRows rows (one contiguous block of the slice) per copy,
-// double-buffered on two mbarriers: the serial row recurrence never waits on a global load, it reads shared memory.
-constexpr int kSweepRows = 32;
-template <int XDIR>        // XDIR 0: isotropic (two-sided x, 3 neighbours, in-place second sweep); +-1: one-sided
-__global__ void __launch_bounds__(1024) ysweep_kernel(const uint8_t *__restrict__ g, uint8_t *__restrict__ dst0, uint8_t *__restrict__ dst1,
-                                                      uint32_t Wb, uint32_t Hb)
+// The input rows arrive by 1-D bulk TMA copies, kSweepRows rows (one contiguous block of the slice) per copy, through a
+// ring of kSweepSlots buffers with one mbarrier each: the serial row recurrence never waits on a global load.
+// A thread owns FOUR adjacent cells.  The previous row lives in shared memory as 16-bit lanes (two u16x2 words per
+// thread), so the whole row step is a handful of native packed instructions with a short dependency chain — the step
+// latency, not the instruction count, is what bounds a sweep of Hb dependent rows:
+//     neighbours x +- 1 : 16-bit funnel shifts against the adjacent words
+//     min of the three  : VIMNMX3.U16x2
+//     min(g, m + 1)     : VIADDMNMX.U16x2     (m <= 255, so m + 1 needs no saturation; the result is <= g <= 255)
+// and a 1024-cell row is 8 warps instead of 32 — the per-row barrier is cheaper and several slices share an SM.
+constexpr int kSweepRows  = 8;
+constexpr int kSweepSlots = 6;
+__device__ __forceinline__ unsigned d_prmt(unsigned a, unsigned b, unsigned sel)
 {
-	extern __shared__ __align__(128) uint8_t s_dyn[];        // 2 chunks of kSweepRows x Wb | 2 x (Wb + 2) row buffers
-	__shared__ __align__(8) uint64_t s_bar[2];
-	const uint32_t x      = threadIdx.x;
-	const bool     active = x < Wb;
+	unsigned r;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+	return r;
+}
+template <int XDIR>        // XDIR 0: isotropic (two-sided x, 3 neighbours, in-place second sweep); +-1: one-sided
+__global__ void __launch_bounds__(256) ysweep_kernel(const uint8_t *__restrict__ g, uint8_t *__restrict__ dst0, uint8_t *__restrict__ dst1,
+                                                     uint32_t Wb, uint32_t Hb)
+{
+	extern __shared__ __align__(128) uint8_t s_dyn[];        // kSweepSlots chunks of kSweepRows x Wb | 2 row buffers of Wb/4 + 2 uint2
+	__shared__ __align__(8) uint64_t s_bar[kSweepSlots];
+	const uint32_t t      = threadIdx.x;                     // group of 4 cells of the row
+	const uint32_t W4     = Wb >> 2;
+	const bool     active = t < W4;
 	const size_t   slice  = (size_t) blockIdx.x * Wb * Hb;
 	const uint32_t chunk_bytes = kSweepRows * Wb;
 	uint8_t       *ring = s_dyn;
-	uint8_t       *buf0 = s_dyn + 2 * (size_t) chunk_bytes + 16 + 1, *buf1 = buf0 + (Wb + 2);
+	uint2         *buf0 = reinterpret_cast<uint2 *>(s_dyn + (size_t) kSweepSlots * chunk_bytes) + 1, *buf1 = buf0 + (W4 + 2);
 	const uint32_t nchunks = (Hb + kSweepRows - 1) / kSweepRows;
-	if (x == 0) {
-		d_mbar_init(&s_bar[0], 1);
-		d_mbar_init(&s_bar[1], 1);
+	constexpr unsigned kFar = 0x00ff00ffu;        // 255 in both lanes
+	if (t == 0) {
+		for (int i = 0; i < kSweepSlots; ++i) d_mbar_init(&s_bar[i], 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
-	unsigned issued = 0;        // copies issued so far (thread 0): copy n lands in ring buffer n & 1, phase (n >> 1) & 1
+	unsigned issued = 0;        // copies issued so far (thread 0): copy n lands in ring slot n % kSweepSlots, phase (n / kSweepSlots) & 1
 	for (int sweep = 0; sweep < 2; ++sweep) {
 		// sweep 0 walks y upwards (sources at y' <= y), sweep 1 downwards (sources at y' >= y)
 		const uint8_t  *src  = (XDIR == 0 && sweep == 1) ? dst0 : g;
 		uint8_t        *dst  = XDIR == 0 ? dst0 : (sweep == 0 ? dst1 : dst0);
-		const ptrdiff_t step = sweep == 0 ? (ptrdiff_t) Wb : -(ptrdiff_t) Wb;
-		uint8_t        *dp   = dst + slice + (sweep == 0 ? 0 : (size_t) (Hb - 1) * Wb) + x;
+		const ptrdiff_t step = sweep == 0 ? (ptrdiff_t) W4 : -(ptrdiff_t) W4;        // in words
+		unsigned       *dp   = reinterpret_cast<unsigned *>(dst + slice + (sweep == 0 ? 0 : (size_t) (Hb - 1) * Wb)) + t;
 		// chunk c of this sweep = rows [lo, lo + n) of the slice, consumed upwards (sweep 0) or downwards (sweep 1)
 		auto issue = [&](uint32_t c) {
 			const uint32_t i0 = c * kSweepRows, n = min((uint32_t) kSweepRows, Hb - i0);
 			const uint32_t lo = sweep == 0 ? i0 : Hb - i0 - n;
-			uint64_t      *bar = &s_bar[issued & 1u];
-			d_mbar_expect_tx(bar, n * Wb);
-			d_tma_load_1d(ring + (size_t) (issued & 1u) * chunk_bytes, src + slice + (size_t) lo * Wb, n * Wb, bar);
+			const unsigned slot = issued % kSweepSlots;
+			d_mbar_expect_tx(&s_bar[slot], n * Wb);
+			d_tma_load_1d(ring + (size_t) slot * chunk_bytes, src + slice + (size_t) lo * Wb, n * Wb, &s_bar[slot]);
 			++issued;
 		};
 		if (XDIR == 0 && sweep == 1) {
@@ -387,30 +422,43 @@ __global__ void __launch_bounds__(1024) ysweep_kernel(const uint8_t *__restrict_
 			__threadfence();
 			asm volatile("fence.proxy.async;" ::: "memory");
 		}
-		if (x == 0) { buf0[-1] = 255; buf1[-1] = 255; buf0[Wb] = 255; buf1[Wb] = 255; }
-		if (active) buf0[x] = 255;        // "row -1": nothing behind the first row
-		__syncthreads();
-		unsigned consumed = issued;       // uniform bookkeeping of the copy sequence number (every thread tracks it)
-		if (x == 0) {
-			issue(0);
-			if (nchunks > 1) issue(1);
+		if (t == 0) {
+			buf0[-1] = make_uint2(kFar, kFar); buf1[-1] = make_uint2(kFar, kFar);
+			buf0[W4] = make_uint2(kFar, kFar); buf1[W4] = make_uint2(kFar, kFar);
 		}
+		if (active) buf0[t] = make_uint2(kFar, kFar);        // "row -1": nothing behind the first row
+		__syncthreads();
+		const unsigned consumed = issued;       // uniform bookkeeping of the copy sequence number (every thread tracks it)
+		if (t == 0)
+			for (uint32_t c = 0; c < (uint32_t) kSweepSlots && c < nchunks; ++c) issue(c);
 		for (uint32_t c = 0; c < nchunks; ++c) {
-			const unsigned seq = consumed + c;
-			d_mbar_wait(&s_bar[seq & 1u], (seq >> 1) & 1u);
-			const uint32_t n  = min((uint32_t) kSweepRows, Hb - c * kSweepRows);
-			const uint8_t *cb = ring + (size_t) (seq & 1u) * chunk_bytes;
+			const unsigned seq = consumed + c, slot = seq % kSweepSlots;
+			d_mbar_wait(&s_bar[slot], (seq / kSweepSlots) & 1u);
+			const uint32_t  n  = min((uint32_t) kSweepRows, Hb - c * kSweepRows);
+			const unsigned *cb = reinterpret_cast<const unsigned *>(ring + (size_t) slot * chunk_bytes);
 			// rows alternate between the two row buffers; a chunk has an even number of rows unless it is the last one, so the
 			// buffer roles are compile-time constants of the 2-row unrolled loop
-			const uint8_t *cp = cb + (sweep == 0 ? 0 : (size_t) (n - 1) * Wb) + x;        // this thread's cell in the chunk's first row
-			auto row_step = [&](const uint8_t *prev, uint8_t *now) {
+			const unsigned *cp = cb + (sweep == 0 ? 0 : (size_t) (n - 1) * W4) + t;        // this thread's word in the chunk's first row
+			auto row_step = [&](const uint2 *prev, uint2 *now) {
 				if (active) {
-					unsigned m = prev[x];
-					if (XDIR >= 0) m = min(m, (unsigned) prev[x + 1]);
-					if (XDIR <= 0) m = min(m, (unsigned) prev[(int) x - 1]);
-					const unsigned val = min((unsigned) *cp, m + 1u);
-					now[x] = (uint8_t) val;
-					*dp    = (uint8_t) val;
+					const unsigned gw = *cp;
+					const uint2    p  = prev[t];                       // cells 0,1 | 2,3 of this thread in the previous row
+					const unsigned mid = __funnelshift_r(p.x, p.y, 16);        // cells 1,2
+					unsigned       ma = p.x, mb = p.y;
+					if (XDIR == 0) {
+						ma = __vimin3_u16x2(p.x, __funnelshift_l(prev[(int) t - 1].y, p.x, 16), mid);        // cells -1,0 and 1,2
+						mb = __vimin3_u16x2(p.y, mid, __funnelshift_r(p.y, prev[t + 1].x, 16));              // cells 1,2 and 3,4
+					} else if (XDIR > 0) {
+						ma = __vminu2(p.x, mid);
+						mb = __vminu2(p.y, __funnelshift_r(p.y, prev[t + 1].x, 16));
+					} else {
+						ma = __vminu2(p.x, __funnelshift_l(prev[(int) t - 1].y, p.x, 16));
+						mb = __vminu2(p.y, mid);
+					}
+					const unsigned va = __viaddmin_u16x2(ma, 0x00010001u, d_prmt(gw, 0u, 0x4140u));
+					const unsigned vb = __viaddmin_u16x2(mb, 0x00010001u, d_prmt(gw, 0u, 0x4342u));
+					now[t] = make_uint2(va, vb);
+					*dp    = d_prmt(va, vb, 0x6420u);
 					dp += step;
 					cp += step;
 				}
@@ -422,8 +470,8 @@ __global__ void __launch_bounds__(1024) ysweep_kernel(const uint8_t *__restrict_
 				row_step(buf1, buf0);
 			}
 			if (k < n) row_step(buf0, buf1);        // odd tail: only ever in the last chunk of a sweep
-			// every thread is past the chunk: its ring buffer may be refilled
-			if (x == 0 && c + 2 < nchunks) issue(c + 2);
+			// every thread is past the chunk: its ring slot may be refilled
+			if (t == 0 && c + kSweepSlots < nchunks) issue(c + kSweepSlots);
 		}
 		issued = consumed + nchunks;        // keep every thread's view of the sequence number in step with thread 0's
 	}
@@ -435,15 +483,39 @@ __global__ void __launch_bounds__(1024) ysweep_kernel(const uint8_t *__restrict_
 //                                                                 r + 1  otherwise ),
 // i.e. ONE range-minimum query per cell instead of an 8-step binary search; the two-sided value is min(F, B) with B the
 // mirror image.  A CTA owns TW adjacent columns: it stages them and builds the sparse range-minimum table four columns
-// per thread (32-bit shared-memory accesses, packed byte minimum), walks them with 2 x TW threads — one per column and
-// direction, every thread of the CTA — and writes the result rows as 32-bit words.
+// per thread (32-bit shared-memory accesses, packed byte minimum).  The walk itself is cut into segments of kWalkSeg
+// cells: a walker (one thread per column, direction and segment) finds the value at the head of its segment with the
+// 8-step binary search and walks from there, so a line of L cells is 2 L / kWalkSeg independent dependency chains of
+// ~kWalkSeg + 8 queries instead of two chains of L — the CTA's shared-memory tables are shared by up to 1024 walkers
+// (with one walker per column and direction a long line left most of the SM idle).  Result rows leave as 32-bit words.
 // MODE 0: dst0 = min(F, B) | 3: dst0 = F (towards +z), dst1 = B (towards -z).   Needs Wb % 4 == 0 and TW % 4 == 0.
+constexpr int kWalkSeg = 32;
+
+// F(z) towards +z (SIDE > 0) or -z (SIDE < 0) from scratch: smallest r with min h over the r + 1 cells from z on <= r.
+// Only radii <= 254 are ever tested (hi <= 255), so windows have at most 255 cells: table levels 0..7.
+template <int SIDE>
+__device__ __forceinline__ unsigned walk_head(const uint8_t *__restrict__ T, int L, int TW, size_t lst, int z, int col, unsigned h0)
+{
+	unsigned lo = 0, hi = min(h0, 255u);
+	while (lo < hi) {
+		const int r = (int) ((lo + hi) >> 1);
+		const int a = SIDE > 0 ? z : max(z - r, 0);
+		const int b = SIDE > 0 ? min(z + r, L - 1) : z;
+		const int k = 31 - __clz(b - a + 1);
+		const uint8_t *Tk = T + (size_t) k * lst;
+		const unsigned w  = min((unsigned) Tk[a * TW + col], (unsigned) Tk[(b - (1 << k) + 1) * TW + col]);
+		if (w <= (unsigned) r) hi = (unsigned) r;
+		else lo = (unsigned) r + 1;
+	}
+	return lo;
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(256) zwalk_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst0, uint8_t *__restrict__ dst1,
-                                                    uint32_t Wb, uint32_t L, size_t line_stride, size_t outer_stride, int TW, int nlev)
+__global__ void __launch_bounds__(1024) zwalk_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst0, uint8_t *__restrict__ dst1,
+                                                     uint32_t Wb, uint32_t L, size_t line_stride, size_t outer_stride, int TW, int nlev)
 {
 	extern __shared__ __align__(16) uint8_t T[];        // nlev levels of L x TW bytes, then the F and B lines (2 x L x TW)
-	const int      nthreads = blockDim.x;               // = 2 * TW
+	const int      nthreads = blockDim.x;
 	const int      TW4 = TW >> 2;                       // words per row
 	const uint32_t x0  = blockIdx.x * TW;
 	const size_t   base = (size_t) blockIdx.y * outer_stride + x0;
@@ -470,38 +542,45 @@ __global__ void __launch_bounds__(256) zwalk_kernel(const uint8_t *__restrict__ 
 		__syncthreads();
 	}
 	{
-		const int col = threadIdx.x % TW, Li = (int) L;
-		if (threadIdx.x < TW) {        // F: towards +z, walking down from the last cell
-			unsigned r = T[(Li - 1) * TW + col];
-			Fl[(Li - 1) * TW + col] = (uint8_t) r;
-			for (int z = Li - 2; z >= 0; --z) {
-				const unsigned hz = T[z * TW + col];
-				unsigned cand = min(r + 1u, 255u);
-				if (r > 0u && hz > r) {        // h(z) <= r decides F(z) = h(z) whatever the window holds
-					const int a = z + 1, b = min(z + (int) r, Li - 1);
-					const int k = 31 - __clz(b - a + 1);
-					const uint8_t *Tk = T + (size_t) k * lst;
-					const unsigned w  = min((unsigned) Tk[a * TW + col], (unsigned) Tk[(b - (1 << k) + 1) * TW + col]);
-					if (w <= r) cand = r;
+		const int Li = (int) L, nseg = (Li + kWalkSeg - 1) / kWalkSeg;
+		const int nwalk = 2 * nseg * TW;        // walker id = (direction * nseg + segment) * TW + column
+		for (int wk = threadIdx.x; wk < nwalk; wk += nthreads) {
+			const int col = wk % TW, sd = wk / TW, seg = sd % nseg;
+			const int z_lo = seg * kWalkSeg, z_hi = min(z_lo + kWalkSeg, Li) - 1;        // inclusive
+			if (sd < nseg) {        // F: towards +z, walking down from the segment's last cell
+				unsigned r = T[z_hi * TW + col];
+				if (z_hi != Li - 1) r = walk_head<1>(T, Li, TW, lst, z_hi, col, r);
+				Fl[z_hi * TW + col] = (uint8_t) r;
+				for (int z = z_hi - 1; z >= z_lo; --z) {
+					const unsigned hz = T[z * TW + col];
+					unsigned cand = min(r + 1u, 255u);
+					if (r > 0u && hz > r) {        // h(z) <= r decides F(z) = h(z) whatever the window holds
+						const int a = z + 1, b = min(z + (int) r, Li - 1);
+						const int k = 31 - __clz(b - a + 1);
+						const uint8_t *Tk = T + (size_t) k * lst;
+						const unsigned w  = min((unsigned) Tk[a * TW + col], (unsigned) Tk[(b - (1 << k) + 1) * TW + col]);
+						if (w <= r) cand = r;
+					}
+					r = min(hz, cand);
+					Fl[z * TW + col] = (uint8_t) r;
 				}
-				r = min(hz, cand);
-				Fl[z * TW + col] = (uint8_t) r;
-			}
-		} else {                       // B: towards -z, walking up from the first cell
-			unsigned r = T[col];
-			Bl[col] = (uint8_t) r;
-			for (int z = 1; z < Li; ++z) {
-				const unsigned hz = T[z * TW + col];
-				unsigned cand = min(r + 1u, 255u);
-				if (r > 0u && hz > r) {
-					const int b = z - 1, a = max(z - (int) r, 0);
-					const int k = 31 - __clz(b - a + 1);
-					const uint8_t *Tk = T + (size_t) k * lst;
-					const unsigned w  = min((unsigned) Tk[a * TW + col], (unsigned) Tk[(b - (1 << k) + 1) * TW + col]);
-					if (w <= r) cand = r;
+			} else {                // B: towards -z, walking up from the segment's first cell
+				unsigned r = T[z_lo * TW + col];
+				if (z_lo != 0) r = walk_head<-1>(T, Li, TW, lst, z_lo, col, r);
+				Bl[z_lo * TW + col] = (uint8_t) r;
+				for (int z = z_lo + 1; z <= z_hi; ++z) {
+					const unsigned hz = T[z * TW + col];
+					unsigned cand = min(r + 1u, 255u);
+					if (r > 0u && hz > r) {
+						const int b = z - 1, a = max(z - (int) r, 0);
+						const int k = 31 - __clz(b - a + 1);
+						const uint8_t *Tk = T + (size_t) k * lst;
+						const unsigned w  = min((unsigned) Tk[a * TW + col], (unsigned) Tk[(b - (1 << k) + 1) * TW + col]);
+						if (w <= r) cand = r;
+					}
+					r = min(hz, cand);
+					Bl[z * TW + col] = (uint8_t) r;
 				}
-				r = min(hz, cand);
-				Bl[z * TW + col] = (uint8_t) r;
 			}
 		}
 	}
@@ -574,12 +653,12 @@ static int run_ysweep(const vkv_volume *vol, const uint8_t *g, uint8_t *dst0, ui
 {
 	const uint32_t Wb = vol->dim_b[0], Hb = vol->dim_b[1], Db = vol->dim_b[2];
 	*done = false;
-	// one cell per thread; bulk copies need 16-byte aligned row blocks (slice size, hence every block start and length)
-	if (Wb > 1024u || ((size_t) Wb * Hb) % 16 != 0 || ((size_t) kSweepRows * Wb) % 16 != 0 || (reinterpret_cast<uintptr_t>(g) % 16) != 0 ||
-	    (reinterpret_cast<uintptr_t>(dst0) % 16) != 0)
+	// four cells per thread; bulk copies need 16-byte aligned row blocks (slice size, hence every block start and length)
+	if (Wb > 1024u || Wb % 4 != 0 || ((size_t) Wb * Hb) % 16 != 0 || ((size_t) kSweepRows * Wb) % 16 != 0 || (reinterpret_cast<uintptr_t>(g) % 16) != 0 ||
+	    (reinterpret_cast<uintptr_t>(dst0) % 16) != 0 || (dst1 && (reinterpret_cast<uintptr_t>(dst1) % 16) != 0))
 		return VKV_OK;        // otherwise the search kernel
-	const int    threads = (int) ((Wb + 31u) / 32u * 32u);
-	const size_t smem    = 2 * (size_t) kSweepRows * Wb + 16 + 2 * ((size_t) Wb + 2);
+	const int    threads = (int) ((Wb / 4 + 31u) / 32u * 32u);
+	const size_t smem    = (size_t) kSweepSlots * kSweepRows * Wb + 2 * ((size_t) Wb / 4 + 2) * sizeof(uint2) + 16;
 	static bool configured = false;
 	if (!configured) {
 		VKV_CUDA_CHECK(cudaFuncSetAttribute(ysweep_kernel<XDIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -601,17 +680,23 @@ static int run_zwalk(const vkv_volume *vol, const uint8_t *src, uint8_t *dst0, u
 	const uint32_t max_window = std::min<uint32_t>(255u, L);
 	int            nlev       = 1;
 	while ((2u << (nlev - 1)) <= max_window) ++nlev;
-	int TW = 64;
-	while (TW > 8 && (size_t) (nlev + 2) * L * TW > (size_t) 72 * 1024) TW >>= 1;
-	const size_t smem = (size_t) (nlev + 2) * L * TW;
+	// 32 columns per CTA (a warp of walkers reads 32 consecutive bytes of a table row) unless the tables then exceed what
+	// lets a few CTAs share an SM; narrower tiles for long lines
+	const size_t per_col = (size_t) (nlev + 2) * L;
+	int          TW      = 32;
+	while (TW > 8 && per_col * TW > (size_t) 100 * 1024) TW >>= 1;
+	if (per_col * TW <= (size_t) 50 * 1024 && Wb >= 64 && L >= 4u * kWalkSeg) TW = 64;
+	const size_t smem = per_col * TW;
 	if (smem > (size_t) 200 * 1024) return VKV_OK;
 	static bool configured = false;
 	if (!configured) {
 		VKV_CUDA_CHECK(cudaFuncSetAttribute(zwalk_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 		configured = true;
 	}
+	const int  nseg    = (int) ((L + kWalkSeg - 1) / kWalkSeg);
+	const int  threads = std::min(1024, std::max(64, (2 * nseg * TW + 31) / 32 * 32));
 	const dim3 grid((Wb + TW - 1) / TW, Hb);
-	zwalk_kernel<MODE><<<grid, 2 * TW, smem, s>>>(src, dst0, dst1, Wb, L, (size_t) Wb * Hb, (size_t) Wb, TW, nlev);
+	zwalk_kernel<MODE><<<grid, threads, smem, s>>>(src, dst0, dst1, Wb, L, (size_t) Wb * Hb, (size_t) Wb, TW, nlev);
 	VKV_LAUNCHED();
 	*done = true;
 	return VKV_OK;
