@@ -284,6 +284,8 @@ VKV_API uint8_t *vkv_volume_device_transfer_function(vkv_volume *vol);
 /* Debug read-backs to HOST memory (synchronous). */
 VKV_API int vkv_volume_download_voxels(vkv_volume *vol, uint8_t *out, size_t out_size);
 VKV_API int vkv_volume_download_gradient(vkv_volume *vol, uint8_t *out, size_t out_size);
+/* The copy of the gradient map the ray caster samples (the texture array behind Volume::get_gradient). */
+VKV_API int vkv_volume_download_gradient_texture(vkv_volume *vol, uint8_t *out, size_t out_size);
 VKV_API int vkv_volume_download_distance_map(vkv_volume *vol, size_t idx, uint8_t *out, size_t out_size);
 VKV_API int vkv_volume_download_transfer_function(vkv_volume *vol, uint8_t *out, size_t out_size);
 /* Replace the gradient map / occupancy input (parity tests feed the oracle's G). */

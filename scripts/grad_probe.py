@@ -21,8 +21,14 @@ capi.synth_volume(ctx, wl["kind"], wl["seed"], W, H, D, vol.device_voxels(), str
 vol.upload_device(vol.device_voxels(), stream)
 tfu = capi.transfer_function_uniform(VolumeOptions(gradient_min=0.0, gradient_max=0.2))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for name, env in (("fp32", {"VKV_GRAD_FP32": "1"}), ("int_nosurf", {"VKV_GRAD_NOSURF": "1"}), ("int_surf", {})):
-    for k in ("VKV_GRAD_FP32", "VKV_GRAD_NOSURF"):
+VARIANTS = {"v1_int_surf": {"VKV_GRAD_V1": "1"}, "flat_nosurf": {"VKV_GRAD_NOSURF": "1"}, "flat_surf": {},
+            "flat_surf_c2": {"VKV_GRAD_CTAS": "2"}, "flat_surf_c4": {"VKV_GRAD_CTAS": "4"}, "flat_surf_c3": {"VKV_GRAD_CTAS": "3"},
+            "flat_surf_c1": {"VKV_GRAD_CTAS": "1"}}
+only = os.environ.get("GRAD_PROBE_ONLY")
+for name, env in VARIANTS.items():
+    if only and name not in only.split(","):
+        continue
+    for k in ("VKV_GRAD_FP32", "VKV_GRAD_NOSURF", "VKV_GRAD_V1", "VKV_GRAD_CTAS"):
         os.environ.pop(k, None)
     os.environ.update(env)
     ts = []

@@ -128,7 +128,30 @@ def test_gradient_integer_path_byte_exact(ctx, kind):
     vol = capi.Volume(ctx, W, H, D)
     vol.upload(V)
     vol.compute_gradient_map(capi.transfer_function_uniform(VolumeOptions(gradient_min=0.0, gradient_max=0.2)))
-    assert np.array_equal(vol.download_gradient(), orc.gradient_map(V))
+    Gref = orc.gradient_map(V)
+    assert np.array_equal(vol.download_gradient(), Gref)
+    assert np.array_equal(vol.download_gradient_texture(), Gref)        # the copy the ray caster samples
+    vol.close()
+
+
+@pytest.mark.parametrize("shape,kind", [((130, 200, 256), "blobs"), ((70, 90, 1024), "low_noise"), ((300, 64, 48), "noise")])
+def test_gradient_persistent_walk_byte_exact(ctx, shape, kind):
+    """More 16-voxel chunks than resident threads: every thread of the flat kernel walks several chunks, its tie queue
+    carries over between them, and ties are patched into both copies of the map (linear + texture array)."""
+    D, H, W = shape
+    rng = np.random.default_rng(D + H + W)
+    if kind == "blobs":
+        V = scene.blobs_volume(shape, seed=11)
+    elif kind == "noise":
+        V = rng.integers(0, 256, size=shape, dtype=np.uint8)
+    else:
+        V = (100 + rng.integers(-2, 3, size=shape)).astype(np.uint8)
+    vol = capi.Volume(ctx, W, H, D)
+    vol.upload(V)
+    vol.compute_gradient_map(capi.transfer_function_uniform(VolumeOptions(gradient_min=0.0, gradient_max=0.2)))
+    Gref = orc.gradient_map(V)
+    assert np.array_equal(vol.download_gradient(), Gref)
+    assert np.array_equal(vol.download_gradient_texture(), Gref)
     vol.close()
 
 

@@ -136,6 +136,7 @@ _SIGNATURES = {
     "vkv_volume_device_transfer_function": (_P, [_P]),
     "vkv_volume_download_voxels": (C.c_int, [_P, _P, C.c_size_t]),
     "vkv_volume_download_gradient": (C.c_int, [_P, _P, C.c_size_t]),
+    "vkv_volume_download_gradient_texture": (C.c_int, [_P, _P, C.c_size_t]),
     "vkv_volume_download_distance_map": (C.c_int, [_P, C.c_size_t, _P, C.c_size_t]),
     "vkv_volume_download_transfer_function": (C.c_int, [_P, _P, C.c_size_t]),
     "vkv_volume_upload_gradient": (C.c_int, [_P, _P, _P]),
@@ -329,6 +330,11 @@ class Volume:
     def download_gradient(self):
         out = np.empty(self.extent[::-1], dtype=np.uint8)
         check(lib().vkv_volume_download_gradient(self.handle, _host_ptr(out), out.nbytes))
+        return out
+
+    def download_gradient_texture(self):
+        out = np.empty(self.extent[::-1], dtype=np.uint8)
+        check(lib().vkv_volume_download_gradient_texture(self.handle, _host_ptr(out), out.nbytes))
         return out
 
     def download_distance_map(self, idx: int = 0):

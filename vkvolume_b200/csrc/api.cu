@@ -559,6 +559,21 @@ static int download(vkv_volume *vol, const uint8_t *src, size_t bytes, uint8_t *
 }
 int vkv_volume_download_voxels(vkv_volume *vol, uint8_t *out, size_t n) { return download(vol, vol ? vol->d_V : nullptr, vol ? vol->N : 0, out, n); }
 int vkv_volume_download_gradient(vkv_volume *vol, uint8_t *out, size_t n) { return download(vol, vol ? vol->d_G : nullptr, vol ? vol->N : 0, out, n); }
+int vkv_volume_download_gradient_texture(vkv_volume *vol, uint8_t *out, size_t n)
+{
+	VKV_REQUIRE(vol && out, VKV_ERR_ARGUMENT, "NULL argument");
+	VKV_REQUIRE(vol->a_G, VKV_ERR_STATE, "resource does not exist");
+	VKV_REQUIRE(n >= vol->N, VKV_ERR_ARGUMENT, "output buffer too small");
+	DeviceGuard guard(vol->ctx->device);
+	VKV_CUDA_CHECK(cudaDeviceSynchronize());
+	cudaMemcpy3DParms p{};
+	p.srcArray = vol->a_G;
+	p.dstPtr   = make_cudaPitchedPtr(out, vol->dim[0], vol->dim[0], vol->dim[1]);
+	p.extent   = make_cudaExtent(vol->dim[0], vol->dim[1], vol->dim[2]);
+	p.kind     = cudaMemcpyDeviceToHost;
+	VKV_CUDA_CHECK(cudaMemcpy3D(&p));
+	return VKV_OK;
+}
 int vkv_volume_download_distance_map(vkv_volume *vol, size_t idx, uint8_t *out, size_t n)
 {
 	return download(vol, vkv_volume_device_distance_map(vol, idx), vol ? vol->M : 0, out, n);

@@ -230,6 +230,184 @@ __global__ void __launch_bounds__(256) gradient_int_kernel(const uint8_t *__rest
 	}
 }
 
+// ---- flat persistent formulation of the integer kernel ---------------------------------------------------------
+// Same arithmetic as gradient_int_kernel, a third of the instructions per voxel:
+//   * work item = one 16-voxel chunk, numbered flat over the volume (no idle lanes for any W % 16 == 0); each thread keeps
+//     its (chunk, y, z) and advances it by the grid stride with carries instead of dividing;
+//   * the x +- 1 neighbours of a chunk are one extra byte load per row (an L1 hit on the neighbouring lane's line) instead
+//     of shuffles with edge cases;
+//   * S is built directly as a biased float (0x4b000000 folded into the multiply-add), one MUFU.SQRT, and ONE fused
+//     multiply-add 64 sqrt(S) + (2^23 + 128) whose mantissa holds the stored byte in bits 8..15 and, in bits 0..7, the
+//     distance from the rounding boundary in 1/256ths: byte 0 == 0 <=> within 1/512 of n + 1/2 (every exact tie
+//     S = (4n + 2)^2 and < 0.4 % false positives) <=> the voxel is decided by the shader's fp32 chain instead;
+//   * those voxels are queued per WORD (one shared-memory atomic per 4-voxel word with a tie, no per-voxel loop), the queue
+//     persists across the thread's chunks and is drained 32 entries at a time by the whole warp, which re-reads the four
+//     taps (L1/L2 hits), evaluates the fp32 chain and patches the byte in the linear map and in the texture array.
+constexpr int kFlatQueue = 96;        // <= 31 carried + 32 pushed per iteration + 32 re-queued per pass
+
+// One entry per 16-voxel chunk holding ties: bit 8 i + j of `tie` <=> voxel 4 j + i of the chunk needs the fp32 chain.
+struct GradQueue {
+	unsigned       tie[8][kFlatQueue];
+	unsigned       yz[8][kFlatQueue];         // y | z << 16
+	unsigned short cx[8][kFlatQueue];         // chunk index within the row
+};
+
+// Warp-converged push: the lanes with `push` set append their entry; n is the warp-uniform entry count (kept in a register,
+// no shared-memory atomics: slots come from a ballot).
+__device__ __forceinline__ void grad_push(GradQueue &q, unsigned &n, int warp, int lane, bool push, unsigned t, unsigned yz, unsigned cx)
+{
+	const unsigned m = __ballot_sync(0xffffffffu, push);
+	if (push) {
+		const unsigned slot = n + __popc(m & ((1u << lane) - 1u));
+		q.tie[warp][slot] = t, q.yz[warp][slot] = yz, q.cx[warp][slot] = (unsigned short) cx;
+	}
+	n += __popc(m);
+}
+
+template <bool SURF>
+__device__ __forceinline__ void grad_drain(GradQueue &q, unsigned &n, const float *s_lut, int warp, int lane, unsigned n_take, const uint8_t *__restrict__ V,
+                                           uint8_t *__restrict__ G, cudaSurfaceObject_t surf, uint32_t W, uint32_t H, uint32_t D)
+{
+	// pops the top n_take (<= 32) entries, one tie each; entries holding more ties push the rest back
+	__syncwarp();
+	const bool mine = (unsigned) lane < n_take;
+	unsigned   t = 0, yz = 0, cx = 0;
+	if (mine) {
+		const unsigned e = n - n_take + lane;
+		t = q.tie[warp][e], yz = q.yz[warp][e], cx = q.cx[warp][e];
+	}
+	n -= n_take;
+	__syncwarp();
+	const unsigned rest = t & (t - 1u);
+	grad_push(q, n, warp, lane, rest != 0u, rest, yz, cx);
+	if (mine) {
+		const unsigned pos = __ffs(t) - 1;
+		const uint32_t x = cx * 16 + 4 * (pos & 7u) + (pos >> 3), y = yz & 0xffffu, z = yz >> 16;
+		const uint32_t xm = x > 0 ? x - 1 : 0, xp = x + 1 < W ? x + 1 : W - 1;
+		const uint32_t ym = y > 0 ? y - 1 : 0, yp = y + 1 < H ? y + 1 : H - 1;
+		const uint32_t zmH = (z > 0 ? z - 1 : 0) * H, zpH = (z + 1 < D ? z + 1 : D - 1) * H;
+		const uint8_t *Vp = V + xp, *Vm = V + xm;
+		const float    a = s_lut[Vp[(size_t) (zmH + ym) * W]];
+		const float    b = s_lut[Vm[(size_t) (zpH + ym) * W]];
+		const float    c = s_lut[Vm[(size_t) (zmH + yp) * W]];
+		const float    d = s_lut[Vp[(size_t) (zpH + yp) * W]];
+		const unsigned char g = gradient_byte(a, b, c, d, 1.0f);
+		G[(size_t) (z * H + y) * W + x] = g;
+		if (SURF) surf3Dwrite(g, surf, (int) x, (int) y, (int) z);
+	}
+}
+
+// The four tap rows of one chunk (+ the neighbouring words of the warp's outer lanes), loaded one iteration ahead.
+struct GradRows {
+	uint4    qA, qB, qC, qE;
+	unsigned eA, eB, eC, eE;
+};
+
+__device__ __forceinline__ void grad_load_rows(GradRows &r, const uint8_t *__restrict__ V, uint32_t cx, uint32_t y, uint32_t z, uint32_t W, uint32_t H,
+                                               uint32_t D, uint32_t nchunks, int lane)
+{
+	const uint32_t ym = y > 0 ? y - 1 : 0, yp = y + 1 < H ? y + 1 : H - 1;
+	const uint32_t zmH = (z > 0 ? z - 1 : 0) * H, zpH = (z + 1 < D ? z + 1 : D - 1) * H;
+	const uint8_t *Vx = V + cx * 16;
+	// rows: A = (y-1, z-1) read at x+1 | B = (y-1, z+1) at x-1 | C = (y+1, z-1) at x-1 | E = (y+1, z+1) at x+1
+	const uint8_t *pA = Vx + (size_t) (zmH + ym) * W, *pB = Vx + (size_t) (zpH + ym) * W;
+	const uint8_t *pC = Vx + (size_t) (zmH + yp) * W, *pE = Vx + (size_t) (zpH + yp) * W;
+	r.qA = __ldg(reinterpret_cast<const uint4 *>(pA)), r.qB = __ldg(reinterpret_cast<const uint4 *>(pB));
+	r.qC = __ldg(reinterpret_cast<const uint4 *>(pC)), r.qE = __ldg(reinterpret_cast<const uint4 *>(pE));
+	r.eA = r.eB = r.eC = r.eE = 0;
+	// the words next to the warp's 512-voxel run come from memory unless they lie in another row (never dereferenced:
+	// the edge voxel is clamped to itself instead); all other lanes get them from the adjacent lane by shuffle
+	if (lane == 31 && cx != nchunks - 1) r.eA = __ldg(reinterpret_cast<const unsigned *>(pA + 16)), r.eE = __ldg(reinterpret_cast<const unsigned *>(pE + 16));
+	if (lane == 0 && cx != 0) r.eB = __ldg(reinterpret_cast<const unsigned *>(pB - 4)), r.eC = __ldg(reinterpret_cast<const unsigned *>(pC - 4));
+}
+
+template <bool SURF>
+__global__ void __launch_bounds__(256) gradient_flat_kernel(const uint8_t *__restrict__ V, uint8_t *__restrict__ G, cudaSurfaceObject_t surf,
+                                                           uint32_t W, uint32_t H, uint32_t D, uint32_t niter, uint32_t dcx, uint32_t dy, uint32_t dz)
+{
+	__shared__ float     s_lut[256];
+	__shared__ GradQueue q;
+	s_lut[threadIdx.x] = (float) threadIdx.x / 255.0f;        // UNORM decode, exactly as imageLoad
+	__syncthreads();
+	const uint32_t nchunks = W / 16;
+	const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	unsigned       qn = 0;        // entries in this warp's queue (warp-uniform)
+	// this thread's first chunk; later ones are (dcx, dy, dz) further on (the grid stride, decomposed by the launcher)
+	uint32_t cx, y, z;
+	{
+		const uint32_t gid = blockIdx.x * 256u + threadIdx.x;
+		const uint32_t r   = gid / nchunks;
+		cx = gid - r * nchunks, z = r / H, y = r - z * H;
+	}
+	// lanes past the end of the volume (last iteration only) mirror its last chunk and store nothing
+	GradRows cur;
+	grad_load_rows(cur, V, z < D ? cx : nchunks - 1, z < D ? y : H - 1, z < D ? z : D - 1, W, H, D, nchunks, lane);
+	for (uint32_t it = 0; it < niter; ++it) {
+		// this thread's next chunk, and its rows requested before the current ones are consumed
+		uint32_t ncx = cx + dcx;
+		const bool c1 = ncx >= nchunks;
+		ncx -= c1 ? nchunks : 0u;
+		uint32_t ny = y + dy + (c1 ? 1u : 0u);
+		const bool c2 = ny >= H;
+		ny -= c2 ? H : 0u;
+		const uint32_t nz = z + dz + (c2 ? 1u : 0u);
+		GradRows       nxt;
+		if (it + 1 < niter) grad_load_rows(nxt, V, nz < D ? ncx : nchunks - 1, nz < D ? ny : H - 1, nz < D ? nz : D - 1, W, H, D, nchunks, lane);
+		const bool active = z < D;
+		{
+			const uint32_t cxe   = active ? cx : nchunks - 1;
+			const bool     first = cxe == 0, last = cxe == nchunks - 1;
+			const uint4    qA = cur.qA, qB = cur.qB, qC = cur.qC, qE = cur.qE;
+			unsigned       eA = __shfl_down_sync(0xffffffffu, qA.x, 1), eE = __shfl_down_sync(0xffffffffu, qE.x, 1);
+			unsigned       eB = __shfl_up_sync(0xffffffffu, qB.w, 1), eC = __shfl_up_sync(0xffffffffu, qC.w, 1);
+			if (lane == 31) eA = cur.eA, eE = cur.eE;
+			if (lane == 0) eB = cur.eB, eC = cur.eC;
+			const unsigned sel_p = last ? 0x3321u : 0x4321u, sel_m = first ? 0x6544u : 0x6543u;
+			// the 16-byte window of each row, shifted by its x offset
+			const unsigned wA[4] = {__funnelshift_r(qA.x, qA.y, 8), __funnelshift_r(qA.y, qA.z, 8), __funnelshift_r(qA.z, qA.w, 8), prmt_(qA.w, eA, sel_p)};
+			const unsigned wE[4] = {__funnelshift_r(qE.x, qE.y, 8), __funnelshift_r(qE.y, qE.z, 8), __funnelshift_r(qE.z, qE.w, 8), prmt_(qE.w, eE, sel_p)};
+			const unsigned wB[4] = {prmt_(eB, qB.x, sel_m), __funnelshift_r(qB.x, qB.y, 24), __funnelshift_r(qB.y, qB.z, 24), __funnelshift_r(qB.z, qB.w, 24)};
+			const unsigned wC[4] = {prmt_(eC, qC.x, sel_m), __funnelshift_r(qC.x, qC.y, 24), __funnelshift_r(qC.y, qC.z, 24), __funnelshift_r(qC.z, qC.w, 24)};
+			unsigned out[4], tie[4];
+#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				// 4x4 byte transpose: taps of voxel i of this word -> one word (A, B, C, D)
+				const unsigned t0 = prmt_(wA[j], wB[j], 0x5140u), t1 = prmt_(wA[j], wB[j], 0x7362u);
+				const unsigned u0 = prmt_(wC[j], wE[j], 0x5140u), u1 = prmt_(wC[j], wE[j], 0x7362u);
+				const unsigned wv[4] = {prmt_(t0, u0, 0x5410u), prmt_(t0, u0, 0x7632u), prmt_(t1, u1, 0x5410u), prmt_(t1, u1, 0x7632u)};
+				unsigned yv[4];
+#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					const unsigned qq = __dp4a(wv[i], wv[i], 0u);                // A^2 + B^2 + C^2 + D^2
+					const unsigned sm = __dp4a(wv[i], 0x01010101u, 0u);          // A + B + C + D
+					unsigned       X, Sb;                                       // Sb = bits of the float 2^23 + S   (S = 4 qq - sm^2 < 2^18)
+					asm("mad.lo.u32 %0, %1, %1, 0xb5000000;" : "=r"(X) : "r"(sm));        // sm^2 - 0x4b000000
+					asm("{.reg .u32 t; shl.b32 t, %1, 2; sub.u32 %0, t, %2;}" : "=r"(Sb) : "r"(qq), "r"(X));
+					const float f = __uint_as_float(Sb) - 8388608.0f;           // S, exactly
+					float       rt;
+					asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rt) : "f"(f));
+					yv[i] = __float_as_uint(__fmaf_rn(rt, 64.0f, 8388736.0f));   // low 16 mantissa bits = rint(64 sqrt(S)) + 128
+				}
+				const unsigned p01 = prmt_(yv[0], yv[1], 0x5410u), p23 = prmt_(yv[2], yv[3], 0x5410u);
+				out[j]             = prmt_(p01, p23, 0x7531u);                  // rint(sqrt(S) / 4) where that is safe
+				const unsigned lo  = prmt_(p01, p23, 0x6420u);
+				tie[j]             = (lo - 0x01010101u) & ~lo & 0x80808080u;     // 0x80 in the bytes of lo that are zero
+			}
+			const uint4 o = make_uint4(out[0], out[1], out[2], out[3]);
+			if (active) {
+				*reinterpret_cast<uint4 *>(G + (size_t) (z * H + y) * W + cx * 16) = o;
+				if (SURF) surf3Dwrite(o, surf, (int) (cx * 16), (int) y, (int) z);        // x in bytes
+			}
+			const unsigned t = (tie[0] >> 7) | (tie[1] >> 6) | (tie[2] >> 5) | (tie[3] >> 4);
+			grad_push(q, qn, warp, lane, t != 0u && active, t, y | (z << 16), cx);
+		}
+		cx = ncx, y = ny, z = nz, cur = nxt;
+		// (the __syncwarp at the top of grad_drain orders this iteration's row stores before the byte patches)
+		while (qn >= 32u) grad_drain<SURF>(q, qn, s_lut, warp, lane, 32u, V, G, surf, W, H, D);
+	}
+	while (qn) grad_drain<SURF>(q, qn, s_lut, warp, lane, qn < 32u ? qn : 32u, V, G, surf, W, H, D);
+}
+
 // Any extents: one thread per voxel, clamped byte loads through L1.
 __global__ void __launch_bounds__(256) gradient_scalar_kernel(const uint8_t *__restrict__ V, uint8_t *__restrict__ G, uint32_t W,
                                                              uint32_t H, uint32_t D, float modifier)
@@ -266,7 +444,24 @@ int launch_gradient(vkv_volume *vol, bool use_gradient, float modifier, cudaStre
 	           (uint64_t) ((vol->dim[0] / 16 + 31) / 32) * vol->dim[1] * vol->dim[2] < (1ull << 31)) {
 		const unsigned ntasks = ((vol->dim[0] / 16 + 31) / 32) * vol->dim[1] * vol->dim[2];
 		const unsigned grid   = (ntasks + 7) / 8;
-		if (vol->s_G && !getenv("VKV_GRAD_NOSURF")) {
+		const uint64_t chunks = (uint64_t) (vol->dim[0] / 16) * vol->dim[1] * vol->dim[2];
+		if (!getenv("VKV_GRAD_V1") && vol->dim[0] <= 65536 && vol->dim[1] <= 65536 && vol->dim[2] < 65536 && chunks < (1ull << 32)) {
+			// persistent: every warp resident at once, each thread walks chunks gid, gid + stride, ...
+			const unsigned nchunks = vol->dim[0] / 16;
+			const char    *e_ctas      = getenv("VKV_GRAD_CTAS");
+			const int      ctas_per_sm = e_ctas ? atoi(e_ctas) : 2;        // measured best on B200 (scripts/grad_probe.py)
+			uint64_t g = (uint64_t) vol->ctx->sm_count * ctas_per_sm;
+			if (g * 256 > chunks) g = (chunks + 255) / 256;
+			const uint64_t stride = g * 256;
+			const uint32_t niter  = (uint32_t) ((chunks + stride - 1) / stride);
+			const uint32_t dcx = (uint32_t) (stride % nchunks), rr = (uint32_t) (stride / nchunks), dy = rr % vol->dim[1], dz = rr / vol->dim[1];
+			const bool     surf = vol->s_G && !getenv("VKV_GRAD_NOSURF");
+			if (surf)
+				gradient_flat_kernel<true><<<(unsigned) g, 256, 0, s>>>(vol->d_V, vol->d_G, vol->s_G, vol->dim[0], vol->dim[1], vol->dim[2], niter, dcx, dy, dz);
+			else
+				gradient_flat_kernel<false><<<(unsigned) g, 256, 0, s>>>(vol->d_V, vol->d_G, 0, vol->dim[0], vol->dim[1], vol->dim[2], niter, dcx, dy, dz);
+			vol->G_array_synced = surf;        // the kernel wrote the array itself
+		} else if (vol->s_G && !getenv("VKV_GRAD_NOSURF")) {
 			gradient_int_kernel<true><<<grid, 256, 0, s>>>(vol->d_V, vol->d_G, vol->s_G, vol->dim[0], vol->dim[1], vol->dim[2]);
 			vol->G_array_synced = true;        // the kernel wrote the array itself
 		} else {
