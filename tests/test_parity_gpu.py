@@ -335,6 +335,57 @@ def test_render_sampling_factor_and_alpha_factor(ctx):
     assert frac >= 0.999 and p >= 50.0, (frac, p)
 
 
+# ---- on-the-fly gradient variant (`--gradient_test`, PRECOMPUTED_GRADIENT undefined) ----------------
+@pytest.mark.parametrize("shape,bs", [((16, 16, 32), 4), ((9, 10, 13), 4), ((7, 9, 10), 3), ((33, 17, 300), 4), ((12, 12, 32), 2)])
+@pytest.mark.parametrize("o", TF_SETS)
+def test_on_the_fly_gradient_occupancy_and_count_bit_exact(ctx, shape, bs, o):
+    D, H, W = shape
+    V = scene.blobs_volume(shape, seed=sum(shape) + bs, n_blobs=5)
+    opt = VolumeOptions(use_precomputed_gradient=0, **o)
+    tfu = capi.transfer_function_uniform(opt)
+    vol = capi.Volume(ctx, W, H, D, block_size=bs, use_precomputed_gradient=False)        # no G, no gradient array: V only
+    vol.upload(V)
+    tf = orc.transfer_function_texture(opt)
+    want_O = orc.occupancy_map(V, None, tf, bs, bool(tfu.use_gradient), precomputed=False)
+    want_n = orc.occupied_voxel_count(V, None, tfu, precomputed=False)
+    n = vol.update_transfer_function(opt, SKIP_BLOCK, count=True)
+    assert np.array_equal(vol.download_distance_map(0), want_O)
+    assert n == want_n
+    assert vol.compute_occupied_voxel_count(tfu) == want_n
+    with pytest.raises(capi.VkvError):
+        vol.compute_gradient_map(tfu)        # there is no map to compute in this mode
+    vol.close()
+
+
+@pytest.mark.parametrize("skip", [SKIP_NONE, SKIP_DISTANCE])
+@pytest.mark.parametrize("filt", [FILTER_EXACT, FILTER_HARDWARE])
+def test_on_the_fly_gradient_render_matches_oracle(ctx, skip, filt):
+    shape, width, height = (48, 64, 80), 160, 128
+    D, H, W = shape
+    V = scene.blobs_volume(shape, seed=1)
+    opt = VolumeOptions(use_precomputed_gradient=0, **TF_SETS[0])
+    tfu = capi.transfer_function_uniform(opt)
+    tf = orc.transfer_function_texture(opt)
+    O = orc.occupancy_map(V, None, tf, 4, True, precomputed=False)
+    maps = orc.distance_map(O) if skip == SKIP_DISTANCE else None
+    vol = capi.Volume(ctx, W, H, D, block_size=4, use_precomputed_gradient=False)
+    vol.upload(V)
+    vol.update_transfer_function(opt, skip)
+    if skip == SKIP_DISTANCE:
+        assert np.array_equal(vol.download_distance_map(0), maps)
+    it = scene.image_transform((0.004,) * 3, (W, H, D))
+    cu, ru = vol.make_uniforms(scene.look_at_camera((34, 22, 50), aspect=width / height), it, 5.0)
+    ropt = RenderOptions(skipping_type=skip, clip_distance=5.0, filter=filt)
+    img, counts = vol.render_to_host(cu, ru, tfu, ropt, width, height)
+    ref, rcounts, _, _ = orc.render(V, None, tf, maps, vol.map_extent, cu, ru, tfu, ropt, width, height, precomputed=False)
+    vol.close()
+    frac, p = frame_bar(img, ref)
+    assert frac >= 0.999 and p >= 50.0, (frac, p)
+    assert counts.covered_pixels == rcounts.covered_pixels
+    tot, rtot = counts.volume_samples + counts.distance_samples, rcounts.volume_samples + rcounts.distance_samples
+    assert abs(tot - rtot) <= (1e-3 if filt == FILTER_EXACT else 2e-2) * rtot + 8
+
+
 def test_render_tiles_equal_full_frame(ctx):
     """Image-tile sharding: rendering tile subsets (as ranks would) reassembles the full frame byte for byte."""
     import torch

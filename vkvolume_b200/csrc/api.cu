@@ -320,11 +320,9 @@ static int ensure_analytic_mask(vkv_volume *vol, const vkv_transfer_function_uni
 
 static int check_gradient_inputs(vkv_volume *vol, const vkv_transfer_function_uniform *tfu)
 {
-	if (tfu->use_gradient) {
-		VKV_REQUIRE(vol->precomputed_gradient, VKV_ERR_STATE,
-		            "on-the-fly gradient variant (--gradient_test) is not implemented; create the volume with use_precomputed_gradient");
+	// volumes created with use_precomputed_gradient = 0 evaluate gradients on the fly (`--gradient_test`) and have no map
+	if (tfu->use_gradient && vol->precomputed_gradient)
 		VKV_REQUIRE(vol->has_G, VKV_ERR_STATE, "gradient map not computed yet (vkv_compute_gradient_map)");
-	}
 	return VKV_OK;
 }
 
@@ -338,7 +336,7 @@ int vkv_compute_occupied_voxel_count(vkv_volume *vol, const vkv_transfer_functio
 	cudaStream_t s = (cudaStream_t) stream;
 	if ((rc = ensure_analytic_mask(vol, tfu, s))) return rc;
 	VKV_CUDA_CHECK(cudaMemsetAsync(vol->d_count, 0, sizeof(unsigned long long), s));
-	if ((rc = launch_occupancy(vol, tfu->use_gradient != 0, true, nullptr, 0, vol->dim_b[2], vol->d_count, s))) return rc;
+	if ((rc = launch_occupancy(vol, tfu, true, nullptr, 0, vol->dim_b[2], vol->d_count, s))) return rc;
 	if (count_out) {
 		VKV_CUDA_CHECK(cudaMemcpyAsync(vol->h_count, vol->d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
 		VKV_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -364,7 +362,7 @@ int vkv_compute_occupancy_slab(vkv_volume *vol, const vkv_transfer_function_unif
 	if ((rc = vkv_volume_set_number_of_distance_maps(vol, n))) return rc;
 	if (count_dev && (rc = ensure_analytic_mask(vol, tfu, s))) return rc;
 	vol->maps_valid_for = -1;
-	return launch_occupancy(vol, tfu->use_gradient != 0, count_dev != nullptr, vol->d_maps[n - 1], zb_first, zb_count,
+	return launch_occupancy(vol, tfu, count_dev != nullptr, vol->d_maps[n - 1], zb_first, zb_count,
 	                        reinterpret_cast<unsigned long long *>(count_dev), s);
 }
 

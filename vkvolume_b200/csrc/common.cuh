@@ -124,7 +124,7 @@ namespace vkv {
 int launch_tf_texture(vkv_volume *vol, const vkv_volume_options *opt, cudaStream_t s);
 int launch_tf_masks(vkv_volume *vol, const vkv_transfer_function_uniform *tfu_or_null, cudaStream_t s);
 int launch_gradient(vkv_volume *vol, bool use_gradient, float modifier, cudaStream_t s);
-int launch_occupancy(vkv_volume *vol, bool use_gradient, bool count, uint8_t *O, uint32_t zb_first, uint32_t zb_count,
+int launch_occupancy(vkv_volume *vol, const vkv_transfer_function_uniform *tfu, bool count, uint8_t *O, uint32_t zb_first, uint32_t zb_count,
                      unsigned long long *count_dev, cudaStream_t s);
 int launch_distance(vkv_volume *vol, int skipping_type, cudaStream_t s);
 int launch_normalise(const void *raw_dev, size_t n, int kind, bool big_endian, float lo, float hi, uint8_t *out,

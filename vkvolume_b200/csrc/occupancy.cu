@@ -16,6 +16,7 @@
 // is unused).
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <type_traits>
 
@@ -581,6 +582,93 @@ __global__ void __launch_bounds__(256) occupancy_generic_kernel(const uint8_t *_
 	}
 }
 
+
+// ---- on-the-fly gradient variant (PRECOMPUTED_GRADIENT undefined: `--gradient_test`, volumes created with
+// use_precomputed_gradient = 0) -------------------------------------------------------------------------------
+// shaders/get_gradient_compute.glsl:12-20 evaluated per voxel in the shader's fp32 operation order (the library is
+// compiled without contraction), then the texture lookup of occupancy_map.comp (row = nearest texel of the FLOAT
+// gradient, not of a stored byte) and the analytic TF of occupied_voxel_count.comp.  No gradient map exists in this
+// mode, so the pass reads V only: 4 clamped taps per voxel, served by L1/L2 (each byte of V is touched by 4 voxels
+// of 4 neighbouring rows).  One thread per voxel; the map slab is pre-set to EMPTY (255) and hits store OCCUPIED (0),
+// one store per run of hit lanes that share a block.
+template <bool COUNT>
+__global__ void __launch_bounds__(256) occupancy_otf_kernel(const uint8_t *__restrict__ V, const uint2 *__restrict__ mask2, uint32_t W, uint32_t H,
+                                                           uint32_t D, uint32_t Wb, uint32_t Hb, uint32_t bsx, uint32_t bsy, uint32_t bsz,
+                                                           uint32_t z_first, uint32_t z_end, vkv_transfer_function_uniform tfu,
+                                                           uint8_t *__restrict__ O, unsigned long long *__restrict__ count)
+{
+	__shared__ uint2              s_mask[kMaskWords];
+	__shared__ unsigned long long s_c[8];
+	for (int i = threadIdx.x; i < kMaskWords; i += blockDim.x) s_mask[i] = mask2[i];
+	__syncthreads();
+	const uint32_t     xchunks = (W + 255u) / 256u;
+	const uint64_t     ntasks  = (uint64_t) xchunks * H * (z_end - z_first);
+	const int          lane    = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int          mx = (int) W - 1, my = (int) H - 1, mz = (int) D - 1;
+	const size_t       WH = (size_t) W * H;
+	unsigned long long local = 0;
+	for (uint64_t task = blockIdx.x; task < ntasks; task += gridDim.x) {
+		const uint32_t xc = (uint32_t) (task % xchunks);
+		const uint64_t r  = task / xchunks;
+		const int      y = (int) (r % H), z = (int) z_first + (int) (r / H);
+		const int      x = (int) (xc * 256u + threadIdx.x);
+		bool           hit = false;
+		if (x <= mx) {
+			const int    xm = max(x - 1, 0), xp = min(x + 1, mx), ym = max(y - 1, 0), yp = min(y + 1, my), zm = max(z - 1, 0), zp = min(z + 1, mz);
+			const float  intensity = (float) __ldg(V + (size_t) z * WH + (size_t) y * W + x) / 255.0f;
+			// k = (1,-1): taps (+,-,-), (-,-,+), (-,+,-), (+,+,+)
+			const float a = (float) __ldg(V + (size_t) zm * WH + (size_t) ym * W + xp) / 255.0f;
+			const float b = (float) __ldg(V + (size_t) zp * WH + (size_t) ym * W + xm) / 255.0f;
+			const float c = (float) __ldg(V + (size_t) zm * WH + (size_t) yp * W + xm) / 255.0f;
+			const float d = (float) __ldg(V + (size_t) zp * WH + (size_t) yp * W + xp) / 255.0f;
+			const float gx  = 0.25f * (((1.0f * a + -1.0f * b) + -1.0f * c) + 1.0f * d);
+			const float gy  = 0.25f * (((-1.0f * a + -1.0f * b) + 1.0f * c) + 1.0f * d);
+			const float gz  = 0.25f * (((-1.0f * a + 1.0f * b) + -1.0f * c) + 1.0f * d);
+			const float len = sqrtf((gx * gx + gy * gy) + gz * gz);
+			const float gradient = fminf(fmaxf(len * tfu.grad_magnitude_modifier, 0.0f), 1.0f);
+			// texture(transfer_function, vec2(intensity, gradient)).a > 0: nearest texel, clamp to edge
+			const int      ti = min(max((int) floorf(intensity * 256.0f), 0), 255), tg = min(max((int) floorf(gradient * 256.0f), 0), 255);
+			hit               = (s_mask[tg * 8 + (ti >> 5)].x >> (ti & 31)) & 1u;
+			if (COUNT) {
+				const float aI = fminf(fmaxf((intensity - tfu.intensity_min) * tfu.intensity_range_inv, 0.0f), 1.0f);
+				const float aG = fminf(fmaxf((gradient - tfu.gradient_min) * tfu.gradient_range_inv, 0.0f), 1.0f);
+				local += (aI * aG > 0.0f) ? 1u : 0u;
+			}
+		}
+		if (O) {
+			const unsigned hits  = __ballot_sync(0xffffffffu, hit);
+			const bool     first = lane == 0 || !((hits >> (lane - 1)) & 1u) || (uint32_t) (x - 1) / bsx != (uint32_t) x / bsx;
+			if (hit && first) O[((size_t) ((uint32_t) z / bsz) * Hb + (uint32_t) y / bsy) * Wb + (uint32_t) x / bsx] = 0;
+		}
+	}
+	if (COUNT) {
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+		if (lane == 0) s_c[warp] = local;
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			unsigned long long t = 0;
+			for (int i = 0; i < 8; ++i) t += s_c[i];
+			if (t) atomicAdd(count, t);
+		}
+	}
+}
+
+static int launch_occupancy_otf(vkv_volume *vol, const vkv_transfer_function_uniform *tfu, bool count, uint8_t *O, uint32_t zb_first,
+                                uint32_t zb_count, unsigned long long *count_dev, cudaStream_t s)
+{
+	const uint32_t z0 = zb_first * vol->bs[2], z1 = std::min<uint32_t>(vol->dim[2], (zb_first + zb_count) * vol->bs[2]);
+	if (O) VKV_CUDA_CHECK(cudaMemsetAsync(O + (size_t) zb_first * vol->dim_b[0] * vol->dim_b[1], 255, (size_t) zb_count * vol->dim_b[0] * vol->dim_b[1], s));
+	if (z1 <= z0) return VKV_OK;
+	const int grid = vol->ctx->sm_count * 8;
+#define VKV_OTF_ARGS vol->d_V, vol->d_mask2, vol->dim[0], vol->dim[1], vol->dim[2], vol->dim_b[0], vol->dim_b[1], vol->bs[0], vol->bs[1], vol->bs[2], z0, z1, *tfu, O, count_dev
+	if (count) occupancy_otf_kernel<true><<<grid, 256, 0, s>>>(VKV_OTF_ARGS);
+	else occupancy_otf_kernel<false><<<grid, 256, 0, s>>>(VKV_OTF_ARGS);
+#undef VKV_OTF_ARGS
+	VKV_LAUNCHED();
+	return VKV_OK;
+}
+
 template <int BS, bool USE_G, bool COUNT>
 static int launch_fast_inst(vkv_volume *vol, uint8_t *O, uint32_t zb_first, uint32_t zb_count, unsigned long long *count_dev, cudaStream_t s)
 {
@@ -642,10 +730,13 @@ int make_volume_tensor_maps(vkv_volume *vol)
 	return VKV_OK;
 }
 
-int launch_occupancy(vkv_volume *vol, bool use_gradient, bool count, uint8_t *O, uint32_t zb_first, uint32_t zb_count,
+int launch_occupancy(vkv_volume *vol, const vkv_transfer_function_uniform *tfu, bool count, uint8_t *O, uint32_t zb_first, uint32_t zb_count,
                      unsigned long long *count_dev, cudaStream_t s)
 {
 	if (zb_count == 0) return VKV_OK;
+	const bool use_gradient = tfu->use_gradient != 0;
+	// no gradient map in this volume: gradients are evaluated per voxel (get_gradient_compute.glsl:12-20)
+	if (use_gradient && !vol->precomputed_gradient) return launch_occupancy_otf(vol, tfu, count, O, zb_first, zb_count, count_dev, s);
 	// gradient bytes are only read when the TF uses them AND a precomputed map exists
 	const bool use_g = use_gradient;
 	const int  grid  = vol->ctx->sm_count * 8;        // persistent: 8 CTAs/SM x 256 threads = full occupancy

@@ -21,6 +21,9 @@
 //     target may be a peer-mapped framebuffer (multi-GPU tile gather fused into the kernel).
 // The march loop is the fragment shader's, statement for statement, in fp32 without contraction.
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 
@@ -55,6 +58,7 @@ struct RayParams {
 	uint8_t       *rgba8;
 	float         *depth;
 	unsigned long long *counts;     // vkv_sample_counts or null
+	unsigned long long *trace;      // debug (VKV_RC_TRACE): per warp {start ns, end ns, loop iterations} or null
 };
 
 __device__ __forceinline__ float clampf_(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
@@ -79,6 +83,28 @@ __device__ __forceinline__ float sample_exact(const uint8_t *__restrict__ T, con
 	const float c01 = t001 * (1.0f - a) + t101 * a, c11 = t011 * (1.0f - a) + t111 * a;
 	const float c0 = c00 * (1.0f - b) + c10 * b, c1 = c01 * (1.0f - b) + c11 * b;
 	return c0 * (1.0f - c) + c1 * c;
+}
+
+// get_gradient of the fragment shader without PRECOMPUTED_GRADIENT (volume_render.frag:91-97): four filtered taps of the
+// VOLUME at pos +- 1/dim on a tetrahedron, combined in the shader's order (no contraction)
+template <bool EXACT>
+__device__ __forceinline__ float gradient_otf(cudaTextureObject_t tex, const uint8_t *__restrict__ V, const int dim[3], const float di[3],
+                                              float modifier, float px, float py, float pz)
+{
+	const float xp = px + di[0] * 1.0f, xm = px + di[0] * -1.0f, yp = py + di[1] * 1.0f, ym = py + di[1] * -1.0f;
+	const float zp = pz + di[2] * 1.0f, zm = pz + di[2] * -1.0f;
+	float a, b, d, e;
+	if (EXACT) {
+		a = sample_exact(V, dim, xp, ym, zm); b = sample_exact(V, dim, xm, ym, zp);
+		d = sample_exact(V, dim, xm, yp, zm); e = sample_exact(V, dim, xp, yp, zp);
+	} else {
+		a = tex3D<float>(tex, xp, ym, zm); b = tex3D<float>(tex, xm, ym, zp);
+		d = tex3D<float>(tex, xm, yp, zm); e = tex3D<float>(tex, xp, yp, zp);
+	}
+	const float gx = (((1.0f * a + -1.0f * b) + -1.0f * d) + 1.0f * e) * 0.25f;
+	const float gy = (((-1.0f * a + -1.0f * b) + 1.0f * d) + 1.0f * e) * 0.25f;
+	const float gz = (((-1.0f * a + 1.0f * b) + -1.0f * d) + 1.0f * e) * 0.25f;
+	return clampf_(sqrtf((gx * gx + gy * gy) + gz * gz) * modifier, 0.0f, 1.0f);
 }
 
 __device__ __forceinline__ float srgb_encode(float c) { return c <= 0.0031308f ? 12.92f * c : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f; }
@@ -109,13 +135,17 @@ __global__ void __launch_bounds__(256) ctab_kernel(const uchar4 *__restrict__ tf
 #endif
 // A CTA is two warps = a 16x4 pixel tile; small CTAs keep the register file busy while long rays finish.
 // grid = (CTAs per tile in x, CTAs per tile in y, tiles of this launch).
-template <int SKIP, bool EXACT, bool COUNT>
-__global__ void __launch_bounds__(64, VKV_RC_MIN_CTAS) raycast_kernel(const __grid_constant__ RayParams P)
+// OTF: the volume has no gradient map; gradients come from gradient_otf (always instantiated with COUNT).
+template <int SKIP, bool EXACT, bool COUNT, bool OTF = false>
+__global__ void __launch_bounds__(64, OTF ? 8 : VKV_RC_MIN_CTAS) raycast_kernel(const __grid_constant__ RayParams P)
 {
 	__shared__ unsigned long long s_cnt[2][4];
 
 	// CTA -> tile -> pixel
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	unsigned long long t_start = 0;
+	unsigned           n_iter  = 0;
+	if (P.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
 	// Tiles are issued from the middle of this launch's tile list outwards (m, m-1, m+1, m-2, ...): the long rays sit
 	// near the image centre, so their latency chains start at t = 0 and the cheap border tiles fill the tail.
 	const int seq        = P.seq_base + (int) blockIdx.z;
@@ -241,11 +271,13 @@ __global__ void __launch_bounds__(64, VKV_RC_MIN_CTAS) raycast_kernel(const __gr
 					bool     voxel_occupied = true;
 					int      i_first_hit    = n_steps;
 					const int back = (int) ceilf(P.sampling_factor);
+					const float dim_inv[3] = {1.0f / P.dimf[0], 1.0f / P.dimf[1], 1.0f / P.dimf[2]};
 					// look-ahead cache of hardware-filtered samples i .. i+3: consecutive volume samples are the common case
 					// inside occupied regions, and one batch of independent fetches replaces four dependent round trips
 					int   pre_base = -0x40000000;
 					float pre_v0 = 0.0f, pre_v1 = 0.0f, pre_v2 = 0.0f, pre_v3 = 0.0f, pre_g0 = 1.0f, pre_g1 = 1.0f, pre_g2 = 1.0f, pre_g3 = 1.0f;
 					for (int i = 0; i < n_steps;) {
+						++n_iter;
 						const float fi     = (float) i;
 						const float pos[3] = {entry[0] + fi * step[0], entry[1] + fi * step[1], entry[2] + fi * step[2]};
 						float    u[3];
@@ -289,7 +321,11 @@ __global__ void __launch_bounds__(64, VKV_RC_MIN_CTAS) raycast_kernel(const __gr
 						} else {
 							++n_vol;
 							float intensity, gradient = 1.0f;
-							if (EXACT) {
+							if (OTF) {
+								intensity = EXACT ? sample_exact(P.V, P.dim, pos[0], pos[1], pos[2]) : tex3D<float>(P.tex_v, pos[0], pos[1], pos[2]);
+								if (P.use_gradient)
+									gradient = gradient_otf<EXACT>(P.tex_v, P.V, P.dim, dim_inv, P.grad_modifier, pos[0], pos[1], pos[2]);
+							} else if (EXACT) {
 								intensity = sample_exact(P.V, P.dim, pos[0], pos[1], pos[2]);
 								if (P.use_gradient) gradient = sample_exact(P.G, P.dim, pos[0], pos[1], pos[2]);
 							} else {
@@ -360,6 +396,15 @@ __global__ void __launch_bounds__(64, VKV_RC_MIN_CTAS) raycast_kernel(const __gr
 		if (P.depth) P.depth[p] = frag_depth;
 	}
 
+	if (P.trace) {
+		unsigned long long t_end;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+		const unsigned it_max = __reduce_max_sync(0xffffffffu, n_iter);
+		if (lane == 0) {
+			const size_t w = (((size_t) blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 2 + warp;
+			P.trace[w * 3 + 0] = t_start; P.trace[w * 3 + 1] = t_end; P.trace[w * 3 + 2] = it_max;
+		}
+	}
 	if (COUNT) {
 		unsigned long long c[4] = {n_vol, n_dist, n_empty, covered};
 #pragma unroll
@@ -523,13 +568,28 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 	P.counts = reinterpret_cast<unsigned long long *>(counts);
 
 	const bool exact = opt->filter == VKV_FILTER_EXACT;
+	// on-the-fly gradients (volume created without a gradient map); the variant always counts, into scratch if need be
+	const bool otf = P.use_gradient && !vol->precomputed_gradient;
+	if (otf && !P.counts) P.counts = reinterpret_cast<unsigned long long *>(vol->d_counts_scratch);
 	// gridDim.z is limited to 65535: launch the tile list in chunks (one chunk up to 134 Mpixel with 64x32 tiles)
+	// debug: VKV_RC_TRACE=<file> dumps per-warp {start ns, end ns, loop iterations} of this launch (synchronous; never set in production)
+	const char         *trace_path = getenv("VKV_RC_TRACE");
+	unsigned long long *d_trace    = nullptr;
+	size_t              trace_n    = 0;
+	if (trace_path && my_tiles <= 65535) {
+		trace_n = (size_t) my_tiles * (tile_w / 16) * (tile_h / 4) * 2 * 3;
+		VKV_CUDA_CHECK(cudaMalloc(&d_trace, trace_n * sizeof(unsigned long long)));
+		VKV_CUDA_CHECK(cudaMemsetAsync(d_trace, 0, trace_n * sizeof(unsigned long long), s));
+		P.trace = d_trace;
+	}
 	for (int base = 0; base < my_tiles; base += 65535) {
 		P.seq_base = base;
 		const dim3 grid((unsigned) (tile_w / 16), (unsigned) (tile_h / 4), (unsigned) std::min(65535, my_tiles - base));
 #define VKV_RC(SK)                                                                      \
 	do {                                                                                \
-		if (exact && counts) raycast_kernel<SK, true, true><<<grid, 64, 0, s>>>(P);      \
+		if (otf && exact) raycast_kernel<SK, true, true, true><<<grid, 64, 0, s>>>(P);   \
+		else if (otf) raycast_kernel<SK, false, true, true><<<grid, 64, 0, s>>>(P);      \
+		else if (exact && counts) raycast_kernel<SK, true, true><<<grid, 64, 0, s>>>(P);      \
 		else if (exact) raycast_kernel<SK, true, false><<<grid, 64, 0, s>>>(P);          \
 		else if (counts) raycast_kernel<SK, false, true><<<grid, 64, 0, s>>>(P);         \
 		else raycast_kernel<SK, false, false><<<grid, 64, 0, s>>>(P);                    \
@@ -542,6 +602,16 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 		}
 #undef VKV_RC
 		VKV_LAUNCHED();
+	}
+	if (d_trace) {
+		std::vector<unsigned long long> h(trace_n);
+		VKV_CUDA_CHECK(cudaStreamSynchronize(s));
+		VKV_CUDA_CHECK(cudaMemcpy(h.data(), d_trace, trace_n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+		cudaFree(d_trace);
+		if (FILE *f = fopen(trace_path, "wb")) {
+			fwrite(h.data(), sizeof(unsigned long long), trace_n, f);
+			fclose(f);
+		}
 	}
 	return VKV_OK;
 }
