@@ -64,6 +64,19 @@ struct RayParams {
 __device__ __forceinline__ float clampf_(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 __device__ __forceinline__ int   clampi_(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
 __device__ __forceinline__ int   tf_texel(float c) { return clampi_((int) floorf(c * 256.0f), 0, 255); }
+// clamp(x, 0, hi) for hi >= 0 in one VIMNMX.RELU
+__device__ __forceinline__ int   clamp0_(int x, int hi) { return __vimin_s32_relu(x, hi); }
+// k in [0,4) -> one of four registers without branches (the compiler otherwise builds a branch tree around the texture scoreboard)
+__device__ __forceinline__ float pick4_(int k, float a, float b, float c, float d)
+{
+	float r;
+	asm("{\n\t.reg .pred p0, p1, p2;\n\t.reg .f32 lo, hi;\n\t"
+	    "setp.eq.s32 p0, %1, 0;\n\tsetp.eq.s32 p1, %1, 2;\n\tsetp.lt.s32 p2, %1, 2;\n\t"
+	    "selp.f32 lo, %2, %3, p0;\n\tselp.f32 hi, %4, %5, p1;\n\tselp.f32 %0, lo, hi, p2;\n\t}"
+	    : "=f"(r)
+	    : "r"(k), "f"(a), "f"(b), "f"(c), "f"(d));
+	return r;
+}
 
 // texture(sampler3D, pos), LINEAR / CLAMP_TO_EDGE / UNORM — fp32 restatement on the linear copy
 __device__ __forceinline__ float sample_exact(const uint8_t *__restrict__ T, const int dim[3], float px, float py, float pz)
@@ -261,6 +274,9 @@ __global__ void __launch_bounds__(64, OTF ? 8 : VKV_RC_MIN_CTAS) raycast_kernel(
 						const float sdt = step[k] * P.dimf[k] / P.block_size[k];
 						sdt_inv[k]      = 1.0f / sdt;
 					}
+					// (st + sg * dist) of the shader is an exact small integer: dist when the ray advances along +k, 1 - dist along -k
+					// (BLOCK_SKIP: 1 or 0).  sdt_inv is finite, non-zero and not NaN here (the `inside` test above saw to that).
+					const bool neg[3] = {sdt_inv[0] < 0.0f, sdt_inv[1] < 0.0f, sdt_inv[2] < 0.0f};
 					const uint8_t *__restrict__ Dm = P.map_ptrs[0];
 					if (SKIP == VKV_SKIP_ANISOTROPIC_DISTANCE)
 						Dm = P.map_ptrs[(dir[2] < 0 ? 1 : 0) + (dir[1] < 0 ? 2 : 0) + (dir[0] < 0 ? 4 : 0)];
@@ -271,6 +287,7 @@ __global__ void __launch_bounds__(64, OTF ? 8 : VKV_RC_MIN_CTAS) raycast_kernel(
 					bool     voxel_occupied = true;
 					int      i_first_hit    = n_steps;
 					const int back = (int) ceilf(P.sampling_factor);
+					const int dim_b1[3] = {P.dim_b[0] - 1, P.dim_b[1] - 1, P.dim_b[2] - 1};
 					const float dim_inv[3] = {1.0f / P.dimf[0], 1.0f / P.dimf[1], 1.0f / P.dimf[2]};
 					// look-ahead cache of hardware-filtered samples i .. i+3: consecutive volume samples are the common case
 					// inside occupied regions, and one batch of independent fetches replaces four dependent round trips
@@ -288,7 +305,7 @@ __global__ void __launch_bounds__(64, OTF ? 8 : VKV_RC_MIN_CTAS) raycast_kernel(
 #pragma unroll
 							for (int k = 0; k < 3; ++k) {
 								u[k]   = P.vol_to_map[k] * pos[k];
-								u_i[k] = clampi_((int) u[k], 0, P.dim_b[k] - 1);
+								u_i[k] = clamp0_((int) u[k], dim_b1[k]);
 							}
 							idx     = ((unsigned) u_i[2] * (unsigned) P.dim_b[1] + (unsigned) u_i[1]) * (unsigned) P.dim_b[0] + (unsigned) u_i[0];
 							do_skip = !voxel_occupied && idx != idx_last;
@@ -297,17 +314,13 @@ __global__ void __launch_bounds__(64, OTF ? 8 : VKV_RC_MIN_CTAS) raycast_kernel(
 							++n_dist;
 							const unsigned dist = __ldg(Dm + idx);
 							if (dist > 0u) {
-								float dxyz[3];
+								float       dxyz[3];
+								const float fd = (float) dist, omfd = 1.0f - fd;        // exact (dist <= 255)
 #pragma unroll
 								for (int k = 0; k < 3; ++k) {
-									const float rr = clampf_((float) u_i[k] - u[k], -1.0f, 0.0f);
-									if (SKIP == VKV_SKIP_BLOCK) {
-										dxyz[k] = ((sdt_inv[k] < 0.0f ? 0.0f : 1.0f) + rr) * sdt_inv[k];
-									} else {
-										const float st = (-sdt_inv[k] < 0.0f) ? 0.0f : 1.0f;
-										const float sg = sdt_inv[k] > 0.0f ? 1.0f : (sdt_inv[k] < 0.0f ? -1.0f : 0.0f);
-										dxyz[k]        = (st + sg * (float) dist + rr) * sdt_inv[k];
-									}
+									const float rr   = clampf_((float) u_i[k] - u[k], -1.0f, 0.0f);
+									const float base = SKIP == VKV_SKIP_BLOCK ? (neg[k] ? 0.0f : 1.0f) : (neg[k] ? omfd : fd);
+									dxyz[k]          = (base + rr) * sdt_inv[k];
 								}
 								const float m       = fminf(fminf(dxyz[0], dxyz[1]), dxyz[2]);
 								int         i_delta = (int) ceilf(m);
@@ -348,8 +361,8 @@ __global__ void __launch_bounds__(64, OTF ? 8 : VKV_RC_MIN_CTAS) raycast_kernel(
 										pre_g3 = tex3D<float>(P.tex_g, q3[0], q3[1], q3[2]);
 									}
 								}
-								intensity = k == 0 ? pre_v0 : (k == 1 ? pre_v1 : (k == 2 ? pre_v2 : pre_v3));
-								if (P.use_gradient) gradient = k == 0 ? pre_g0 : (k == 1 ? pre_g1 : (k == 2 ? pre_g2 : pre_g3));
+								intensity = pick4_(k, pre_v0, pre_v1, pre_v2, pre_v3);
+								if (P.use_gradient) gradient = pick4_(k, pre_g0, pre_g1, pre_g2, pre_g3);
 							}
 							const float4 c = __ldg(P.ctab + tf_texel(gradient) * 256 + tf_texel(intensity));
 							voxel_occupied = c.w >= 0.0f;
