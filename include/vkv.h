@@ -115,9 +115,17 @@ typedef struct vkv_render_options {
 	int32_t skipping_type;         /* VKV_SKIP_*, default DISTANCE */
 	float   clip_distance;         /* default 50                   */
 	int32_t early_ray_termination; /* default 1                    */
-	int32_t depth_attachment;      /* must be 0   */
+	int32_t depth_attachment;      /* DEPTH_ATTACHMENT variant (volume_render.frag:122-136,151-165): the ray is
+	                                * discarded behind / shortened at the depth already in `depth_dev`.
+	                                * Needs load_framebuffer = 1 and a depth buffer.  default 0 */
 	int32_t test;                  /* VKV_TEST_*                   */
 	int32_t filter;                /* VKV_FILTER_* (extension; 0 = hardware) */
+	int32_t load_framebuffer;      /* extension.  0: the target starts from the render pass clear — colour (0,0,0,1),
+	                                * depth 0 (render_pipeline.cpp:38-39) — which is what a single volume over an empty
+	                                * scene sees.  1: blend and depth-test (GREATER_OR_EQUAL, depth write on,
+	                                * volume_render_subpass.cpp:176-190) over what `rgba8_dev` / `depth_dev` already
+	                                * hold: the second and later volumes of VolumeRenderSubpass::draw's loop
+	                                * (:219-293), or a volume drawn over rasterised geometry. */
 } vkv_render_options;
 
 /* Camera + scene-node description from which the host maths of
@@ -249,7 +257,10 @@ VKV_API int vkv_make_uniforms(const vkv_volume *vol, const vkv_camera_desc *cam,
  * (SURVEY A.6): writes a width*height RGBA8 (sRGB-encoded RGB) framebuffer, row 0
  * at the top.  `rgba8_dev` is a DEVICE pointer; `depth_dev` (float per pixel,
  * reverse-Z gl_FragDepth) and `counts_dev` (vkv_sample_counts, accumulated into —
- * zero it first) may be NULL. */
+ * zero it first) may be NULL.  With opt->load_framebuffer both buffers are read
+ * first and the volume is composited over them (see vkv_render_options); a scene
+ * with several volumes is one call per volume in scene order, the first with
+ * load_framebuffer = 0 (or 1 over a rasterised background), the rest with 1. */
 VKV_API int vkv_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_cast_uniform *ray,
                        const vkv_transfer_function_uniform *tfu, const vkv_render_options *opt, int width,
                        int height, uint8_t *rgba8_dev, float *depth_dev, vkv_sample_counts *counts_dev,
@@ -270,6 +281,20 @@ VKV_API int vkv_render_tiles(vkv_volume *vol, const vkv_camera_uniform *cam, con
 VKV_API int vkv_render_to_host(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_cast_uniform *ray,
                                const vkv_transfer_function_uniform *tfu, const vkv_render_options *opt, int width,
                                int height, uint8_t *rgba8_host, vkv_sample_counts *counts_host, void *stream);
+
+/* Host-buffer call that also carries the depth attachment and composites: with
+ * opt->load_framebuffer the contents of `rgba8_host` (and `depth_host`, float per
+ * pixel, reverse-Z, may be NULL unless opt->depth_attachment) are uploaded, the
+ * volume is blended and depth-tested over them as VolumeRenderSubpass::draw does
+ * for each volume of the scene in turn (src/volume_render_subpass.cpp:176-190,
+ * 219-293) — a rasterised background (src/volume_render.cpp:344-350 feeds the
+ * Sponza depth to the DEPTH_ATTACHMENT shader variant) or the volumes drawn before
+ * this one — and both buffers are copied back.  Without load_framebuffer it is
+ * vkv_render_to_host plus the gl_FragDepth image. */
+VKV_API int vkv_render_over_host(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_cast_uniform *ray,
+                                 const vkv_transfer_function_uniform *tfu, const vkv_render_options *opt, int width,
+                                 int height, uint8_t *rgba8_host, float *depth_host, vkv_sample_counts *counts_host,
+                                 void *stream);
 
 /* ---- resource access (Volume::get_* : src/volume_component.h:65-69) --------- */
 VKV_API int      vkv_volume_extent(const vkv_volume *vol, uint32_t out[3]);

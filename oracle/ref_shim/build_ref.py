@@ -115,6 +115,10 @@ def variants():
             continue
         d = (["PRECOMPUTED_GRADIENT"] if pre else []) + skip_defs[skip] + ([] if ert else ["DISABLE_EARLY_RAY_TERMINATION"]) + test_defs[test]
         v[f"frag_p{pre}_s{skip}_e{ert}_t{test}"] = ("volume_render.frag", d, "HARNESS_FRAG")
+    # DEPTH_ATTACHMENT (options.depth_attachment, volume_render_subpass.cpp:77-80): the march variants with ERT on + the ray-exit view
+    for skip, test in ((0, 0), (1, 0), (2, 0), (3, 0), (2, 2)):
+        d = ["PRECOMPUTED_GRADIENT", "DEPTH_ATTACHMENT"] + skip_defs[skip] + test_defs[test]
+        v[f"frag_p1_s{skip}_e1_t{test}_d1"] = ("volume_render.frag", d, "HARNESS_FRAG")
     return v
 
 

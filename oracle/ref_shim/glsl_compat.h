@@ -252,6 +252,9 @@ inline vec4 texture(const sampler2D &s, const vec2 &p)
 	const uint8_t *t = s.rgba + (size_t(y) * s.w + size_t(x)) * 4;
 	return vec4(float(t[0]) / 255.0f, float(t[1]) / 255.0f, float(t[2]) / 255.0f, float(t[3]) / 255.0f);
 }
+// input attachment (DEPTH_ATTACHMENT): the harness stores the depth value this fragment's subpassLoad returns
+struct subpassInput { float value = 0.0f; };
+inline vec4 subpassLoad(const subpassInput &s) { return vec4(s.value, 0.0f, 0.0f, 1.0f); }
 inline uvec4 texelFetch(const usampler3D &s, const ivec3 &p, int) { return uvec4(uint(s.data[(size_t(p.z) * s.h + size_t(p.y)) * s.w + size_t(p.x)]), 0u, 0u, 1u); }
 
 // ---- invocation state + subgroup emulation (two-phase: gather the operands, then replay) ---------------------------

@@ -33,4 +33,9 @@ struct RefArgs {
 	float       *frag_depth;        // n_frag
 	// vertex outputs: up to 8 vertices: position_out (4), ray_entry (3), clip distance (1)
 	float vert_out[8 * 8];
+	// DEPTH_ATTACHMENT variants: the interpolated `position` varying (n_frag * 4), the depth subpassLoad returns (n_frag),
+	// and whether the invocation executed `discard` (n_frag); all may be null for the other variants
+	const float *frag_position;
+	const float *frag_depth_in;
+	int32_t     *frag_discarded;
 };

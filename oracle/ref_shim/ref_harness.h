@@ -216,7 +216,13 @@ static void harness_entry(RefArgs *a)
 	for (int i = 0; i < a->n_frag; ++i) {
 		ray_entry = vec3(a->frag_entry[i * 3 + 0], a->frag_entry[i * 3 + 1], a->frag_entry[i * 3 + 2]);
 		position  = vec4(0.0f, 0.0f, 0.5f, 1.0f);        // only read under DEPTH_ATTACHMENT
+		if (a->frag_position) position = vec4(a->frag_position[i * 4 + 0], a->frag_position[i * 4 + 1], a->frag_position[i * 4 + 2], a->frag_position[i * 4 + 3]);
+#ifdef DEPTH_ATTACHMENT
+		i_depth.value = a->frag_depth_in ? a->frag_depth_in[i] : 0.0f;
+#endif
+		shader_discarded = false;
 		shader_main();
+		if (a->frag_discarded) a->frag_discarded[i] = shader_discarded ? 1 : 0;
 		for (int k = 0; k < 4; ++k) a->frag_out[i * 4 + k] = out_color[k];
 		a->frag_depth[i] = gl_FragDepth;
 	}

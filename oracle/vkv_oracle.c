@@ -756,15 +756,34 @@ static float frag_gradient(const frag_ctx *c, const float pos[3], const float di
 static inline float glsl_step(float edge, float x) { return x < edge ? 0.0f : 1.0f; }
 static inline float glsl_sign(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
 
-/* main() of shaders/volume_render.frag:117-336 for one fragment whose interpolated varying is `entry`.
- * `out` is the shader's out_color (premultiplied, before blending); returns the gl_FragDepth value. */
-static float frag_main(const frag_ctx *c, const float entry[3], float out[4], uint32_t n_samples[3])
+/* mat4 * vec4 in fp32, summed left to right as a GLSL compiler without contraction does */
+static void m4f_mul_v(const float *m, const float v[4], float out[4])
+{
+	for (int r = 0; r < 4; ++r) out[r] = ((m[0 + r] * v[0] + m[4 + r] * v[1]) + m[8 + r] * v[2]) + m[12 + r] * v[3];
+}
+
+/* main() of shaders/volume_render.frag:117-336 for one fragment whose interpolated varyings are `entry` (ray_entry) and
+ * `position` (clip-space gl_Position of the entry point; read only under DEPTH_ATTACHMENT, where `depth_in` is what
+ * subpassLoad(i_depth) returns).  `out` is the shader's out_color (premultiplied, before blending); returns the gl_FragDepth
+ * value; *discarded is set when the shader executes `discard` (:133). */
+static float frag_main(const frag_ctx *c, const float entry[3], const float position[4], float depth_in, float out[4],
+                       uint32_t n_samples[3], int *discarded)
 {
 	const vkv_transfer_function_uniform *tfu = c->tfu;
 	const vkv_render_options            *opt = c->opt;
 	out[0] = out[1] = out[2] = out[3] = 0.0f;
 	float frag_depth = 0.0f; /* REVERSE_DEPTH, no depth attachment (:139-141) */
 	n_samples[0] = n_samples[1] = n_samples[2] = 0;
+	*discarded = 0;
+	float frag_depth_front = 0.0f;
+	if (opt->depth_attachment) { /* :122-136 */
+		frag_depth_front = position[2] / position[3];
+		if (depth_in > frag_depth_front) { /* REVERSE_DEPTH: the front face is behind the scene */
+			*discarded = 1;
+			return frag_depth;
+		}
+		frag_depth = depth_in;
+	}
 
 	/* ray exit (:146-149) */
 	float dv[3] = {entry[0] - c->ray->cam_pos_tex[0], entry[1] - c->ray->cam_pos_tex[1], entry[2] - c->ray->cam_pos_tex[2]};
@@ -783,6 +802,23 @@ static float frag_main(const frag_ctx *c, const float entry[3], float out[4], ui
 	float ray_exit[3] = {t_far * dir[0] + entry[0], t_far * dir[1] + entry[1], t_far * dir[2] + entry[2]};
 	float ev[3]       = {entry[0] - ray_exit[0], entry[1] - ray_exit[1], entry[2] - ray_exit[2]};
 	float ray_distance = sqrtf((ev[0] * ev[0] + ev[1] * ev[1]) + ev[2] * ev[2]);
+
+	if (opt->depth_attachment) { /* :151-165: stop the ray where it meets the depth buffer */
+		float clip_at_depth[4] = {position[0] * depth_in / frag_depth_front, position[1] * depth_in / frag_depth_front,
+		                          position[2] * depth_in / frag_depth_front, position[3]};
+		float pos_at_depth[4], pm[4];
+		m4f_mul_v(c->cam->view_proj_inv, clip_at_depth, pos_at_depth);
+		const float w = pos_at_depth[3];
+		for (int a = 0; a < 4; ++a) pos_at_depth[a] = pos_at_depth[a] / w;
+		m4f_mul_v(c->cam->model_inv, pos_at_depth, pm);
+		float hit[3] = {pm[0] + 0.5f, pm[1] + 0.5f, pm[2] + 0.5f};
+		float hv[3]  = {entry[0] - hit[0], entry[1] - hit[1], entry[2] - hit[2]};
+		float hd     = sqrtf((hv[0] * hv[0] + hv[1] * hv[1]) + hv[2] * hv[2]);
+		if (hd < ray_distance) {
+			ray_exit[0] = hit[0]; ray_exit[1] = hit[1]; ray_exit[2] = hit[2];
+			ray_distance = hd;
+		}
+	}
 
 	if (opt->test == VKV_TEST_RAY_ENTRY) { /* :168-170 */
 		out[0] = entry[0]; out[1] = entry[1]; out[2] = entry[2]; out[3] = 1.0f;
@@ -922,6 +958,12 @@ static inline uint8_t unorm8(float c)
 {
 	return (uint8_t) (clampf(c, 0.0f, 1.0f) * 255.0f + 0.5f);
 }
+/* R8G8B8A8_SRGB load (Vulkan spec, "sRGB EOTF"): what the blender reads back from the attachment */
+static inline float srgb_decode(uint8_t b)
+{
+	float c = (float) b / 255.0f;
+	return c <= 0.04045f ? c / 12.92f : powf((c + 0.055f) / 1.055f, 2.4f);
+}
 
 /* Analytic replacement of both vertex shaders + rasteriser: returns 1 and the
  * interpolated ray_entry varying if the pixel is covered. */
@@ -975,6 +1017,16 @@ void orc_render(const uint8_t *V, const uint8_t *G, const uint8_t *tf, const uin
 	double vp_inv[16], model_inv[16];
 	m4_from_float(cam->view_proj_inv, vp_inv);
 	m4_from_float(cam->model_inv, model_inv);
+	double pvm[16];
+	{
+		double pr[16], vw[16], md[16], pv[16];
+		m4_from_float(cam->proj, pr);
+		m4_from_float(cam->view, vw);
+		m4_from_float(cam->model, md);
+		m4_mul(pr, vw, pv);
+		m4_mul(pv, md, pvm);
+	}
+	const int load = opt->load_framebuffer != 0;
 	uint64_t nv = 0, nd = 0, ne = 0, ncov = 0;
 	if (y_count < 0) { y_first = 0; y_count = height; }
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : nv, nd, ne, ncov)
@@ -984,28 +1036,49 @@ void orc_render(const uint8_t *V, const uint8_t *G, const uint8_t *tf, const uin
 			float    entry[3], out[4] = {0, 0, 0, 0}, fd = 0.0f;
 			uint32_t ns[3] = {0, 0, 0};
 			int      covered = pixel_entry(&c, vp_inv, model_inv, px, py, width, height, entry);
-			float    r, g, b, a;
+			int      discarded = 0, write = 0;
+			/* destination: the render-pass clear (0,0,0,1) / depth 0 (render_pipeline.cpp:38-39), or what the target holds */
+			float dst[4] = {0.0f, 0.0f, 0.0f, 1.0f}, dst_depth = 0.0f;
+			if (load) {
+				if (rgba8) {
+					dst[0] = srgb_decode(rgba8[p * 4 + 0]); dst[1] = srgb_decode(rgba8[p * 4 + 1]); dst[2] = srgb_decode(rgba8[p * 4 + 2]);
+					dst[3] = (float) rgba8[p * 4 + 3] / 255.0f;
+				}
+				if (depth) dst_depth = depth[p];
+			}
+			float r = dst[0], g = dst[1], b = dst[2], a = dst[3];
 			if (covered) {
-				fd = frag_main(&c, entry, out, ns);
-				/* blend with clear (0,0,0,1): rgb = src.rgb + 0*(1-a); a = src.a*(1-src.a)
-				 * (src/volume_render_subpass.cpp:176-186 + pipeline_state.h:108-125) */
-				r = out[0]; g = out[1]; b = out[2];
-				a = out[3] * (1.0f - out[3]);
+				/* the `position` varying: gl_Position of the entry point = proj * view * model * (ray_entry - 0.5)
+				 * (volume_render_clipped.vert:58-62, volume_render_plane_intersection.vert:128) */
+				float position[4] = {0.0f, 0.0f, 0.5f, 1.0f};
+				if (opt->depth_attachment) {
+					double pm[4] = {(double) entry[0] - 0.5, (double) entry[1] - 0.5, (double) entry[2] - 0.5, 1.0}, p4[4];
+					m4_mul_v(pvm, pm, p4);
+					for (int k = 0; k < 4; ++k) position[k] = (float) p4[k];
+				}
+				fd = frag_main(&c, entry, position, dst_depth, out, ns, &discarded);
 				ncov++;
-			} else {
-				r = g = b = 0.0f;
-				a = 1.0f; /* clear colour (render_pipeline.cpp:38) */
+				/* depth test GREATER_OR_EQUAL with depth write, then blend: rgb = src.rgb + dst.rgb * (1 - src.a),
+				 * a = src.a * (1 - src.a) + dst.a * 0  (src/volume_render_subpass.cpp:176-190 + pipeline_state.h:91-125) */
+				if (!discarded && fd >= dst_depth) {
+					const float sa = clampf(out[3], 0.0f, 1.0f);
+					r = clampf(out[0], 0.0f, 1.0f) + dst[0] * (1.0f - sa);
+					g = clampf(out[1], 0.0f, 1.0f) + dst[1] * (1.0f - sa);
+					b = clampf(out[2], 0.0f, 1.0f) + dst[2] * (1.0f - sa);
+					a = sa * (1.0f - sa);
+					write = 1;
+				}
 			}
 			nv += ns[0]; nd += ns[1]; ne += ns[2];
-			if (rgba8) {
+			if (rgba8 && (write || !load)) {
 				/* R8G8B8A8_SRGB store (render_context.cpp:22): sRGB-encode RGB, alpha linear */
 				rgba8[p * 4 + 0] = unorm8(srgb_encode(clampf(r, 0.0f, 1.0f)));
 				rgba8[p * 4 + 1] = unorm8(srgb_encode(clampf(g, 0.0f, 1.0f)));
 				rgba8[p * 4 + 2] = unorm8(srgb_encode(clampf(b, 0.0f, 1.0f)));
 				rgba8[p * 4 + 3] = unorm8(a);
 			}
-			if (rgba_f) { rgba_f[p * 4 + 0] = out[0]; rgba_f[p * 4 + 1] = out[1]; rgba_f[p * 4 + 2] = out[2]; rgba_f[p * 4 + 3] = covered ? out[3] : -1.0f; }
-			if (depth) depth[p] = fd;
+			if (depth && (write || !load)) depth[p] = write ? fd : 0.0f;
+			if (rgba_f) { rgba_f[p * 4 + 0] = out[0]; rgba_f[p * 4 + 1] = out[1]; rgba_f[p * 4 + 2] = out[2]; rgba_f[p * 4 + 3] = covered ? (discarded ? -2.0f : out[3]) : -1.0f; }
 		}
 	if (counts) {
 		counts->volume_samples += nv;

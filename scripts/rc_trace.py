@@ -54,17 +54,22 @@ def main():
     vol.render(cu, ru, tfu, ropt, FW, FH, fb.data_ptr(), 0, 0, 0)
     torch.cuda.synchronize()
     del os.environ["VKV_RC_TRACE"]
-    t = np.fromfile(out, dtype=np.uint64).reshape(-1, 3)
+    t = np.fromfile(out, dtype=np.uint64).reshape(-1, 8)
     t = t[t[:, 0] > 0]
     t0 = t[:, 0].min()
-    start, end, it_ = (t[:, 0] - t0).astype(np.int64), (t[:, 1] - t0).astype(np.int64), t[:, 2].astype(np.int64)
+    start, end = (t[:, 0] - t0).astype(np.int64), (t[:, 1] - t0).astype(np.int64)
+    w = t[:, 2]
+    it_, it_d, it_r, it_m, lanes = [((w >> np.uint64(s)) & np.uint64(0xfff)).astype(np.int64) for s in (0, 12, 24, 36, 48)]
     dur = end - start
     print(f"warps traced {len(t)}  kernel span {end.max() / 1e3:.1f} us  last start {start.max() / 1e3:.1f} us")
     print(f"warp duration us: mean {dur.mean() / 1e3:.2f} p50 {np.median(dur) / 1e3:.2f} p99 {np.percentile(dur, 99) / 1e3:.2f} max {dur.max() / 1e3:.2f}")
     k = np.argsort(-dur)[:8]
     for i in k:
-        print(f"  long warp: start {start[i] / 1e3:7.1f} us  dur {dur[i] / 1e3:7.1f} us  iterations {it_[i]}  ns/iter {dur[i] / max(it_[i], 1):.0f}")
+        print(f"  long warp: start {start[i] / 1e3:7.1f} us  dur {dur[i] / 1e3:7.1f} us  iterations {it_[i]}  ns/iter {dur[i] / max(it_[i], 1):.0f}"
+              f"  with skip load {it_d[i]}  with tex batch {it_r[i]}  mixed {it_m[i]}  mean live lanes {lanes[i]}"
+              f"  | kcycles head {t[i, 3] / 1e3:.1f} issue {t[i, 4] / 1e3:.1f} skip branch {t[i, 5] / 1e3:.1f} sample branch {t[i, 6] / 1e3:.1f}")
     act = it_ > 0
+    print(f"all marching warps: iterations {it_[act].sum()}  with skip load {it_d[act].sum()}  with tex batch {it_r[act].sum()}  mixed {it_m[act].sum()}  mean live lanes {(lanes[act] * it_[act]).sum() / it_[act].sum():.1f}")
     print(f"marching warps {act.sum()}  mean iterations {it_[act].mean():.1f}  mean ns/iter {dur[act].sum() / it_[act].sum():.0f}")
     # concurrency over time (warps in flight, whole GPU) in 5 us buckets
     edges = np.arange(0, end.max() + 5000, 5000)

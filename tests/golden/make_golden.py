@@ -72,6 +72,16 @@ def main():
         for test in (1, 2):
             col, _ = ref.fragments(s["V"], s["G"], s["tf"], s["Dm"], s["dim_b"], s["cu"], s["ru"], s["tfu"], entries, 2, True, test)
             out[f"frag/{tname}/s2_e1_t{test}"] = col
+        # DEPTH_ATTACHMENT variants against a synthetic depth attachment (far / just inside / deeper inside / in front)
+        depth, d_entries, d_pos, d_cov = cases.depth_attachment_pattern(s)
+        out[f"frag_d1/{tname}/depth_in"] = depth
+        out[f"frag_d1/{tname}/position"] = d_pos
+        for skip, test in ((0, 0), (1, 0), (2, 0), (3, 0), (2, 2)):
+            col, dep, disc = ref.fragments(s["V"], s["G"], s["tf"], maps[skip], s["dim_b"], s["cu"], s["ru"], s["tfu"], d_entries, skip, True, test,
+                                           positions=d_pos, depth_in=depth[d_cov])
+            out[f"frag_d1/{tname}/s{skip}_t{test}"] = col
+            out[f"frag_d1_depth/{tname}/s{skip}_t{test}"] = dep
+            out[f"frag_d1_discard/{tname}/s{skip}_t{test}"] = disc
         for skip in (0, 2):        # on-the-fly gradient variant (--gradient_test)
             col, _ = ref.fragments(s["V"], None, s["tf"], maps[skip], s["dim_b"], s["cu"], s["ru"], s["tfu"], entries, skip, True, 0, precomputed=False)
             out[f"frag_otf/{tname}/s{skip}"] = col

@@ -161,8 +161,10 @@ def make_uniforms(dim_whd, dim_b_whd, cam: CameraDesc, image_transform, clip_dis
 
 
 def render(V, G, tf_rgba, maps, dim_b_whd, cu, ru, tfu, opt: RenderOptions, width: int, height: int,
-           precomputed: bool = True, y_first: int = 0, y_count: int = -1, want_float=False, want_depth=False):
-    """Returns (rgba8 [H,W,4], counts, rgba_float or None, depth or None)."""
+           precomputed: bool = True, y_first: int = 0, y_count: int = -1, want_float=False, want_depth=False,
+           rgba_init=None, depth_init=None):
+    """Returns (rgba8 [H,W,4], counts, rgba_float or None, depth or None).  With opt.load_framebuffer the frame is blended and
+    depth-tested over `rgba_init` / `depth_init` (the attachments' previous contents)."""
     V, pv = _u8(V)
     D, H, W = V.shape
     if G is None:
@@ -172,9 +174,11 @@ def render(V, G, tf_rgba, maps, dim_b_whd, cu, ru, tfu, opt: RenderOptions, widt
     if maps is None:
         maps = np.zeros(1, dtype=np.uint8)
     maps, pm = _u8(maps)
-    rgba = np.zeros((height, width, 4), dtype=np.uint8)
+    rgba = np.zeros((height, width, 4), dtype=np.uint8) if rgba_init is None else np.ascontiguousarray(rgba_init, np.uint8).copy()
     rf = np.zeros((height, width, 4), dtype=np.float32) if want_float else None
-    dp = np.zeros((height, width), dtype=np.float32) if want_depth else None
+    if depth_init is not None:
+        want_depth = True
+    dp = (np.zeros((height, width), dtype=np.float32) if depth_init is None else np.ascontiguousarray(depth_init, np.float32).copy()) if want_depth else None
     counts = SampleCounts()
     lib().orc_render(pv, pg, pt, pm, _dims((W, H, D)), _dims(dim_b_whd), C.byref(cu), C.byref(ru), C.byref(tfu), C.byref(opt),
                      C.c_int(int(precomputed)), C.c_int(width), C.c_int(height), C.c_int(y_first), C.c_int(y_count),

@@ -28,6 +28,7 @@ class RefArgs(C.Structure):
         ("block_size_f", C.c_float * 4), ("front_index", C.c_int32),
         ("n_frag", C.c_int32), ("frag_entry", _P), ("frag_out", _P), ("frag_depth", _P),
         ("vert_out", C.c_float * 64),
+        ("frag_position", _P), ("frag_depth_in", _P), ("frag_discarded", _P),
     ]
 
 
@@ -144,8 +145,10 @@ def _set_camera(a: RefArgs, cu, ru):
     a.plane, a.plane_tex, a.cam_pos_tex, a.block_size_f, a.front_index = ru.plane, ru.plane_tex, ru.cam_pos_tex, ru.block_size, ru.front_index
 
 
-def fragments(V, G, tf, maps, dim_b_whd, cu, ru, tfu, entries: np.ndarray, skip: int, ert: bool, test: int = 0, precomputed=True):
-    """Runs volume_render.frag (the selected #define variant) for each ray_entry in `entries` [n,3]."""
+def fragments(V, G, tf, maps, dim_b_whd, cu, ru, tfu, entries: np.ndarray, skip: int, ert: bool, test: int = 0, precomputed=True,
+              positions: np.ndarray | None = None, depth_in: np.ndarray | None = None):
+    """Runs volume_render.frag (the selected #define variant) for each ray_entry in `entries` [n,3].
+    With `positions` [n,4] and `depth_in` [n] the DEPTH_ATTACHMENT variant runs and a third array (1 = discarded) is returned."""
     V = np.ascontiguousarray(V, np.uint8)
     G = np.ascontiguousarray(G if G is not None else np.zeros_like(V), np.uint8)
     tf = np.ascontiguousarray(tf, np.uint8)
@@ -170,6 +173,13 @@ def fragments(V, G, tf, maps, dim_b_whd, cu, ru, tfu, entries: np.ndarray, skip:
             a.maps[0] = _ptr(maps).value
         keep.append(maps)
     a.n_frag, a.frag_entry, a.frag_out, a.frag_depth = n, _ptr(entries), _ptr(out), _ptr(depth)
+    if depth_in is not None:
+        positions = np.ascontiguousarray(positions, np.float32)
+        depth_in = np.ascontiguousarray(depth_in, np.float32)
+        disc = np.zeros(n, np.int32)
+        a.frag_position, a.frag_depth_in, a.frag_discarded = _ptr(positions), _ptr(depth_in), _ptr(disc)
+        _call(f"frag_p{int(precomputed)}_s{skip}_e{int(ert)}_t{test}_d1", a)
+        return out, depth, disc
     _call(f"frag_p{int(precomputed)}_s{skip}_e{int(ert)}_t{test}", a)
     return out, depth
 

@@ -69,3 +69,28 @@ def ray_entries(s, width=40, height=30):
     _, _, rf, _ = orc.render(s["V"], s["G"], s["tf"], None, s["dim_b"], s["cu"], s["ru"], s["tfu"], ropt, width, height, want_float=True)
     cov = rf[..., 3] >= 0
     return rf[cov][:, :3].copy(), cov
+
+
+def entry_positions(s, entries):
+    """The `position` varying of each ray entry: gl_Position = proj * view * model * (ray_entry - 0.5)
+    (volume_render_clipped.vert:58-62), evaluated like the oracle does (fp64 product, rounded once)."""
+    m = lambda a: np.array(list(a), np.float32).astype(np.float64).reshape(4, 4).T        # column-major uniforms
+    pvm = (m(s["cu"].proj) @ m(s["cu"].view)) @ m(s["cu"].model)
+    pm = np.concatenate([entries.astype(np.float64) - 0.5, np.ones((len(entries), 1))], axis=1)
+    return (pm @ pvm.T).astype(np.float32)
+
+
+def depth_attachment_pattern(s, width=40, height=30):
+    """A synthetic depth attachment for the DEPTH_ATTACHMENT variants, as a full frame: per pixel one of
+    nothing behind the volume (0 = far in reverse-Z) | geometry just inside the front face | geometry deeper inside |
+    geometry in front of the volume (the fragment is discarded)."""
+    entries, cov = ray_entries(s, width, height)
+    pos = entry_positions(s, entries)
+    front = np.zeros((height, width), np.float32)
+    front[cov] = pos[:, 2] / pos[:, 3]
+    yy, xx = np.mgrid[0:height, 0:width]
+    sel = (xx + 2 * yy) % 4
+    factor = np.choose(sel, [0.0, 1.0 / 1.004, 1.0 / 1.02, 1.1]).astype(np.float32)
+    depth = (front * factor).astype(np.float32)
+    depth[~cov] = np.float32(0.25) * (sel[~cov] == 3)        # something also behind pixels the volume does not cover
+    return depth, entries, pos, cov

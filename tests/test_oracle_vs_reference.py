@@ -131,6 +131,33 @@ def test_fragment_shader_variants_match_reference(tname):
         assert np.abs(rf[cov] - gold(f"frag_otf/{tname}/s{skip}")).max() <= 2e-6
 
 
+@pytest.mark.parametrize("tname", ["default", "beetle_nograd", "snake_window"])
+def test_depth_attachment_variants_match_reference(tname):
+    """volume_render.frag with DEPTH_ATTACHMENT (:122-136,151-165): discard behind the scene's depth, rays shortened at it."""
+    s = cases.render_scene(tname, False)
+    depth, entries, pos, cov = cases.depth_attachment_pattern(s)
+    assert np.array_equal(depth, gold(f"frag_d1/{tname}/depth_in")) and np.array_equal(pos, gold(f"frag_d1/{tname}/position"))
+    W, H = 40, 30
+    clear = np.zeros((H, W, 4), np.uint8)
+    clear[..., 3] = 255
+    n_short = 0
+    for skip, test in ((0, 0), (1, 0), (2, 0), (3, 0), (2, 2)):
+        maps = None if skip == 0 else s[SKIP_MAPS[skip]]
+        ropt = RenderOptions(skipping_type=skip, clip_distance=s["clip"], early_ray_termination=1, test=test, depth_attachment=1, load_framebuffer=1)
+        _, _, rf, dp = orc.render(s["V"], s["G"], s["tf"], maps, s["dim_b"], s["cu"], s["ru"], s["tfu"], ropt, W, H, want_float=True,
+                                  rgba_init=clear, depth_init=depth)
+        got, disc = rf[cov], gold(f"frag_d1_discard/{tname}/s{skip}_t{test}").astype(bool)
+        assert np.array_equal(got[:, 3] == -2.0, disc) and 0 < disc.sum() < len(disc)
+        assert np.abs(got[~disc] - gold(f"frag_d1/{tname}/s{skip}_t{test}")[~disc]).max() <= 2e-6
+        # depth written where the fragment survives = the shader's gl_FragDepth (>= the attachment's value: the test passes)
+        assert np.allclose(dp[cov][~disc], gold(f"frag_d1_depth/{tname}/s{skip}_t{test}")[~disc], rtol=1e-4, atol=1e-6)
+        assert np.array_equal(dp[cov][disc], depth[cov][disc]) and np.array_equal(dp[~cov], depth[~cov])        # untouched elsewhere
+        if test == 2:
+            full = gold(f"frag/{tname}/s2_e1_t2")
+            n_short = int((np.abs(full[~disc, :3] - got[~disc, :3]).max(axis=1) > 1e-6).sum())
+    assert n_short > 20        # the pattern really shortens rays
+
+
 @pytest.mark.parametrize("tname", ["uint8_t", "int8_t", "uint16_t", "int16_t"])
 @pytest.mark.parametrize("endian", ["little", "big"])
 def test_loader_matches_reference_load_volume_cpp(tname, endian):

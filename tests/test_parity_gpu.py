@@ -320,6 +320,131 @@ def test_render_camera_inside_with_clip_plane_anisotropic_voxels(ctx):
     assert counts.covered_pixels == rcounts.covered_pixels
 
 
+# ---- depth output, depth attachment, compositing over an existing target -------------------------------
+def _scene_for_compositing(ctx, shape, opt, seed, skip, bs=4):
+    D, H, W = shape
+    V = scene.blobs_volume(shape, seed=seed)
+    tfu = capi.transfer_function_uniform(opt)
+    G = orc.gradient_map(V, bool(tfu.use_gradient))
+    tf = orc.transfer_function_texture(opt)
+    O = orc.occupancy_map(V, G, tf, bs, bool(tfu.use_gradient))
+    maps = {SKIP_NONE: None, SKIP_BLOCK: O, SKIP_DISTANCE: orc.distance_map(O), SKIP_ANISOTROPIC_DISTANCE: orc.distance_map_anisotropic(O)}[skip]
+    vol = capi.Volume(ctx, W, H, D, block_size=bs)
+    vol.upload(V)
+    vol.upload_gradient(G)
+    vol.update_transfer_function_texture(opt)
+    vol.compute_distance_map(tfu, skip)
+    return dict(V=V, G=G, tf=tf, tfu=tfu, maps=maps, vol=vol)
+
+
+def _depth_close(d, ref):
+    return np.allclose(d, ref, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("skip", [SKIP_NONE, SKIP_DISTANCE])
+def test_render_depth_output_matches_oracle(ctx, skip):
+    """gl_FragDepth at the first contributing sample (volume_render.frag:314-321), 0 where nothing was hit."""
+    opt = VolumeOptions(**TF_SETS[0])
+    sc = _scene_for_compositing(ctx, (48, 64, 80), opt, 1, skip)
+    vol, width, height = sc["vol"], 160, 128
+    it = scene.image_transform((0.004,) * 3, (80, 64, 48))
+    cu, ru = vol.make_uniforms(scene.look_at_camera((34, 22, 50), aspect=width / height), it, 5.0)
+    ropt = RenderOptions(skipping_type=skip, clip_distance=5.0, filter=FILTER_EXACT)
+    img, depth, counts = vol.render_over_host(cu, ru, sc["tfu"], ropt, width, height, depth=np.full((height, width), 7.0, np.float32))
+    ref, rcounts, _, rdepth = orc.render(sc["V"], sc["G"], sc["tf"], sc["maps"], vol.map_extent, cu, ru, sc["tfu"], ropt, width, height, want_depth=True)
+    frac, p = frame_bar(img, ref)
+    assert frac >= 0.999 and p >= 50.0, (frac, p)
+    assert (rdepth > 0).sum() > 1000 and np.array_equal(depth > 0, rdepth > 0)
+    assert _depth_close(depth, rdepth)
+    vol.close()
+
+
+def _depth_wall(sc, cu, ru, tfu, width, height, clip):
+    """A synthetic depth attachment: stripes of nothing (0 = far) | geometry inside the volume | geometry in front of it."""
+    ropt = RenderOptions(skipping_type=SKIP_NONE, clip_distance=clip, test=TEST_RAY_ENTRY)
+    _, _, rf, _ = orc.render(sc["V"], sc["G"], sc["tf"], None, sc["vol"].map_extent, cu, ru, tfu, ropt, width, height, want_float=True)
+    cov = rf[..., 3] >= 0
+    m = lambda a: np.array(list(a), np.float32).astype(np.float64).reshape(4, 4).T
+    pvm = (m(cu.proj) @ m(cu.view)) @ m(cu.model)
+    pm = np.concatenate([rf[..., :3].astype(np.float64) - 0.5, np.ones((height, width, 1))], axis=2)
+    pos = pm @ pvm.T
+    front = np.where(cov, pos[..., 2] / pos[..., 3], 0.0)
+    yy, xx = np.mgrid[0:height, 0:width]
+    sel = ((xx // 8) + (yy // 8)) % 4
+    depth = (front * np.choose(sel, [0.0, 1 / 1.004, 1 / 1.02, 1.1])).astype(np.float32)
+    depth[~cov] = np.where(sel[~cov] == 3, np.float32(0.25), np.float32(0.0))
+    return depth, cov
+
+
+@pytest.mark.parametrize("skip", [SKIP_NONE, SKIP_BLOCK, SKIP_DISTANCE, SKIP_ANISOTROPIC_DISTANCE])
+@pytest.mark.parametrize("filt", [FILTER_EXACT, FILTER_HARDWARE])
+def test_render_depth_attachment_over_background(ctx, skip, filt):
+    """DEPTH_ATTACHMENT variant (volume_render.frag:122-136,151-165) over a coloured background with a depth image: fragments
+    behind the scene are discarded, rays stop at the scene's depth, the rest blends over the background (sRGB target)."""
+    opt = VolumeOptions(**TF_SETS[0])
+    sc = _scene_for_compositing(ctx, (48, 64, 80), opt, 1, skip)
+    vol, width, height, clip = sc["vol"], 160, 128, 5.0
+    it = scene.image_transform((0.004,) * 3, (80, 64, 48))
+    cu, ru = vol.make_uniforms(scene.look_at_camera((34, 22, 50), aspect=width / height), it, clip)
+    depth0, cov = _depth_wall(sc, cu, ru, sc["tfu"], width, height, clip)
+    rng = np.random.default_rng(3)
+    bg = rng.integers(0, 256, size=(height, width, 4), dtype=np.uint8)
+    ropt = RenderOptions(skipping_type=skip, clip_distance=clip, filter=filt, depth_attachment=1, load_framebuffer=1)
+    img, depth, counts = vol.render_over_host(cu, ru, sc["tfu"], ropt, width, height, rgba=bg.copy(), depth=depth0.copy())
+    ref, rcounts, rf, rdepth = orc.render(sc["V"], sc["G"], sc["tf"], sc["maps"], vol.map_extent, cu, ru, sc["tfu"], ropt, width, height,
+                                          want_float=True, rgba_init=bg, depth_init=depth0)
+    discarded = rf[..., 3] == -2.0
+    assert discarded.sum() > 500 and (cov & ~discarded).sum() > 2000
+    frac, p = frame_bar(img, ref)
+    assert frac >= 0.999 and p >= 50.0, (frac, p)
+    keep = ~cov | discarded        # pixels the volume does not write keep the background and its depth, byte for byte
+    assert np.array_equal(img[keep], bg[keep]) and np.array_equal(depth[keep], depth0[keep])
+    assert _depth_close(depth, rdepth)
+    assert counts.covered_pixels == rcounts.covered_pixels
+    if filt == FILTER_EXACT:
+        tot, rtot = counts.volume_samples + counts.distance_samples, rcounts.volume_samples + rcounts.distance_samples
+        assert abs(tot - rtot) <= 1e-3 * rtot + 8
+    vol.close()
+
+
+def test_render_depth_attachment_argument_checks(ctx):
+    opt = VolumeOptions(**TF_SETS[1])
+    sc = _scene_for_compositing(ctx, (16, 16, 16), opt, 2, SKIP_NONE)
+    vol = sc["vol"]
+    cu, ru = vol.make_uniforms(scene.look_at_camera((10, 8, 14), aspect=1.0), scene.image_transform((0.004,) * 3, (16, 16, 16)), 1.0)
+    with pytest.raises(capi.VkvError):        # no depth buffer
+        vol.render_over_host(cu, ru, sc["tfu"], RenderOptions(skipping_type=SKIP_NONE, depth_attachment=1, load_framebuffer=1), 32, 32)
+    with pytest.raises(capi.VkvError):        # depth attachment without loading the target
+        vol.render_over_host(cu, ru, sc["tfu"], RenderOptions(skipping_type=SKIP_NONE, depth_attachment=1), 32, 32, depth=np.zeros((32, 32), np.float32))
+    vol.close()
+
+
+@pytest.mark.parametrize("skip", [SKIP_DISTANCE, SKIP_ANISOTROPIC_DISTANCE])
+def test_render_two_volumes_composited_in_scene_order(ctx, skip):
+    """VolumeRenderSubpass::draw loops over the scene's volumes (volume_render_subpass.cpp:219-293): the second volume blends
+    and depth-tests over what the first one left in the target."""
+    width, height, clip = 160, 128, 5.0
+    a = _scene_for_compositing(ctx, (48, 64, 80), VolumeOptions(**TF_SETS[0]), 1, skip)
+    b = _scene_for_compositing(ctx, (40, 40, 56), VolumeOptions(**TF_SETS[1]), 5, skip)
+    cam = scene.look_at_camera((34, 22, 50), aspect=width / height)
+    cu_a, ru_a = a["vol"].make_uniforms(cam, scene.image_transform((0.004,) * 3, (80, 64, 48)), clip)
+    cu_b, ru_b = b["vol"].make_uniforms(cam, scene.image_transform((0.006, 0.005, 0.004), (56, 40, 40), (0, 1, 0, 25)), clip)
+    first = RenderOptions(skipping_type=skip, clip_distance=clip, filter=FILTER_EXACT)
+    second = RenderOptions(skipping_type=skip, clip_distance=clip, filter=FILTER_EXACT, load_framebuffer=1)
+    img, depth, _ = a["vol"].render_over_host(cu_a, ru_a, a["tfu"], first, width, height, depth=np.zeros((height, width), np.float32))
+    only_a = img.copy()
+    img, depth, _ = b["vol"].render_over_host(cu_b, ru_b, b["tfu"], second, width, height, rgba=img, depth=depth)
+    ref, _, _, rdepth = orc.render(a["V"], a["G"], a["tf"], a["maps"], a["vol"].map_extent, cu_a, ru_a, a["tfu"], first, width, height, want_depth=True)
+    ref, _, rf, rdepth = orc.render(b["V"], b["G"], b["tf"], b["maps"], b["vol"].map_extent, cu_b, ru_b, b["tfu"], second, width, height,
+                                    want_float=True, rgba_init=ref, depth_init=rdepth)
+    frac, p = frame_bar(img, ref)
+    assert frac >= 0.999 and p >= 50.0, (frac, p)
+    assert _depth_close(depth, rdepth)
+    assert (img != only_a).any(axis=2).sum() > 500        # the second volume really drew over the first
+    a["vol"].close()
+    b["vol"].close()
+
+
 @pytest.mark.parametrize("test_mode", [TEST_RAY_ENTRY, TEST_RAY_EXIT, TEST_NUM_TEXTURE_SAMPLES])
 def test_render_debug_views(ctx, test_mode):
     img, counts, ref, rcounts, _ = _render_case(ctx, (48, 64, 80), VolumeOptions(**TF_SETS[0]), (34, 22, 50), 5.0, SKIP_DISTANCE,

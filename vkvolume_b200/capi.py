@@ -7,6 +7,7 @@ raises.  Nothing here imports or calls the CPU oracle.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
@@ -60,11 +61,11 @@ class VolumeOptions(C.Structure):
 class RenderOptions(C.Structure):
     """VolumeRenderSubpass::Options (src/volume_render_subpass.h:74-81) + filter selector."""
     _fields_ = [("skipping_type", C.c_int32), ("clip_distance", C.c_float), ("early_ray_termination", C.c_int32),
-                ("depth_attachment", C.c_int32), ("test", C.c_int32), ("filter", C.c_int32)]
+                ("depth_attachment", C.c_int32), ("test", C.c_int32), ("filter", C.c_int32), ("load_framebuffer", C.c_int32)]
 
     def __init__(self, skipping_type=SKIP_DISTANCE, clip_distance=50.0, early_ray_termination=1,
-                 depth_attachment=0, test=TEST_NONE, filter=FILTER_HARDWARE):
-        super().__init__(skipping_type, clip_distance, early_ray_termination, depth_attachment, test, filter)
+                 depth_attachment=0, test=TEST_NONE, filter=FILTER_HARDWARE, load_framebuffer=0):
+        super().__init__(skipping_type, clip_distance, early_ray_termination, depth_attachment, test, filter, load_framebuffer)
 
 
 class CameraDesc(C.Structure):
@@ -126,6 +127,8 @@ _SIGNATURES = {
                                    _P, _P, _P, _P]),
     "vkv_render_to_host": (C.c_int, [_P, C.POINTER(CameraUniform), C.POINTER(RayCastUniform), C.POINTER(TransferFunctionUniform),
                                      C.POINTER(RenderOptions), C.c_int, C.c_int, _P, C.POINTER(SampleCounts), _P]),
+    "vkv_render_over_host": (C.c_int, [_P, C.POINTER(CameraUniform), C.POINTER(RayCastUniform), C.POINTER(TransferFunctionUniform),
+                                       C.POINTER(RenderOptions), C.c_int, C.c_int, _P, _P, C.POINTER(SampleCounts), _P]),
     "vkv_volume_extent": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
     "vkv_volume_map_extent": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
     "vkv_volume_block_size": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
@@ -165,7 +168,8 @@ def lib() -> C.CDLL:
             raise FileNotFoundError(
                 f"{LIB_PATH} is missing: build it with `python -m vkvolume_b200.build` "
                 "(there is no CPU or PyTorch fallback for this path)")
-        handle = C.CDLL(str(LIB_PATH))
+        # VKV_LIB: debug knob, an alternative build of the same library (A/B of compile-time kernel parameters)
+        handle = C.CDLL(os.environ.get("VKV_LIB") or str(LIB_PATH))
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)        # AttributeError if the symbol is not exported
             fn.restype, fn.argtypes = res, args
@@ -320,6 +324,21 @@ class Volume:
         check(lib().vkv_render_to_host(self.handle, C.byref(cu), C.byref(ru), C.byref(tfu), C.byref(opt), width, height,
                                        _host_ptr(out), C.byref(counts) if want_counts else None, _P(stream)))
         return out, counts
+
+    def render_over_host(self, cu, ru, tfu, opt, width, height, rgba: np.ndarray | None = None, depth: np.ndarray | None = None,
+                         want_counts=True, stream: int = 0):
+        """vkv_render_over_host: composites over `rgba` [H,W,4] u8 / `depth` [H,W] f32 in place when opt.load_framebuffer
+        (VolumeRenderSubpass::draw's blend + depth test over what is already in the target); returns (rgba, depth, counts)."""
+        if rgba is None:
+            rgba = np.empty((height, width, 4), dtype=np.uint8)
+        assert rgba.dtype == np.uint8 and rgba.flags.c_contiguous and rgba.shape == (height, width, 4)
+        if depth is not None:
+            assert depth.dtype == np.float32 and depth.flags.c_contiguous and depth.shape == (height, width)
+        counts = SampleCounts()
+        check(lib().vkv_render_over_host(self.handle, C.byref(cu), C.byref(ru), C.byref(tfu), C.byref(opt), width, height,
+                                         _host_ptr(rgba), _host_ptr(depth) if depth is not None else None,
+                                         C.byref(counts) if want_counts else None, _P(stream)))
+        return rgba, depth, counts
 
     # -- read-backs ------------------------------------------------------------------------
     def download_voxels(self):

@@ -405,14 +405,15 @@ int vkv_update_transfer_function(vkv_volume *vol, const vkv_volume_options *opt,
 }
 
 static int check_render(vkv_volume *vol, const vkv_transfer_function_uniform *tfu, const vkv_render_options *opt, int width, int height,
-                        int tile_w, int tile_h, int tile_stride)
+                        int tile_w, int tile_h, int tile_stride, bool have_depth)
 {
 	VKV_REQUIRE(width > 0 && height > 0, VKV_ERR_ARGUMENT, "bad framebuffer extent");
 	VKV_REQUIRE(tile_w > 0 && tile_h > 0 && tile_w % 16 == 0 && tile_h % 8 == 0, VKV_ERR_ARGUMENT, "tile extent must be a multiple of 16x8");
 	VKV_REQUIRE(tile_stride > 0, VKV_ERR_ARGUMENT, "tile stride must be positive");
 	VKV_REQUIRE(opt->skipping_type >= 0 && opt->skipping_type <= 3, VKV_ERR_ARGUMENT, "bad skipping type");
 	VKV_REQUIRE(opt->test >= 0 && opt->test <= 3, VKV_ERR_ARGUMENT, "bad test mode");
-	VKV_REQUIRE(!opt->depth_attachment, VKV_ERR_ARGUMENT, "depth_attachment is not supported by the headless renderer");
+	VKV_REQUIRE(!opt->depth_attachment || (opt->load_framebuffer && have_depth), VKV_ERR_ARGUMENT,
+	            "depth_attachment needs load_framebuffer = 1 and a depth buffer holding the scene's depth");
 	VKV_REQUIRE(vol->has_V && vol->has_tf, VKV_ERR_STATE, "vkv_render: upload voxels and a transfer function first");
 	int rc;
 	if ((rc = check_gradient_inputs(vol, tfu))) return rc;
@@ -434,7 +435,7 @@ int vkv_render_tiles(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_r
 	VKV_REQUIRE(vol && cam && ray && tfu && opt && rgba8_dev, VKV_ERR_ARGUMENT, "vkv_render: NULL argument");
 	VKV_REQUIRE(tile_first >= 0, VKV_ERR_ARGUMENT, "tile_first must be >= 0");
 	int rc;
-	if ((rc = check_render(vol, tfu, opt, width, height, tile_w, tile_h, tile_stride))) return rc;
+	if ((rc = check_render(vol, tfu, opt, width, height, tile_w, tile_h, tile_stride, depth_dev != nullptr))) return rc;
 	DeviceGuard guard(vol->ctx->device);
 	return launch_render(vol, cam, ray, tfu, opt, width, height, tile_w, tile_h, tile_first, tile_stride, -1, rgba8_dev, depth_dev,
 	                     counts_dev, (cudaStream_t) stream);
@@ -452,9 +453,10 @@ int vkv_render_to_host(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv
                        uint8_t *rgba8_host, vkv_sample_counts *counts_host, void *stream)
 {
 	VKV_REQUIRE(vol && cam && ray && tfu && opt && rgba8_host, VKV_ERR_ARGUMENT, "vkv_render_to_host: NULL argument");
+	if (opt->load_framebuffer || opt->depth_attachment) return vkv_render_over_host(vol, cam, ray, tfu, opt, width, height, rgba8_host, nullptr, counts_host, stream);
 	constexpr int TW = 64, TH = 32, kBands = 1;        // measured on B200: cross-stream band overlap costs more than it hides (scripts/e2e_probe.py)
 	int rc;
-	if ((rc = check_render(vol, tfu, opt, width, height, TW, TH, 1))) return rc;
+	if ((rc = check_render(vol, tfu, opt, width, height, TW, TH, 1, false))) return rc;
 	DeviceGuard  guard(vol->ctx->device);
 	cudaStream_t s     = (cudaStream_t) stream;
 	const size_t bytes = (size_t) width * height * 4;
@@ -516,6 +518,42 @@ int vkv_render_to_host(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv
 	if (counts_host) VKV_CUDA_CHECK(cudaMemcpyAsync(vol->h_count, vol->d_counts_scratch, sizeof(vkv_sample_counts), cudaMemcpyDeviceToHost, s));
 	VKV_CUDA_CHECK(cudaEventRecord(vol->copies_done, vol->copy_stream));
 	VKV_CUDA_CHECK(cudaStreamWaitEvent(s, vol->copies_done, 0));
+	VKV_CUDA_CHECK(cudaStreamSynchronize(s));
+	if (counts_host) memcpy(counts_host, vol->h_count, sizeof(vkv_sample_counts));
+	return VKV_OK;
+}
+
+int vkv_render_over_host(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_cast_uniform *ray,
+                         const vkv_transfer_function_uniform *tfu, const vkv_render_options *opt, int width, int height,
+                         uint8_t *rgba8_host, float *depth_host, vkv_sample_counts *counts_host, void *stream)
+{
+	VKV_REQUIRE(vol && cam && ray && tfu && opt && rgba8_host, VKV_ERR_ARGUMENT, "vkv_render_over_host: NULL argument");
+	int rc;
+	if ((rc = check_render(vol, tfu, opt, width, height, 64, 32, 1, depth_host != nullptr))) return rc;
+	DeviceGuard  guard(vol->ctx->device);
+	cudaStream_t s      = (cudaStream_t) stream;
+	const size_t px     = (size_t) width * height;
+	const size_t fbytes = px * 4, dbytes = depth_host ? px * sizeof(float) : 0;
+	// one scratch allocation: colour, then depth
+	if (vol->fb_scratch_bytes < fbytes + dbytes) {
+		cudaFree(vol->d_fb_scratch);
+		vol->d_fb_scratch     = nullptr;
+		vol->fb_scratch_bytes = 0;
+		VKV_CUDA_CHECK(cudaMalloc(&vol->d_fb_scratch, fbytes + dbytes));
+		vol->fb_scratch_bytes = fbytes + dbytes;
+	}
+	uint8_t *d_rgba  = vol->d_fb_scratch;
+	float   *d_depth = depth_host ? reinterpret_cast<float *>(vol->d_fb_scratch + fbytes) : nullptr;
+	if (opt->load_framebuffer) {
+		VKV_CUDA_CHECK(cudaMemcpyAsync(d_rgba, rgba8_host, fbytes, cudaMemcpyHostToDevice, s));
+		if (d_depth) VKV_CUDA_CHECK(cudaMemcpyAsync(d_depth, depth_host, dbytes, cudaMemcpyHostToDevice, s));
+	}
+	vkv_sample_counts *counts_dev = counts_host ? vol->d_counts_scratch : nullptr;
+	if (counts_host) VKV_CUDA_CHECK(cudaMemsetAsync(vol->d_counts_scratch, 0, sizeof(vkv_sample_counts), s));
+	if ((rc = launch_render(vol, cam, ray, tfu, opt, width, height, 64, 32, 0, 1, -1, d_rgba, d_depth, counts_dev, s))) return rc;
+	VKV_CUDA_CHECK(cudaMemcpyAsync(rgba8_host, d_rgba, fbytes, cudaMemcpyDeviceToHost, s));
+	if (d_depth) VKV_CUDA_CHECK(cudaMemcpyAsync(depth_host, d_depth, dbytes, cudaMemcpyDeviceToHost, s));
+	if (counts_host) VKV_CUDA_CHECK(cudaMemcpyAsync(vol->h_count, vol->d_counts_scratch, sizeof(vkv_sample_counts), cudaMemcpyDeviceToHost, s));
 	VKV_CUDA_CHECK(cudaStreamSynchronize(s));
 	if (counts_host) memcpy(counts_host, vol->h_count, sizeof(vkv_sample_counts));
 	return VKV_OK;

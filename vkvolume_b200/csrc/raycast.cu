@@ -33,6 +33,7 @@ struct RayParams {
 	double o[3];                    // camera position, texture space
 	double d0[3], ddx[3], ddy[3];   // far-plane direction of pixel (px,py): d0 + px*ddx + py*ddy
 	double plane[4];                // clip plane, texture space
+	double pvm_x[4], pvm_y[4];      // rows x and y of proj*view*model (the `position` varying under depth_attachment)
 	double pvm_z[4], pvm_w[4];      // rows z and w of proj*view*model (depth output)
 	double s0;                      // plane . (o, 1)
 	float  fd0[3], fddx[3], fddy[3], fo[3], fplane[3], fs0;        // fp32 copies for the conservative rejection test
@@ -46,6 +47,8 @@ struct RayParams {
 	float  sampling_factor, sampling_factor_inv, voxel_alpha_factor, grad_modifier;
 	int    use_gradient;
 	int    ert, test;
+	int    depth_attachment;        // DEPTH_ATTACHMENT variant of the fragment shader (LOAD instantiations only)
+	float  vpi[16], mi[16];         // view_proj_inv and model_inv in fp32, column-major (depth-buffer intersection)
 	int    width, height;
 	int    tile_w, tile_h, tiles_x, tile_first, tile_stride, my_tiles, seq_base;
 	int    bbox[4];                 // conservative screen bounds (inclusive) of the unit cube: x0, y0, x1, y1
@@ -121,6 +124,12 @@ __device__ __forceinline__ float gradient_otf(cudaTextureObject_t tex, const uin
 }
 
 __device__ __forceinline__ float srgb_encode(float c) { return c <= 0.0031308f ? 12.92f * c : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f; }
+// R8G8B8A8_SRGB load (sRGB EOTF of the Vulkan specification): what the blender reads back from the attachment
+__device__ __forceinline__ float srgb_decode(unsigned b)
+{
+	const float c = (float) b / 255.0f;
+	return c <= 0.04045f ? c / 12.92f : powf((c + 0.055f) / 1.055f, 2.4f);
+}
 __device__ __forceinline__ unsigned unorm8(float c) { return (unsigned) (clampf_(c, 0.0f, 1.0f) * 255.0f + 0.5f); }
 
 
@@ -143,22 +152,27 @@ __global__ void __launch_bounds__(256) ctab_kernel(const uchar4 *__restrict__ tf
 	ctab[idx] = e;
 }
 
+constexpr int kTraceWords = 8;
 #ifndef VKV_RC_MIN_CTAS
 #define VKV_RC_MIN_CTAS 16
 #endif
 // A CTA is two warps = a 16x4 pixel tile; small CTAs keep the register file busy while long rays finish.
 // grid = (CTAs per tile in x, CTAs per tile in y, tiles of this launch).
 // OTF: the volume has no gradient map; gradients come from gradient_otf (always instantiated with COUNT).
-template <int SKIP, bool EXACT, bool COUNT, bool OTF = false>
-__global__ void __launch_bounds__(64, OTF ? 8 : VKV_RC_MIN_CTAS) raycast_kernel(const __grid_constant__ RayParams P)
+// TRACE: debug instantiation (VKV_RC_TRACE) that also records the per-warp timeline.
+// LOAD: blend and depth-test over the existing contents of the target (vkv_render_options::load_framebuffer) instead of the
+// render-pass clear, and honour depth_attachment; these instantiations always count (COUNT).
+template <int SKIP, bool EXACT, bool COUNT, bool OTF = false, bool TRACE = false, bool LOAD = false>
+__global__ void __launch_bounds__(64, (OTF || LOAD) ? 8 : VKV_RC_MIN_CTAS) raycast_kernel(const __grid_constant__ RayParams P)
 {
 	__shared__ unsigned long long s_cnt[2][4];
 
 	// CTA -> tile -> pixel
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	unsigned long long t_start = 0;
-	unsigned           n_iter  = 0;
-	if (P.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+	unsigned           n_iter  = 0, tr_lanes = 0, tr_d = 0, tr_r = 0, tr_mixed = 0;
+	long long          tc_top = 0, tc_req = 0, tc_d = 0, tc_v = 0, tc_mark = 0;        // trace: cycles per loop section
+	if (TRACE) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
 	// Tiles are issued from the middle of this launch's tile list outwards (m, m-1, m+1, m-2, ...): the long rays sit
 	// near the image centre, so their latency chains start at t = 0 and the cheap border tiles fill the tail.
 	const int seq        = P.seq_base + (int) blockIdx.z;
@@ -175,7 +189,7 @@ __global__ void __launch_bounds__(64, OTF ? 8 : VKV_RC_MIN_CTAS) raycast_kernel(
 	// CTA-uniform rejection against the projected bounds of the unit cube: such pixels keep the clear colour
 	// (0,0,0,1) (render_pipeline.cpp:38) and depth 0.
 	if (tx0 > P.bbox[2] || tx0 + 15 < P.bbox[0] || ty0 > P.bbox[3] || ty0 + 3 < P.bbox[1]) {
-		if (in_frame) {
+		if (in_frame && !LOAD) {
 			reinterpret_cast<unsigned *>(P.rgba8)[p] = 0xff000000u;
 			if (P.depth) P.depth[p] = 0.0f;
 		}
@@ -185,8 +199,11 @@ __global__ void __launch_bounds__(64, OTF ? 8 : VKV_RC_MIN_CTAS) raycast_kernel(
 	unsigned n_vol = 0, n_dist = 0, n_empty = 0, covered = 0;
 	float    out[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 	float    frag_depth = 0.0f;
+	float    dst_depth  = 0.0f;        // what the depth attachment holds (LOAD) or the clear value
+	bool     discarded  = false;
 
 	if (in_frame) {
+		if (LOAD && P.depth) dst_depth = P.depth[p];
 		// ---- analytic ray entry (replaces both vertex shaders + rasteriser) ----
 		// (1) conservative fp32 rejection (approximate divisions; only ever used to say "certainly misses")
 		bool maybe = px >= P.bbox[0] && px <= P.bbox[2] && py >= P.bbox[1] && py <= P.bbox[3];
@@ -235,7 +252,20 @@ __global__ void __launch_bounds__(64, OTF ? 8 : VKV_RC_MIN_CTAS) raycast_kernel(
 			}
 		}
 
-		if (covered) {
+		float position[4] = {0.0f, 0.0f, 0.5f, 1.0f}, frag_depth_front = 0.0f;
+		if (LOAD && covered && P.depth_attachment) {
+			// the `position` varying = gl_Position of the entry point (volume_render_clipped.vert:58-62), then :122-136
+			const double pm[3] = {(double) entry[0] - 0.5, (double) entry[1] - 0.5, (double) entry[2] - 0.5};
+			position[0] = (float) (P.pvm_x[0] * pm[0] + P.pvm_x[1] * pm[1] + P.pvm_x[2] * pm[2] + P.pvm_x[3]);
+			position[1] = (float) (P.pvm_y[0] * pm[0] + P.pvm_y[1] * pm[1] + P.pvm_y[2] * pm[2] + P.pvm_y[3]);
+			position[2] = (float) (P.pvm_z[0] * pm[0] + P.pvm_z[1] * pm[1] + P.pvm_z[2] * pm[2] + P.pvm_z[3]);
+			position[3] = (float) (P.pvm_w[0] * pm[0] + P.pvm_w[1] * pm[1] + P.pvm_w[2] * pm[2] + P.pvm_w[3]);
+			frag_depth_front = position[2] / position[3];
+			if (dst_depth > frag_depth_front) discarded = true;        // REVERSE_DEPTH: the front face is behind the scene
+			else frag_depth = dst_depth;
+		}
+
+		if (covered && !discarded) {
 			// ---- fragment shader main() (volume_render.frag:117-336) ----
 			const float dv[3] = {entry[0] - P.cam_pos_tex[0], entry[1] - P.cam_pos_tex[1], entry[2] - P.cam_pos_tex[2]};
 			const float dl    = sqrtf((dv[0] * dv[0] + dv[1] * dv[1]) + dv[2] * dv[2]);
@@ -248,9 +278,29 @@ __global__ void __launch_bounds__(64, OTF ? 8 : VKV_RC_MIN_CTAS) raycast_kernel(
 				t2[k]             = fmaxf(t_min, t_max);
 			}
 			const float t_far       = fminf(fminf(t2[0], t2[1]), t2[2]);
-			const float ray_exit[3] = {t_far * dir[0] + entry[0], t_far * dir[1] + entry[1], t_far * dir[2] + entry[2]};
+			float       ray_exit[3] = {t_far * dir[0] + entry[0], t_far * dir[1] + entry[1], t_far * dir[2] + entry[2]};
 			const float ev[3]       = {entry[0] - ray_exit[0], entry[1] - ray_exit[1], entry[2] - ray_exit[2]};
-			const float ray_distance = sqrtf((ev[0] * ev[0] + ev[1] * ev[1]) + ev[2] * ev[2]);
+			float       ray_distance = sqrtf((ev[0] * ev[0] + ev[1] * ev[1]) + ev[2] * ev[2]);
+			if (LOAD && P.depth_attachment) {
+				// :151-165 — stop the ray where it meets the depth buffer
+				const float cad[4] = {position[0] * dst_depth / frag_depth_front, position[1] * dst_depth / frag_depth_front,
+				                      position[2] * dst_depth / frag_depth_front, position[3]};
+				float pad[4], pmv[3];
+#pragma unroll
+				for (int r = 0; r < 4; ++r) pad[r] = ((P.vpi[0 + r] * cad[0] + P.vpi[4 + r] * cad[1]) + P.vpi[8 + r] * cad[2]) + P.vpi[12 + r] * cad[3];
+				const float pw = pad[3];
+#pragma unroll
+				for (int r = 0; r < 4; ++r) pad[r] = pad[r] / pw;
+#pragma unroll
+				for (int r = 0; r < 3; ++r) pmv[r] = ((P.mi[0 + r] * pad[0] + P.mi[4 + r] * pad[1]) + P.mi[8 + r] * pad[2]) + P.mi[12 + r] * pad[3];
+				const float hit[3] = {pmv[0] + 0.5f, pmv[1] + 0.5f, pmv[2] + 0.5f};
+				const float hv[3]  = {entry[0] - hit[0], entry[1] - hit[1], entry[2] - hit[2]};
+				const float hd     = sqrtf((hv[0] * hv[0] + hv[1] * hv[1]) + hv[2] * hv[2]);
+				if (hd < ray_distance) {
+					ray_exit[0] = hit[0]; ray_exit[1] = hit[1]; ray_exit[2] = hit[2];
+					ray_distance = hd;
+				}
+			}
 
 			if (P.test == VKV_TEST_RAY_ENTRY) {
 				out[0] = entry[0]; out[1] = entry[1]; out[2] = entry[2]; out[3] = 1.0f;
@@ -291,10 +341,11 @@ __global__ void __launch_bounds__(64, OTF ? 8 : VKV_RC_MIN_CTAS) raycast_kernel(
 					const float dim_inv[3] = {1.0f / P.dimf[0], 1.0f / P.dimf[1], 1.0f / P.dimf[2]};
 					// look-ahead cache of hardware-filtered samples i .. i+3: consecutive volume samples are the common case
 					// inside occupied regions, and one batch of independent fetches replaces four dependent round trips
-					int   pre_base = -0x40000000;
+					int      pre_base = -0x40000000;
 					float pre_v0 = 0.0f, pre_v1 = 0.0f, pre_v2 = 0.0f, pre_v3 = 0.0f, pre_g0 = 1.0f, pre_g1 = 1.0f, pre_g2 = 1.0f, pre_g3 = 1.0f;
 					for (int i = 0; i < n_steps;) {
 						++n_iter;
+						if (TRACE) tc_mark = clock64();
 						const float fi     = (float) i;
 						const float pos[3] = {entry[0] + fi * step[0], entry[1] + fi * step[1], entry[2] + fi * step[2]};
 						float    u[3];
@@ -310,9 +361,53 @@ __global__ void __launch_bounds__(64, OTF ? 8 : VKV_RC_MIN_CTAS) raycast_kernel(
 							idx     = ((unsigned) u_i[2] * (unsigned) P.dim_b[1] + (unsigned) u_i[1]) * (unsigned) P.dim_b[0] + (unsigned) u_i[0];
 							do_skip = !voxel_occupied && idx != idx_last;
 						}
+						// ---- memory requests of this iteration, issued before any result is consumed ----
+						// Every sampling lane keeps a batch of four hardware-filtered samples (steps pre_base .. pre_base + 3).  The
+						// batches of a warp are kept aligned: when one lane runs out, every sampling lane that has used part of its
+						// batch starts a new one, so the warp waits for one texture round trip per four iterations instead of one per
+						// iteration with its lanes out of phase.  (Fetching early returns the same value: positions depend on the step
+						// index alone.)  BLOCK mode is texture-throughput-bound rather than latency-bound (measured: alignment costs 10 %
+						// there and gains 10 % with the distance maps), so its lanes refill on their own.
+						if (TRACE) { const long long c = clock64(); tc_top += c - tc_mark; tc_mark = c; }
+						constexpr bool kLookAhead = !OTF && !EXACT;
+						unsigned       dist       = 0u;
+						int            k          = 0;
+						if (SKIP != VKV_SKIP_NONE && do_skip) dist = __ldg(Dm + idx);
+						bool any_refill = false;
+						if (kLookAhead) {
+							k                = i - pre_base;
+							const bool vmode = !do_skip;
+							const bool need  = vmode && (unsigned) k >= 4u;
+							any_refill       = __any_sync(__activemask(), need);
+							if (SKIP == VKV_SKIP_BLOCK ? need : (any_refill && vmode && k != 0)) {
+								pre_base = i;
+								k        = 0;
+								const float f1 = (float) (i + 1), f2 = (float) (i + 2), f3 = (float) (i + 3);
+								const float q1[3] = {entry[0] + f1 * step[0], entry[1] + f1 * step[1], entry[2] + f1 * step[2]};
+								const float q2[3] = {entry[0] + f2 * step[0], entry[1] + f2 * step[1], entry[2] + f2 * step[2]};
+								const float q3[3] = {entry[0] + f3 * step[0], entry[1] + f3 * step[1], entry[2] + f3 * step[2]};
+								pre_v0 = tex3D<float>(P.tex_v, pos[0], pos[1], pos[2]);
+								pre_v1 = tex3D<float>(P.tex_v, q1[0], q1[1], q1[2]);
+								pre_v2 = tex3D<float>(P.tex_v, q2[0], q2[1], q2[2]);
+								pre_v3 = tex3D<float>(P.tex_v, q3[0], q3[1], q3[2]);
+								if (P.use_gradient) {
+									pre_g0 = tex3D<float>(P.tex_g, pos[0], pos[1], pos[2]);
+									pre_g1 = tex3D<float>(P.tex_g, q1[0], q1[1], q1[2]);
+									pre_g2 = tex3D<float>(P.tex_g, q2[0], q2[1], q2[2]);
+									pre_g3 = tex3D<float>(P.tex_g, q3[0], q3[1], q3[2]);
+								}
+							}
+						}
+						if (TRACE) {
+							{ const long long c = clock64(); tc_req += c - tc_mark; tc_mark = c; }
+							const unsigned am = __activemask();
+							tr_lanes += __popc(am);
+							tr_d += __any_sync(am, do_skip) ? 1u : 0u;
+							tr_r += any_refill ? 1u : 0u;
+							tr_mixed += (__any_sync(am, do_skip) && __any_sync(am, !do_skip)) ? 1u : 0u;
+						}
 						if (SKIP != VKV_SKIP_NONE && do_skip) {
 							++n_dist;
-							const unsigned dist = __ldg(Dm + idx);
 							if (dist > 0u) {
 								float       dxyz[3];
 								const float fd = (float) dist, omfd = 1.0f - fd;        // exact (dist <= 255)
@@ -331,7 +426,9 @@ __global__ void __launch_bounds__(64, OTF ? 8 : VKV_RC_MIN_CTAS) raycast_kernel(
 								idx_last       = idx;
 								i              = max(i - back, i_min);
 							}
+							if (TRACE) { const long long c = clock64(); tc_d += c - tc_mark; tc_mark = c; }
 						} else {
+							if (TRACE) tc_mark = clock64();
 							++n_vol;
 							float intensity, gradient = 1.0f;
 							if (OTF) {
@@ -342,25 +439,6 @@ __global__ void __launch_bounds__(64, OTF ? 8 : VKV_RC_MIN_CTAS) raycast_kernel(
 								intensity = sample_exact(P.V, P.dim, pos[0], pos[1], pos[2]);
 								if (P.use_gradient) gradient = sample_exact(P.G, P.dim, pos[0], pos[1], pos[2]);
 							} else {
-								int k = i - pre_base;
-								if ((unsigned) k >= 4u) {
-									pre_base = i;
-									k        = 0;
-									const float f1 = (float) (i + 1), f2 = (float) (i + 2), f3 = (float) (i + 3);
-									const float q1[3] = {entry[0] + f1 * step[0], entry[1] + f1 * step[1], entry[2] + f1 * step[2]};
-									const float q2[3] = {entry[0] + f2 * step[0], entry[1] + f2 * step[1], entry[2] + f2 * step[2]};
-									const float q3[3] = {entry[0] + f3 * step[0], entry[1] + f3 * step[1], entry[2] + f3 * step[2]};
-									pre_v0 = tex3D<float>(P.tex_v, pos[0], pos[1], pos[2]);
-									pre_v1 = tex3D<float>(P.tex_v, q1[0], q1[1], q1[2]);
-									pre_v2 = tex3D<float>(P.tex_v, q2[0], q2[1], q2[2]);
-									pre_v3 = tex3D<float>(P.tex_v, q3[0], q3[1], q3[2]);
-									if (P.use_gradient) {
-										pre_g0 = tex3D<float>(P.tex_g, pos[0], pos[1], pos[2]);
-										pre_g1 = tex3D<float>(P.tex_g, q1[0], q1[1], q1[2]);
-										pre_g2 = tex3D<float>(P.tex_g, q2[0], q2[1], q2[2]);
-										pre_g3 = tex3D<float>(P.tex_g, q3[0], q3[1], q3[2]);
-									}
-								}
 								intensity = pick4_(k, pre_v0, pre_v1, pre_v2, pre_v3);
 								if (P.use_gradient) gradient = pick4_(k, pre_g0, pre_g1, pre_g2, pre_g3);
 							}
@@ -380,6 +458,7 @@ __global__ void __launch_bounds__(64, OTF ? 8 : VKV_RC_MIN_CTAS) raycast_kernel(
 							}
 							++i;
 							if (SKIP != VKV_SKIP_NONE) i_min = i;
+							if (TRACE) { const long long c = clock64(); tc_v += c - tc_mark; tc_mark = c; }
 						}
 					}
 					if (P.depth && out[3] > 0.0f && i_first_hit < n_steps) {
@@ -399,23 +478,46 @@ __global__ void __launch_bounds__(64, OTF ? 8 : VKV_RC_MIN_CTAS) raycast_kernel(
 				}
 			}
 		}
-		// blend with the clear colour (0,0,0,1): rgb = src.rgb + dst.rgb*(1-src.a), a = src.a*(1-src.a) + dst.a*0;
-		// R8G8B8A8_SRGB store.  Uncovered pixels keep the clear colour.
-		unsigned packed = 0xff000000u;
-		if (covered)
-			packed = unorm8(srgb_encode(clampf_(out[0], 0.0f, 1.0f))) | (unorm8(srgb_encode(clampf_(out[1], 0.0f, 1.0f))) << 8) |
-			         (unorm8(srgb_encode(clampf_(out[2], 0.0f, 1.0f))) << 16) | (unorm8(out[3] * (1.0f - out[3])) << 24);
-		reinterpret_cast<unsigned *>(P.rgba8)[p] = packed;
-		if (P.depth) P.depth[p] = frag_depth;
+		// depth test GREATER_OR_EQUAL + depth write, then blend: rgb = src.rgb + dst.rgb*(1-src.a), a = src.a*(1-src.a) + dst.a*0
+		// (volume_render_subpass.cpp:176-190); R8G8B8A8_SRGB store.  Without LOAD the destination is the clear colour
+		// (0,0,0,1) / depth 0 and uncovered pixels are written with it.
+		const bool pass = covered && !discarded && frag_depth >= dst_depth;
+		if (!LOAD) {
+			unsigned packed = 0xff000000u;
+			if (pass)
+				packed = unorm8(srgb_encode(clampf_(out[0], 0.0f, 1.0f))) | (unorm8(srgb_encode(clampf_(out[1], 0.0f, 1.0f))) << 8) |
+				         (unorm8(srgb_encode(clampf_(out[2], 0.0f, 1.0f))) << 16) | (unorm8(out[3] * (1.0f - out[3])) << 24);
+			reinterpret_cast<unsigned *>(P.rgba8)[p] = packed;
+			if (P.depth) P.depth[p] = pass ? frag_depth : 0.0f;
+		} else if (pass) {
+			const unsigned d8 = reinterpret_cast<const unsigned *>(P.rgba8)[p];
+			const float    sa = clampf_(out[3], 0.0f, 1.0f), om = 1.0f - sa;
+			const float    r  = clampf_(out[0], 0.0f, 1.0f) + srgb_decode(d8 & 0xffu) * om;
+			const float    g  = clampf_(out[1], 0.0f, 1.0f) + srgb_decode((d8 >> 8) & 0xffu) * om;
+			const float    b  = clampf_(out[2], 0.0f, 1.0f) + srgb_decode((d8 >> 16) & 0xffu) * om;
+			reinterpret_cast<unsigned *>(P.rgba8)[p] = unorm8(srgb_encode(clampf_(r, 0.0f, 1.0f))) | (unorm8(srgb_encode(clampf_(g, 0.0f, 1.0f))) << 8) |
+			                                           (unorm8(srgb_encode(clampf_(b, 0.0f, 1.0f))) << 16) | (unorm8(sa * om) << 24);
+			if (P.depth) P.depth[p] = frag_depth;
+		}
 	}
 
-	if (P.trace) {
+	if (TRACE) {
 		unsigned long long t_end;
 		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+		// per-warp record (kTraceWords u64): start ns, end ns, {iterations | with a skip-map load | with a texture batch | with both kinds
+		// of lane | mean live lanes}, then cycles of the longest-lived lanes in: loop head, request issue, skip branch, sample branch
 		const unsigned it_max = __reduce_max_sync(0xffffffffu, n_iter);
+		const unsigned m_d = __reduce_max_sync(0xffffffffu, tr_d), m_r = __reduce_max_sync(0xffffffffu, tr_r), m_m = __reduce_max_sync(0xffffffffu, tr_mixed);
+		const unsigned m_l = __reduce_max_sync(0xffffffffu, tr_lanes);
+		const unsigned c_top = __reduce_max_sync(0xffffffffu, (unsigned) tc_top), c_req = __reduce_max_sync(0xffffffffu, (unsigned) tc_req);
+		const unsigned c_d = __reduce_max_sync(0xffffffffu, (unsigned) tc_d), c_v = __reduce_max_sync(0xffffffffu, (unsigned) tc_v);
 		if (lane == 0) {
 			const size_t w = (((size_t) blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 2 + warp;
-			P.trace[w * 3 + 0] = t_start; P.trace[w * 3 + 1] = t_end; P.trace[w * 3 + 2] = it_max;
+			unsigned long long *t = P.trace + w * kTraceWords;
+			t[0] = t_start; t[1] = t_end;
+			t[2] = (unsigned long long) (it_max & 0xfffu) | ((unsigned long long) (m_d & 0xfffu) << 12) | ((unsigned long long) (m_r & 0xfffu) << 24) |
+			       ((unsigned long long) (m_m & 0xfffu) << 36) | ((unsigned long long) (it_max ? m_l / it_max : 0u) << 48);
+			t[3] = c_top; t[4] = c_req; t[5] = c_d; t[6] = c_v; t[7] = 0;
 		}
 	}
 	if (COUNT) {
@@ -539,7 +641,8 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 		for (int i = 0; i < 16; ++i) { pr[i] = cam->proj[i]; vw[i] = cam->view[i]; md[i] = cam->model[i]; }
 		mul_mm(pr, vw, pv);
 		mul_mm(pv, md, pvm);
-		for (int c = 0; c < 4; ++c) { P.pvm_z[c] = pvm[c * 4 + 2]; P.pvm_w[c] = pvm[c * 4 + 3]; }
+		for (int c = 0; c < 4; ++c) { P.pvm_x[c] = pvm[c * 4 + 0]; P.pvm_y[c] = pvm[c * 4 + 1]; P.pvm_z[c] = pvm[c * 4 + 2]; P.pvm_w[c] = pvm[c * 4 + 3]; }
+		for (int i = 0; i < 16; ++i) { P.vpi[i] = cam->view_proj_inv[i]; P.mi[i] = cam->model_inv[i]; }
 	}
 	P.dim_max             = (int) std::max(vol->dim[0], std::max(vol->dim[1], vol->dim[2]));
 	P.sampling_factor     = tfu->sampling_factor;
@@ -549,6 +652,7 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 	P.use_gradient        = tfu->use_gradient ? 1 : 0;
 	P.ert                 = opt->early_ray_termination ? 1 : 0;
 	P.test                = opt->test;
+	P.depth_attachment    = opt->depth_attachment ? 1 : 0;
 	P.width = width; P.height = height;
 	P.tile_w = tile_w; P.tile_h = tile_h;
 	P.tiles_x         = (width + tile_w - 1) / tile_w;
@@ -583,14 +687,15 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 	const bool exact = opt->filter == VKV_FILTER_EXACT;
 	// on-the-fly gradients (volume created without a gradient map); the variant always counts, into scratch if need be
 	const bool otf = P.use_gradient && !vol->precomputed_gradient;
-	if (otf && !P.counts) P.counts = reinterpret_cast<unsigned long long *>(vol->d_counts_scratch);
+	const bool load = opt->load_framebuffer != 0;
+	if ((otf || load) && !P.counts) P.counts = reinterpret_cast<unsigned long long *>(vol->d_counts_scratch);
 	// gridDim.z is limited to 65535: launch the tile list in chunks (one chunk up to 134 Mpixel with 64x32 tiles)
 	// debug: VKV_RC_TRACE=<file> dumps per-warp {start ns, end ns, loop iterations} of this launch (synchronous; never set in production)
 	const char         *trace_path = getenv("VKV_RC_TRACE");
 	unsigned long long *d_trace    = nullptr;
 	size_t              trace_n    = 0;
 	if (trace_path && my_tiles <= 65535) {
-		trace_n = (size_t) my_tiles * (tile_w / 16) * (tile_h / 4) * 2 * 3;
+		trace_n = (size_t) my_tiles * (tile_w / 16) * (tile_h / 4) * 2 * kTraceWords;
 		VKV_CUDA_CHECK(cudaMalloc(&d_trace, trace_n * sizeof(unsigned long long)));
 		VKV_CUDA_CHECK(cudaMemsetAsync(d_trace, 0, trace_n * sizeof(unsigned long long), s));
 		P.trace = d_trace;
@@ -600,7 +705,12 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 		const dim3 grid((unsigned) (tile_w / 16), (unsigned) (tile_h / 4), (unsigned) std::min(65535, my_tiles - base));
 #define VKV_RC(SK)                                                                      \
 	do {                                                                                \
-		if (otf && exact) raycast_kernel<SK, true, true, true><<<grid, 64, 0, s>>>(P);   \
+		if (load && otf && exact) raycast_kernel<SK, true, true, true, false, true><<<grid, 64, 0, s>>>(P);  \
+		else if (load && otf) raycast_kernel<SK, false, true, true, false, true><<<grid, 64, 0, s>>>(P);     \
+		else if (load && exact) raycast_kernel<SK, true, true, false, false, true><<<grid, 64, 0, s>>>(P);   \
+		else if (load) raycast_kernel<SK, false, true, false, false, true><<<grid, 64, 0, s>>>(P);           \
+		else if (d_trace && !otf && !exact) raycast_kernel<SK, false, false, false, true><<<grid, 64, 0, s>>>(P); \
+		else if (otf && exact) raycast_kernel<SK, true, true, true><<<grid, 64, 0, s>>>(P);   \
 		else if (otf) raycast_kernel<SK, false, true, true><<<grid, 64, 0, s>>>(P);      \
 		else if (exact && counts) raycast_kernel<SK, true, true><<<grid, 64, 0, s>>>(P);      \
 		else if (exact) raycast_kernel<SK, true, false><<<grid, 64, 0, s>>>(P);          \

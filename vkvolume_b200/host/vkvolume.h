@@ -316,6 +316,11 @@ class VolumeRenderSubpass {
 	void prepare();                                    // allocates the headless render target
 	void draw(CommandBuffer &command_buffer);          // src/volume_render_subpass.cpp:159-294
 	uint8_t *get_framebuffer() const { return framebuffer; }        // device pointer, RGBA8, sRGB-encoded RGB, row 0 on top
+	float   *get_depth_buffer() const { return depth_buffer; }      // device pointer, float per pixel, reverse-Z (0 = far)
+	// The reference draws the volumes after a geometry subpass whose colour and depth are already in the render target
+	// (src/volume_render.cpp:344-350).  Headless: the caller fills get_framebuffer() / get_depth_buffer() and says so here;
+	// draw() then composites over them (and, with options.depth_attachment, clips the rays at that depth).
+	void set_background_loaded(bool loaded) { background_loaded = loaded; }
 	std::vector<uint8_t> read_framebuffer(CommandBuffer &command_buffer);
 	vkv_sample_counts    read_sample_counts(CommandBuffer &command_buffer);
 	void                 reset_sample_counts(CommandBuffer &command_buffer);
@@ -326,8 +331,10 @@ class VolumeRenderSubpass {
 	std::vector<Volume *> volumes;
 	Options               options;
 	uint32_t              width, height;
-	uint8_t              *framebuffer = nullptr;
-	vkv_sample_counts    *counts      = nullptr;
+	uint8_t              *framebuffer  = nullptr;
+	float                *depth_buffer = nullptr;
+	vkv_sample_counts    *counts       = nullptr;
+	bool                  background_loaded = false;
 };
 
 // ~ the orchestration half of VolumeRender (src/volume_render.cpp): everything except Vulkan bring-up and the GUI.
@@ -368,12 +375,14 @@ namespace vkvolume {
 inline VolumeRenderSubpass::~VolumeRenderSubpass()
 {
 	cudaFree(framebuffer);
+	cudaFree(depth_buffer);
 	cudaFree(counts);
 }
 
 inline void VolumeRenderSubpass::prepare()
 {
 	if (!framebuffer && cudaMalloc((void **) &framebuffer, (size_t) width * height * 4) != cudaSuccess) throw std::runtime_error("cudaMalloc(framebuffer) failed");
+	if (!depth_buffer && cudaMalloc((void **) &depth_buffer, (size_t) width * height * sizeof(float)) != cudaSuccess) throw std::runtime_error("cudaMalloc(depth buffer) failed");
 	if (!counts && cudaMalloc((void **) &counts, sizeof(vkv_sample_counts)) != cudaSuccess) throw std::runtime_error("cudaMalloc(counts) failed");
 	cudaMemset(counts, 0, sizeof(vkv_sample_counts));
 }
@@ -381,6 +390,10 @@ inline void VolumeRenderSubpass::prepare()
 inline void VolumeRenderSubpass::draw(CommandBuffer &command_buffer)
 {
 	if (!framebuffer) prepare();
+	if (options.depth_attachment && !background_loaded) throw std::runtime_error("depth_attachment: fill the depth buffer and call set_background_loaded(true) first");
+	// the first volume starts from the render-pass clear unless a background was loaded; every later one blends and
+	// depth-tests over what is already in the target (the loop of src/volume_render_subpass.cpp:219-293)
+	bool load = background_loaded;
 	for (auto volume : volumes) {
 		TransferFunctionUniform tfu = volume->get_transfer_function_uniform();
 		Node                    default_node;
@@ -393,9 +406,10 @@ inline void VolumeRenderSubpass::draw(CommandBuffer &command_buffer)
 		RayCastUniform ray_cast_uniform;
 		check(vkv_make_uniforms(volume->handle(), &cd, volume->get_image_transform(), options.clip_distance, &camera_uniform, &ray_cast_uniform));
 		vkv_render_options ro{(int) options.skipping_type, options.clip_distance, options.early_ray_termination ? 1 : 0,
-		                      options.depth_attachment ? 1 : 0, (int) options.test, VKV_FILTER_HARDWARE};
-		check(vkv_render(volume->handle(), &camera_uniform, &ray_cast_uniform, &tfu, &ro, (int) width, (int) height, framebuffer, nullptr, counts,
+		                      options.depth_attachment ? 1 : 0, (int) options.test, VKV_FILTER_HARDWARE, load ? 1 : 0};
+		check(vkv_render(volume->handle(), &camera_uniform, &ray_cast_uniform, &tfu, &ro, (int) width, (int) height, framebuffer, depth_buffer, counts,
 		                 command_buffer.stream));
+		load = true;
 	}
 }
 
