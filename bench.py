@@ -10,11 +10,15 @@ orbits the volume, one view per step).  `value` times the frame with everything 
 HBM; `e2e` goes through vkv_render_to_host (uniforms from host structs, RGBA8 frame and
 counters copied back to pinned host memory inside the timed region).
 
-N > 1 (launched under torchrun, one rank per GPU, NCCL): every rank holds a full replica, the
-frame is cut into 64x32 tiles dealt round-robin to the ranks, and each rank's kernel stores its
-tiles straight into rank 0's framebuffer through a CUDA-IPC peer mapping (the gather is fused
-into the ray caster's epilogue); the TF-change rebuild shards the O(N) occupancy pass by
-z-slabs and all-gathers the slab rows of the occupancy map over NCCL.
+N > 1 (launched under torchrun, one rank per GPU, NCCL): every rank holds a full replica and
+stores its pixels straight into rank 0's HBM through a CUDA-IPC peer mapping (the gather is fused
+into the ray caster's epilogue, no collective on the data path).  Two decompositions
+(--parallelism): `frames` — a step is N consecutive views of the orbit, one per rank, each landing
+in its slot of a frame ring on rank 0 (independent units, weak scaling; the default for the
+1080p-class workloads, whose 0.13 ms frame is bound by its longest rays and cannot be cut N ways);
+`tiles` — one frame cut into 64x32 tiles dealt round-robin to the ranks (strong scaling; the
+default for the 8K workloads c5 / c5s, BASELINE.json config 5).  The TF-change rebuild shards the
+O(N) occupancy pass by z-slabs and all-gathers the slab rows of the occupancy map over NCCL.
 
 --impl reference times the reference algorithm on the host CPU cores (the oracle port: the
 reference has no CPU path and cannot be built here) on the same config.
@@ -142,6 +146,7 @@ def run_native(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")        # rank 0's stdout carries the one JSON line and nothing else
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -150,6 +155,11 @@ def run_native(args):
     W, H, D = wl["dim"]
     FW, FH = wl["frame"]
     K, Wm = args.steps, args.warmup
+    par = args.parallelism
+    if par == "auto":
+        par = "tiles" if FW * FH >= 16_000_000 else "frames"
+    frames_mode = world > 1 and par == "frames"
+    slots = world if frames_mode else 1        # frames held in rank 0's HBM per step
 
     ctx = capi.Context(local_rank)
     vol = capi.Volume(ctx, W, H, D, block_size=4)
@@ -243,9 +253,11 @@ def run_native(args):
     it = scene.image_transform(wl["voxel"], wl["dim"], wl["axis_angle"])
     ropt = RenderOptions(skipping_type=skip, clip_distance=wl["clip"], early_ray_termination=1)
     fb_ptr, peer_ptr = None, None
+    frame_bytes = FW * FH * 4
     if rank == 0:
-        fb = torch.zeros((FH, FW, 4), dtype=torch.uint8, device=dev)
-        fb_ptr = fb.data_ptr()
+        fb_all = torch.zeros((slots, FH, FW, 4), dtype=torch.uint8, device=dev)
+        fb = fb_all[0]
+        fb_ptr = fb_all.data_ptr()
     if world > 1:
         import ctypes as C
         handle = [None]
@@ -259,7 +271,7 @@ def run_native(args):
             p = C.c_void_p()
             capi.check(capi.lib().vkv_ipc_open(hbuf, C.byref(p)))
             peer_ptr = p.value
-            fb_ptr = peer_ptr
+            fb_ptr = peer_ptr + (rank * frame_bytes if frames_mode else 0)        # this rank's slot of rank 0's frame ring
     counts_t = torch.zeros(4, dtype=torch.int64, device=dev)
 
     cams = [scene.look_at_camera(orbit_eye(k, 72, wl), aspect=FW / FH) for k in range(72)]        # synthetic inputs: the camera path
@@ -268,6 +280,10 @@ def run_native(args):
         return vol.make_uniforms(cams[step % 72], it, wl["clip"])        # host maths of VolumeRenderSubpass::draw (C ABI call)
 
     def render_step(step, counts_ptr):
+        if frames_mode:        # N consecutive views per step, one per rank, each into its slot on rank 0
+            cu, ru = uniforms(step * world + rank)
+            vol.render(cu, ru, tfu, ropt, FW, FH, fb_ptr, 0, counts_ptr, stream)
+            return
         cu, ru = uniforms(step)
         if world == 1:
             vol.render(cu, ru, tfu, ropt, FW, FH, fb_ptr, 0, counts_ptr, stream)
@@ -288,16 +304,18 @@ def run_native(args):
     # stores must equal rank 0's own full-frame render of the same view, byte for byte
     tiles_match = None
     if world > 1:
-        fb.zero_() if rank == 0 else None
+        fb_all.zero_() if rank == 0 else None
         barrier()
         render_step(0, 0)
         barrier()
         if rank == 0:
             full = torch.zeros_like(fb)
-            cu0, ru0 = uniforms(0)
-            vol.render(cu0, ru0, tfu, ropt, FW, FH, full.data_ptr(), 0, 0, stream)
-            torch.cuda.synchronize()
-            tiles_match = bool(torch.equal(full, fb))
+            tiles_match = True
+            for r in range(slots):        # frames mode: slot r holds view r, rendered by rank r
+                cu0, ru0 = uniforms(r)
+                vol.render(cu0, ru0, tfu, ropt, FW, FH, full.data_ptr(), 0, 0, stream)
+                torch.cuda.synchronize()
+                tiles_match = tiles_match and bool(torch.equal(full, fb_all[r]))
             del full
         barrier()
     sampler = ClockSampler(local_rank)
@@ -319,8 +337,11 @@ def run_native(args):
     sampler.join()
     step_ms = torch.tensor([a.elapsed_time(b) for a, b in zip(starts, stops)], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)        # a frame is done when the slowest rank's tiles are
+        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)        # a step is done when the slowest rank is
         dist.all_reduce(counts_t)
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt.item())        # whole job
     total_ms = float(step_ms.sum().item())
     n_vol, n_dist, n_empty, n_cov = [int(x) for x in counts_t.tolist()]
     samples = n_vol + n_dist
@@ -375,7 +396,7 @@ def run_native(args):
     else:
         # multi-GPU e2e: frame lands in rank 0's HBM through the peer stores; rank 0 then copies it to pinned host memory
         if rank == 0:
-            host_fb = torch.empty((FH, FW, 4), dtype=torch.uint8).pin_memory()
+            host_fb = torch.empty((slots, FH, FW, 4), dtype=torch.uint8).pin_memory()
         ke = max(10, K // 4)
         counts_t.zero_()
         barrier()
@@ -384,20 +405,21 @@ def run_native(args):
             render_step(s, counts_t.data_ptr())
             barrier()
             if rank == 0:
-                host_fb.copy_(fb, non_blocking=False)
+                host_fb.copy_(fb_all, non_blocking=False)
         t1 = time.perf_counter()
         dist.all_reduce(counts_t)
         c = counts_t.tolist()
         tt = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": (c[0] + c[1]) / tt.item() / 1e6, "unit": UNIT, "h2d_bytes_per_step": 480 * world, "d2h_bytes_per_step": FW * FH * 4,
-               "ms_per_frame": tt.item() * 1e3 / ke, "steps": ke,
-               "note": "tiles rendered on all ranks with peer stores into rank 0, barrier, rank 0 copies the frame to pinned host memory"}
+        e2e = {"value": (c[0] + c[1]) / tt.item() / 1e6, "unit": UNIT, "h2d_bytes_per_step": 480 * world, "d2h_bytes_per_step": slots * FW * FH * 4,
+               "ms_per_frame": tt.item() * 1e3 / ke / slots, "ms_per_step": tt.item() * 1e3 / ke, "steps": ke,
+               "note": ("one view per rank with peer stores into rank 0's frame ring" if frames_mode else "tiles rendered on all ranks with peer stores into rank 0") +
+                       ", barrier, rank 0 copies the frame(s) to pinned host memory"}
 
     # ---- roofline --------------------------------------------------------------------------------------------------
     hbm_peak, peak_src = measured_peaks()
     gamma = 1 if use_g else 0
-    texel_bytes_per_step = (n_vol * (8 * (1 + gamma) + 4) + n_dist) / K / max(world, 1)
+    texel_bytes_per_step = (n_vol * (8 * (1 + gamma) + 4) + n_dist) / K / max(world, 1)        # per launch: one frame (frames) or one rank's tiles
     tex_peak = None
     if rank == 0:
         try:
@@ -441,14 +463,17 @@ def run_native(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "u8 voxels / f32 march",
+            "higher_is_better": True, "scaling": "strong" if (world > 1 and not frames_mode) else "weak", "vs_baseline": None, "dtype": "u8 voxels / f32 march",
             "data": "synthetic", "impl": "native",
             "config": {"workload": wl["name"], "volume": [W, H, D], "frame": [FW, FH], "block_size": 4, "ess": ["none", "block", "distance", "anisotropic"][skip],
                        "ert": True, "tf": wl["tf"], "views": "72-view orbit, one view per step",
                        "l2": "256 MiB flush write between timed steps (untimed); volume 342 MB > 126 MB L2" if args.workload == "c2" else "256 MiB flush write between timed steps (untimed)",
-                       "parallelism": f"image tiles {TILE_W}x{TILE_H} round-robin over {world} ranks, peer stores into rank 0" if world > 1 else "single GPU"},
-            "ms_per_frame": ms_per_step, "samples_per_frame": samples / K, "volume_samples_per_frame": n_vol / K,
-            "distance_samples_per_frame": n_dist / K, "covered_pixels_per_frame": n_cov / K, "mpixels_per_s": FW * FH / (ms_per_step * 1e-3) / 1e6,
+                       "parallelism": (f"frames: a step is {world} consecutive orbit views, one per rank, each stored into its slot of rank 0's frame ring through peer stores"
+                                       if frames_mode else f"image tiles {TILE_W}x{TILE_H} round-robin over {world} ranks, peer stores into rank 0") if world > 1 else "single GPU",
+                       "frames_per_step": slots},
+            "ms_per_frame": ms_per_step, "samples_per_frame": samples / K / slots, "volume_samples_per_frame": n_vol / K / slots,
+            "distance_samples_per_frame": n_dist / K / slots, "covered_pixels_per_frame": n_cov / K / slots,
+            "mpixels_per_s": slots * FW * FH / (ms_per_step * 1e-3) / 1e6,
             "ess_rebuild_ms": {"median": float(np.median(rebuild_ms)), "mean": float(np.mean(rebuild_ms)), "p95": float(np.percentile(rebuild_ms, 95)),
                                "changes": n_changes, "stages": stage_ms, "sharded_z_slabs": world > 1},
             "occupied_voxels": occupied, "occupied_percent": 100.0 * occupied / N_vox,
@@ -583,6 +608,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--parallelism", default="auto", choices=["auto", "tiles", "frames"], help="N > 1: one view per rank (weak) or one frame cut into tiles (strong)")
     ap.add_argument("--tf-changes", type=int, default=100)
     ap.add_argument("--quick", action="store_true", help="skip the per-mode table")
     ap.add_argument("--no-cpu-baseline", action="store_true")
