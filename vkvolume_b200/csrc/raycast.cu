@@ -51,6 +51,7 @@ struct RayParams {
 	float  vpi[16], mi[16];         // view_proj_inv and model_inv in fp32, column-major (depth-buffer intersection)
 	int    width, height;
 	int    tile_w, tile_h, tiles_x, tile_first, tile_stride, my_tiles, seq_base;
+	unsigned tiles_x_magic;         // floor(2^32 / tiles_x) + 1: tile / tiles_x == umulhi(tile, magic) for every tile of a frame; 0: divide
 	int    bbox[4];                 // conservative screen bounds (inclusive) of the unit cube: x0, y0, x1, y1
 	cudaTextureObject_t tex_v, tex_g;
 	const uint8_t *V, *G;
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(64, (OTF || LOAD) ? 8 : VKV_RC_MIN_CTAS) rayca
 	const int seq        = P.seq_base + (int) blockIdx.z;
 	const int local_tile = P.my_tiles / 2 + ((seq & 1) ? -((seq + 1) >> 1) : (seq >> 1));
 	const int tile       = P.tile_first + local_tile * P.tile_stride;
-	const int tile_y = tile / P.tiles_x, tile_x = tile - tile_y * P.tiles_x;
+	const int tile_y = P.tiles_x_magic ? (int) __umulhi((unsigned) tile, P.tiles_x_magic) : tile / P.tiles_x, tile_x = tile - tile_y * P.tiles_x;
 	const int tx0 = tile_x * P.tile_w + (int) blockIdx.x * 16;
 	const int ty0 = tile_y * P.tile_h + (int) blockIdx.y * 4;
 	const int px = tx0 + warp * 8 + (lane & 7);
@@ -484,9 +485,14 @@ __global__ void __launch_bounds__(64, (OTF || LOAD) ? 8 : VKV_RC_MIN_CTAS) rayca
 		const bool pass = covered && !discarded && frag_depth >= dst_depth;
 		if (!LOAD) {
 			unsigned packed = 0xff000000u;
-			if (pass)
-				packed = unorm8(srgb_encode(clampf_(out[0], 0.0f, 1.0f))) | (unorm8(srgb_encode(clampf_(out[1], 0.0f, 1.0f))) << 8) |
-				         (unorm8(srgb_encode(clampf_(out[2], 0.0f, 1.0f))) << 16) | (unorm8(out[3] * (1.0f - out[3])) << 24);
+			if (pass) {
+				// the built-in transfer function is grey (volume_component.cpp:250-261): one encode serves the three channels
+				const unsigned er = unorm8(srgb_encode(clampf_(out[0], 0.0f, 1.0f)));
+				const bool     grey = out[1] == out[0] && out[2] == out[0];
+				const unsigned eg = grey ? er : unorm8(srgb_encode(clampf_(out[1], 0.0f, 1.0f)));
+				const unsigned eb = grey ? er : unorm8(srgb_encode(clampf_(out[2], 0.0f, 1.0f)));
+				packed = er | (eg << 8) | (eb << 16) | (unorm8(out[3] * (1.0f - out[3])) << 24);
+			}
 			reinterpret_cast<unsigned *>(P.rgba8)[p] = packed;
 			if (P.depth) P.depth[p] = pass ? frag_depth : 0.0f;
 		} else if (pass) {
@@ -658,6 +664,8 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 	P.tiles_x         = (width + tile_w - 1) / tile_w;
 	const int tiles_y = (height + tile_h - 1) / tile_h;
 	const int n_tiles = P.tiles_x * tiles_y;
+	// exact while tile * tiles_x < 2^32 (Granlund-Montgomery round-up reciprocal)
+	P.tiles_x_magic = (P.tiles_x > 1 && (unsigned long long) n_tiles * (unsigned) P.tiles_x < (1ull << 32)) ? (unsigned) ((1ull << 32) / (unsigned) P.tiles_x) + 1u : 0u;
 	P.tile_first = tile_first; P.tile_stride = tile_stride;
 	int my_tiles = tile_first < n_tiles ? (n_tiles - tile_first + tile_stride - 1) / tile_stride : 0;
 	if (tile_limit >= 0 && my_tiles > tile_limit) my_tiles = tile_limit;
