@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--flags", default="0,1,2,3")
     ap.add_argument("--skips", default="2,1,3,0")
     ap.add_argument("--env", default="VKV_RC_FLAGS")
+    ap.add_argument("--view-step", type=int, default=3, help="orbit views between consecutive frames (bench.py: 1 = 5 degrees)")
     a = ap.parse_args()
     import torch
     wl = bench.WORKLOADS[a.workload]
@@ -36,7 +37,7 @@ def main():
     fb = torch.zeros((FH, FW, 4), dtype=torch.uint8, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     counts = torch.zeros(4, dtype=torch.int64, device="cuda")
-    views = [vol.make_uniforms(scene.look_at_camera(bench.orbit_eye(v, 72, wl), aspect=FW / FH), it, wl["clip"]) for v in range(0, 72, 3)]
+    views = [vol.make_uniforms(scene.look_at_camera(bench.orbit_eye(v, 72, wl), aspect=FW / FH), it, wl["clip"]) for v in range(0, 24 * a.view_step, a.view_step)]
     for skip in [int(x) for x in a.skips.split(",")]:
         vol.update_transfer_function(opt, skip)
         ropt = RenderOptions(skipping_type=skip, clip_distance=wl["clip"], early_ray_termination=1)

@@ -183,6 +183,9 @@ void vkv_volume_destroy(vkv_volume *vol)
 	cudaFree(vol->d_swap); cudaFree(vol->d_tmp); cudaFree(vol->d_count); cudaFree(vol->d_counts_scratch);
 	cudaFree(vol->d_fb_scratch);
 	cudaFree(vol->d_ctab);
+	cudaFree(vol->d_tile_cost);
+	cudaFree(vol->d_tile_order);
+	if (vol->h_tile_promote) cudaFreeHost(vol->h_tile_promote);
 	if (vol->copy_stream) {
 		cudaStreamDestroy(vol->copy_stream);
 		for (auto &e : vol->band_done) cudaEventDestroy(e);

@@ -117,6 +117,14 @@ struct vkv_volume {
 	void               *d_ctab = nullptr;              // ray caster: 256x256 float4 premultiplied colour table + the key it was built for
 	uint64_t            ctab_tf_version = ~0ull;
 	float               ctab_sampling = -1.0f, ctab_alpha = -1.0f;
+	// ray caster tile scheduling from the previous frame's cost (raycast.cu): per tile of the last launch's tile list the
+	// largest loop count of its warps, and the issue order derived from it
+	unsigned           *d_tile_cost = nullptr, *d_tile_order = nullptr;
+	int                 tile_hist_capacity = 0;
+	int                 tile_hist_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};        // width, height, tile_w, tile_h, tile_first, tile_stride, my_tiles, skipping type of the history
+	bool                tile_hist_valid = false;
+	int                *h_tile_promote = nullptr;        // pinned + mapped: the last ordering pass's decision (1 = long tiles promoted)
+	int                 tile_order_holdoff = 0;          // frames to go before the ordering pass is tried again
 };
 
 namespace vkv {

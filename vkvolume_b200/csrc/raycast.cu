@@ -20,6 +20,7 @@
 //   * blend-with-clear, sRGB encode and the RGBA8 store happen in the epilogue; the store
 //     target may be a peer-mapped framebuffer (multi-GPU tile gather fused into the kernel).
 // The march loop is the fragment shader's, statement for statement, in fp32 without contraction.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -51,6 +52,8 @@ struct RayParams {
 	float  vpi[16], mi[16];         // view_proj_inv and model_inv in fp32, column-major (depth-buffer intersection)
 	int    width, height;
 	int    tile_w, tile_h, tiles_x, tile_first, tile_stride, my_tiles, seq_base;
+	const unsigned *tile_order;     // issue order of this launch's tile list (from the previous frame's cost) or null: centre-out
+	unsigned       *tile_cost;      // per tile of the list: largest warp loop count of this frame (atomicMax) or null
 	unsigned tiles_x_magic;         // floor(2^32 / tiles_x) + 1: tile / tiles_x == umulhi(tile, magic) for every tile of a frame; 0: divide
 	int    bbox[4];                 // conservative screen bounds (inclusive) of the unit cube: x0, y0, x1, y1
 	cudaTextureObject_t tex_v, tex_g;
@@ -153,7 +156,14 @@ __global__ void __launch_bounds__(256) ctab_kernel(const uchar4 *__restrict__ tf
 	ctab[idx] = e;
 }
 
+// Tiles of a launch are issued from the middle of its tile list outwards (m, m-1, m+1, m-2, ...) unless a history says otherwise.
+__device__ __forceinline__ int centre_out(int seq, int n) { return n / 2 + ((seq & 1) ? -((seq + 1) >> 1) : (seq >> 1)); }
 constexpr int kTraceWords = 8;
+// A CTA is kRcWarps warps, two across and kRcWarps / 2 down: 16 x (2 kRcWarps) pixels.
+#ifndef VKV_RC_WARPS
+#define VKV_RC_WARPS 2
+#endif
+constexpr int kRcWarps = VKV_RC_WARPS, kRcThreads = 32 * kRcWarps, kRcRows = 2 * kRcWarps;
 #ifndef VKV_RC_MIN_CTAS
 #define VKV_RC_MIN_CTAS 16
 #endif
@@ -164,9 +174,9 @@ constexpr int kTraceWords = 8;
 // LOAD: blend and depth-test over the existing contents of the target (vkv_render_options::load_framebuffer) instead of the
 // render-pass clear, and honour depth_attachment; these instantiations always count (COUNT).
 template <int SKIP, bool EXACT, bool COUNT, bool OTF = false, bool TRACE = false, bool LOAD = false>
-__global__ void __launch_bounds__(64, (OTF || LOAD) ? 8 : VKV_RC_MIN_CTAS) raycast_kernel(const __grid_constant__ RayParams P)
+__global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CTAS) * 2 / kRcWarps) raycast_kernel(const __grid_constant__ RayParams P)
 {
-	__shared__ unsigned long long s_cnt[2][4];
+	__shared__ unsigned long long s_cnt[kRcWarps][4];
 
 	// CTA -> tile -> pixel
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -176,20 +186,23 @@ __global__ void __launch_bounds__(64, (OTF || LOAD) ? 8 : VKV_RC_MIN_CTAS) rayca
 	if (TRACE) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
 	// Tiles are issued from the middle of this launch's tile list outwards (m, m-1, m+1, m-2, ...): the long rays sit
 	// near the image centre, so their latency chains start at t = 0 and the cheap border tiles fill the tail.
+	// With a history (the previous frame of this volume at this frame size) the tiles are issued in decreasing order of the loop
+	// count their longest ray needed last time: the frame time is the critical path of a few hundred long warps (profiles/
+	// r1s_trace.md), so they have to start at t = 0, not whenever the sweep reaches them.
 	const int seq        = P.seq_base + (int) blockIdx.z;
-	const int local_tile = P.my_tiles / 2 + ((seq & 1) ? -((seq + 1) >> 1) : (seq >> 1));
+	const int local_tile = P.tile_order ? (int) P.tile_order[seq] : centre_out(seq, P.my_tiles);
 	const int tile       = P.tile_first + local_tile * P.tile_stride;
 	const int tile_y = P.tiles_x_magic ? (int) __umulhi((unsigned) tile, P.tiles_x_magic) : tile / P.tiles_x, tile_x = tile - tile_y * P.tiles_x;
 	const int tx0 = tile_x * P.tile_w + (int) blockIdx.x * 16;
-	const int ty0 = tile_y * P.tile_h + (int) blockIdx.y * 4;
-	const int px = tx0 + warp * 8 + (lane & 7);
-	const int py = ty0 + (lane >> 3);
+	const int ty0 = tile_y * P.tile_h + (int) blockIdx.y * kRcRows;
+	const int px = tx0 + (warp & 1) * 8 + (lane & 7);
+	const int py = ty0 + (warp >> 1) * 4 + (lane >> 3);
 	const bool   in_frame = px < P.width && py < P.height;
 	const size_t p        = (size_t) py * P.width + px;
 
 	// CTA-uniform rejection against the projected bounds of the unit cube: such pixels keep the clear colour
 	// (0,0,0,1) (render_pipeline.cpp:38) and depth 0.
-	if (tx0 > P.bbox[2] || tx0 + 15 < P.bbox[0] || ty0 > P.bbox[3] || ty0 + 3 < P.bbox[1]) {
+	if (tx0 > P.bbox[2] || tx0 + 15 < P.bbox[0] || ty0 > P.bbox[3] || ty0 + kRcRows - 1 < P.bbox[1]) {
 		if (in_frame && !LOAD) {
 			reinterpret_cast<unsigned *>(P.rgba8)[p] = 0xff000000u;
 			if (P.depth) P.depth[p] = 0.0f;
@@ -507,6 +520,10 @@ __global__ void __launch_bounds__(64, (OTF || LOAD) ? 8 : VKV_RC_MIN_CTAS) rayca
 		}
 	}
 
+	if (P.tile_cost) {
+		const unsigned it_warp = __reduce_max_sync(0xffffffffu, n_iter);
+		if (lane == 0 && it_warp) atomicMax(P.tile_cost + local_tile, it_warp);
+	}
 	if (TRACE) {
 		unsigned long long t_end;
 		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
@@ -518,7 +535,7 @@ __global__ void __launch_bounds__(64, (OTF || LOAD) ? 8 : VKV_RC_MIN_CTAS) rayca
 		const unsigned c_top = __reduce_max_sync(0xffffffffu, (unsigned) tc_top), c_req = __reduce_max_sync(0xffffffffu, (unsigned) tc_req);
 		const unsigned c_d = __reduce_max_sync(0xffffffffu, (unsigned) tc_d), c_v = __reduce_max_sync(0xffffffffu, (unsigned) tc_v);
 		if (lane == 0) {
-			const size_t w = (((size_t) blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 2 + warp;
+			const size_t w = (((size_t) blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * kRcWarps + warp;
 			unsigned long long *t = P.trace + w * kTraceWords;
 			t[0] = t_start; t[1] = t_end;
 			t[2] = (unsigned long long) (it_max & 0xfffu) | ((unsigned long long) (m_d & 0xfffu) << 12) | ((unsigned long long) (m_r & 0xfffu) << 24) |
@@ -536,9 +553,87 @@ __global__ void __launch_bounds__(64, (OTF || LOAD) ? 8 : VKV_RC_MIN_CTAS) rayca
 		}
 		__syncthreads();
 		if (threadIdx.x < 4) {
-			const unsigned long long t = s_cnt[0][threadIdx.x] + s_cnt[1][threadIdx.x];
+			unsigned long long t = 0;
+#pragma unroll
+			for (int w = 0; w < kRcWarps; ++w) t += s_cnt[w][threadIdx.x];
 			if (t) atomicAdd(P.counts + threadIdx.x, t);
 		}
+	}
+}
+
+// ---- tile issue order from the previous frame's cost --------------------------------------------------------------------
+// One CTA.  cost[t] = largest warp loop count inside tile t of the launch's tile list last frame.  A frame whose longest rays are
+// few is bound by their latency chains: its long tiles (cost >= 3/4, then >= 1/2 of the frame's maximum, after a 3x3 dilation over
+// the tile grid that absorbs the camera motion between two frames — full-frame lists only: in a strided multi-GPU list the
+// neighbours belong to other ranks) are promoted to the front; all other tiles keep the centre-out order, which keeps the tiles
+// that run together neighbours in the volume (texture and L2 locality).  When more than a third of the tiles are long the frame is
+// throughput-bound (ESS off, block skipping, small volumes) and nothing is promoted: measured, reordering costs those 5-13 %.
+// Also clears cost[] for the frame about to start.
+
+__global__ void __launch_bounds__(1024) tile_order_kernel(unsigned *__restrict__ cost, unsigned *__restrict__ order, int n, int tiles_x, int tiles_y, int dilate, int *__restrict__ decision)
+{
+	extern __shared__ unsigned s_cost[];        // n raw costs, then n dilated costs
+	unsigned *s_dil = s_cost + n;
+	__shared__ unsigned           s_max;
+	__shared__ unsigned long long s_warp[32];
+	__shared__ unsigned long long s_total;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (threadIdx.x == 0) s_max = 0u;
+	for (int t = threadIdx.x; t < n; t += blockDim.x) s_cost[t] = cost[t];
+	__syncthreads();
+	unsigned mx = 0u;
+	for (int t = threadIdx.x; t < n; t += blockDim.x) {
+		unsigned c = s_cost[t];
+		if (dilate) {
+			const int ty = t / tiles_x, tx = t - ty * tiles_x;
+			for (int dy = -1; dy <= 1; ++dy)
+				for (int dx = -1; dx <= 1; ++dx) {
+					const int x = tx + dx, y = ty + dy;
+					if (x >= 0 && x < tiles_x && y >= 0 && y < tiles_y) c = max(c, s_cost[y * tiles_x + x]);
+				}
+		}
+		s_dil[t] = c;
+		mx       = max(mx, c);
+		cost[t]  = 0u;
+	}
+	mx = __reduce_max_sync(0xffffffffu, mx);
+	if (lane == 0) atomicMax(&s_max, mx);
+	__syncthreads();
+	const unsigned hi = max(1u, s_max - s_max / 4u), lo = max(1u, s_max / 2u);
+	auto group = [&](int t) { const unsigned c = s_dil[t]; return c >= hi ? 0 : (c >= lo ? 1 : 2); };
+	// each thread owns a run of the centre-out sequence; counts per group packed 3 x 20 bits
+	const int per = (n + (int) blockDim.x - 1) / (int) blockDim.x;
+	const int s0 = min(n, (int) threadIdx.x * per), s1 = min(n, s0 + per);
+	unsigned long long mine = 0ull;
+	for (int q = s0; q < s1; ++q) mine += 1ull << (20 * group(centre_out(q, n)));
+	unsigned long long incl = mine;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= o) incl += v;
+	}
+	if (lane == 31) s_warp[warp] = incl;
+	__syncthreads();
+	if (warp == 0) {
+		unsigned long long w = s_warp[lane], wi = w;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const unsigned long long v = __shfl_up_sync(0xffffffffu, wi, o);
+			if (lane >= o) wi += v;
+		}
+		s_warp[lane] = wi - w;        // exclusive prefix of the warps
+		if (lane == 31) s_total = wi;
+	}
+	__syncthreads();
+	const unsigned long long excl = s_warp[warp] + incl - mine, total = s_total;
+	const unsigned n0 = (unsigned) (total & 0xfffffu), n1 = (unsigned) ((total >> 20) & 0xfffffu);
+	const bool     promote = (n0 + n1) * 3u <= (unsigned) n;
+	if (threadIdx.x == 0) *decision = promote ? 1 : 0;        // host-visible hint (read a frame or more later, without synchronising)
+	unsigned       pos[3] = {(unsigned) (excl & 0xfffffu), n0 + (unsigned) ((excl >> 20) & 0xfffffu), n0 + n1 + (unsigned) ((excl >> 40) & 0xfffffu)};
+	for (int q = s0; q < s1; ++q) {
+		const int t = centre_out(q, n);
+		if (promote) order[pos[group(t)]++] = (unsigned) t;
+		else order[q] = (unsigned) t;
 	}
 }
 
@@ -703,27 +798,71 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 	unsigned long long *d_trace    = nullptr;
 	size_t              trace_n    = 0;
 	if (trace_path && my_tiles <= 65535) {
-		trace_n = (size_t) my_tiles * (tile_w / 16) * (tile_h / 4) * 2 * kTraceWords;
+		trace_n = (size_t) my_tiles * (tile_w / 16) * (tile_h / kRcRows) * kRcWarps * kTraceWords;
 		VKV_CUDA_CHECK(cudaMalloc(&d_trace, trace_n * sizeof(unsigned long long)));
 		VKV_CUDA_CHECK(cudaMemsetAsync(d_trace, 0, trace_n * sizeof(unsigned long long), s));
 		P.trace = d_trace;
 	}
+	// tile scheduling history (see tile_order_kernel); VKV_RC_NO_HISTORY=1 keeps the centre-out order
+	{
+		const char *no_hist  = getenv("VKV_RC_NO_HISTORY");
+		// distance-map modes only: block skipping and ESS off are throughput-bound at every size measured (promotion costs them 2 %)
+		const bool  use_hist = !(no_hist && atoi(no_hist) != 0) && my_tiles >= 64 && my_tiles <= 6000 &&
+		                       (opt->skipping_type == VKV_SKIP_DISTANCE || opt->skipping_type == VKV_SKIP_ANISOTROPIC_DISTANCE);
+		const int   key[8]   = {width, height, tile_w, tile_h, tile_first, tile_stride, my_tiles, opt->skipping_type};
+		if (use_hist) {
+			if (vol->tile_hist_capacity < my_tiles) {
+				cudaFree(vol->d_tile_cost);
+				cudaFree(vol->d_tile_order);
+				vol->d_tile_cost = vol->d_tile_order = nullptr;
+				vol->tile_hist_capacity = 0;
+				vol->tile_hist_valid    = false;
+				VKV_CUDA_CHECK(cudaMalloc(&vol->d_tile_cost, (size_t) my_tiles * sizeof(unsigned)));
+				VKV_CUDA_CHECK(cudaMalloc(&vol->d_tile_order, (size_t) my_tiles * sizeof(unsigned)));
+				vol->tile_hist_capacity = my_tiles;
+			}
+			const bool same = vol->tile_hist_valid && std::equal(key, key + 8, vol->tile_hist_key);
+			if (!vol->h_tile_promote) {
+				VKV_CUDA_CHECK(cudaHostAlloc(&vol->h_tile_promote, sizeof(int), cudaHostAllocMapped));
+				*vol->h_tile_promote = 1;
+			}
+			// a frame that did not qualify (throughput-bound) is not asked again for a while: the pass costs ~4 us
+			if (same && vol->tile_order_holdoff == 0 && *static_cast<volatile int *>(vol->h_tile_promote) == 0) {
+				vol->tile_order_holdoff  = 32;
+				*vol->h_tile_promote     = 1;
+			}
+			if (!same) vol->tile_order_holdoff = 0;
+			if (same && vol->tile_order_holdoff > 0) {
+				--vol->tile_order_holdoff;        // centre-out order; the cost keeps accumulating (maximum over the frames in between)
+			} else if (same) {
+				const int full = (tile_first == 0 && tile_stride == 1 && my_tiles == n_tiles) ? 1 : 0;
+				tile_order_kernel<<<1, 1024, 2 * (size_t) my_tiles * sizeof(unsigned), s>>>(vol->d_tile_cost, vol->d_tile_order, my_tiles, P.tiles_x, tiles_y, full, vol->h_tile_promote);
+				VKV_LAUNCHED();
+				P.tile_order = vol->d_tile_order;
+			} else {
+				VKV_CUDA_CHECK(cudaMemsetAsync(vol->d_tile_cost, 0, (size_t) my_tiles * sizeof(unsigned), s));
+			}
+			P.tile_cost = vol->d_tile_cost;
+			std::copy(key, key + 8, vol->tile_hist_key);
+		}
+		vol->tile_hist_valid = use_hist;
+	}
 	for (int base = 0; base < my_tiles; base += 65535) {
 		P.seq_base = base;
-		const dim3 grid((unsigned) (tile_w / 16), (unsigned) (tile_h / 4), (unsigned) std::min(65535, my_tiles - base));
+		const dim3 grid((unsigned) (tile_w / 16), (unsigned) (tile_h / kRcRows), (unsigned) std::min(65535, my_tiles - base));
 #define VKV_RC(SK)                                                                      \
 	do {                                                                                \
-		if (load && otf && exact) raycast_kernel<SK, true, true, true, false, true><<<grid, 64, 0, s>>>(P);  \
-		else if (load && otf) raycast_kernel<SK, false, true, true, false, true><<<grid, 64, 0, s>>>(P);     \
-		else if (load && exact) raycast_kernel<SK, true, true, false, false, true><<<grid, 64, 0, s>>>(P);   \
-		else if (load) raycast_kernel<SK, false, true, false, false, true><<<grid, 64, 0, s>>>(P);           \
-		else if (d_trace && !otf && !exact) raycast_kernel<SK, false, false, false, true><<<grid, 64, 0, s>>>(P); \
-		else if (otf && exact) raycast_kernel<SK, true, true, true><<<grid, 64, 0, s>>>(P);   \
-		else if (otf) raycast_kernel<SK, false, true, true><<<grid, 64, 0, s>>>(P);      \
-		else if (exact && counts) raycast_kernel<SK, true, true><<<grid, 64, 0, s>>>(P);      \
-		else if (exact) raycast_kernel<SK, true, false><<<grid, 64, 0, s>>>(P);          \
-		else if (counts) raycast_kernel<SK, false, true><<<grid, 64, 0, s>>>(P);         \
-		else raycast_kernel<SK, false, false><<<grid, 64, 0, s>>>(P);                    \
+		if (load && otf && exact) raycast_kernel<SK, true, true, true, false, true><<<grid, kRcThreads, 0, s>>>(P);  \
+		else if (load && otf) raycast_kernel<SK, false, true, true, false, true><<<grid, kRcThreads, 0, s>>>(P);     \
+		else if (load && exact) raycast_kernel<SK, true, true, false, false, true><<<grid, kRcThreads, 0, s>>>(P);   \
+		else if (load) raycast_kernel<SK, false, true, false, false, true><<<grid, kRcThreads, 0, s>>>(P);           \
+		else if (d_trace && !otf && !exact) raycast_kernel<SK, false, false, false, true><<<grid, kRcThreads, 0, s>>>(P); \
+		else if (otf && exact) raycast_kernel<SK, true, true, true><<<grid, kRcThreads, 0, s>>>(P);   \
+		else if (otf) raycast_kernel<SK, false, true, true><<<grid, kRcThreads, 0, s>>>(P);      \
+		else if (exact && counts) raycast_kernel<SK, true, true><<<grid, kRcThreads, 0, s>>>(P);      \
+		else if (exact) raycast_kernel<SK, true, false><<<grid, kRcThreads, 0, s>>>(P);          \
+		else if (counts) raycast_kernel<SK, false, true><<<grid, kRcThreads, 0, s>>>(P);         \
+		else raycast_kernel<SK, false, false><<<grid, kRcThreads, 0, s>>>(P);                    \
 	} while (0)
 		switch (opt->skipping_type) {
 			case VKV_SKIP_NONE: VKV_RC(VKV_SKIP_NONE); break;
