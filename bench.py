@@ -146,7 +146,6 @@ def run_native(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")        # rank 0's stdout carries the one JSON line and nothing else
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -481,7 +480,7 @@ def run_native(args):
             "clocks": sampler.summary(), "roofline": roofline, "rooflines_hbm": hbm_rooflines, "tex3d_fetch_per_s": tex_peak,
             "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         if peer_ptr:
             capi.check(capi.lib().vkv_ipc_close(__import__("ctypes").c_void_p(peer_ptr)))
@@ -598,10 +597,29 @@ def run_reference(args):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "ess_rebuild_ms": {"occupancy": t_occ * 1e3, "distance": t_dist * 1e3}, "setup_s": t_setup,
             "note": "the reference (Vulkan/GLSL) has no CPU path and cannot be built in this image; this is the oracle port of its shaders on the host cores"}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout carries the one JSON line and nothing else: everything any library writes to fd 1 from here on (NCCL prints its
+    version banner there at communicator creation) goes to stderr; emit() writes the line to the original stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
