@@ -3,21 +3,84 @@
 //
 // Accepts the reference's flags (src/volume_render.h:46-56, VS/app/plugins/*):
 //   --imin= --imax= --gmin= --gmax= --skipmode= --blocksize= --gradient_test --width= --height=
-//   --benchmark[=frames] --stop-after-frame= --screenshot-output=<file.ppm> <dataset>
+//   --benchmark[=frames] --stop-after-frame= --screenshot-output=<file.png|file.ppm> <dataset>
 // and prints the log lines scripts/benchmark.py greps (scripts/benchmark.py:55-60):
 //   "Updated gradient map in {}ms", "Occupied voxels: {}% in {}ms", "Updated occupancy/distance map in {}ms",
 //   "... (ran {} frames, averaged {} fps)".
 // Benchmark mode applies the reference's silent changes (src/volume_render.cpp:177-183,224-234): clip distance 1,
 // early ray termination off, NumTextureSamples view, node scale 100/|R*scale|.
 // <dataset> is a raw volume with a "<dataset>.header" next to it, or "synth:<kind>:<W>x<H>x<D>" for a generated one.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "vkvolume.h"
 
 using namespace vkvolume;
+
+// PNG writer for the screenshot (the reference goes through stb_image_write after forcing alpha to 255,
+// VS/framework/common/utils.cpp:141-175): 8-bit RGBA, filter 0 on every row, zlib stream of stored (uncompressed) blocks.
+static uint32_t crc32_update(uint32_t crc, const uint8_t *p, size_t n)
+{
+	static uint32_t table[256];
+	if (!table[1])
+		for (uint32_t i = 0; i < 256; ++i) {
+			uint32_t c = i;
+			for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xedb88320u ^ (c >> 1) : c >> 1;
+			table[i] = c;
+		}
+	for (size_t i = 0; i < n; ++i) crc = table[(crc ^ p[i]) & 0xffu] ^ (crc >> 8);
+	return crc;
+}
+static void png_chunk(FILE *f, const char type[4], const std::vector<uint8_t> &data)
+{
+	const uint32_t n      = (uint32_t) data.size();
+	const uint8_t  len[4] = {(uint8_t) (n >> 24), (uint8_t) (n >> 16), (uint8_t) (n >> 8), (uint8_t) n};
+	fwrite(len, 1, 4, f);
+	fwrite(type, 1, 4, f);
+	if (n) fwrite(data.data(), 1, n, f);
+	uint32_t crc = crc32_update(0xffffffffu, reinterpret_cast<const uint8_t *>(type), 4);
+	crc          = crc32_update(crc, data.data(), n) ^ 0xffffffffu;
+	const uint8_t c[4] = {(uint8_t) (crc >> 24), (uint8_t) (crc >> 16), (uint8_t) (crc >> 8), (uint8_t) crc};
+	fwrite(c, 1, 4, f);
+}
+static void write_png_rgba(const std::string &path, const uint8_t *rgba, uint32_t width, uint32_t height)
+{
+	FILE *f = fopen(path.c_str(), "wb");
+	if (!f) throw std::runtime_error("cannot open screenshot file");
+	static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+	fwrite(sig, 1, 8, f);
+	std::vector<uint8_t> ihdr = {(uint8_t) (width >> 24), (uint8_t) (width >> 16), (uint8_t) (width >> 8), (uint8_t) width,
+	                             (uint8_t) (height >> 24), (uint8_t) (height >> 16), (uint8_t) (height >> 8), (uint8_t) height,
+	                             8, 6, 0, 0, 0};        // 8 bits, colour type 6 (RGBA), deflate, adaptive filtering, no interlace
+	png_chunk(f, "IHDR", ihdr);
+	std::vector<uint8_t> raw;        // filter byte 0 + row
+	raw.reserve((size_t) height * (1 + (size_t) width * 4));
+	for (uint32_t y = 0; y < height; ++y) {
+		raw.push_back(0);
+		raw.insert(raw.end(), rgba + (size_t) y * width * 4, rgba + (size_t) (y + 1) * width * 4);
+	}
+	std::vector<uint8_t> z = {0x78, 0x01};
+	uint32_t             a = 1, b = 0;        // Adler-32
+	for (size_t off = 0; off < raw.size() || off == 0; off += 65535) {
+		const size_t n     = std::min<size_t>(65535, raw.size() - off);
+		const bool   final = off + n >= raw.size();
+		z.push_back(final ? 1 : 0);
+		z.push_back((uint8_t) n); z.push_back((uint8_t) (n >> 8));
+		z.push_back((uint8_t) ~n); z.push_back((uint8_t) (~n >> 8));
+		z.insert(z.end(), raw.begin() + off, raw.begin() + off + n);
+		for (size_t i = 0; i < n; ++i) { a = (a + raw[off + i]) % 65521u; b = (b + a) % 65521u; }
+		if (final) break;
+	}
+	const uint32_t adler = (b << 16) | a;
+	z.push_back((uint8_t) (adler >> 24)); z.push_back((uint8_t) (adler >> 16)); z.push_back((uint8_t) (adler >> 8)); z.push_back((uint8_t) adler);
+	png_chunk(f, "IDAT", z);
+	png_chunk(f, "IEND", {});
+	fclose(f);
+}
 
 static bool flag_value(const char *arg, const char *name, std::string &out)
 {
@@ -112,7 +175,11 @@ int main(int argc, char **argv)
 		const vkv_sample_counts c = subpass.read_sample_counts(cmd);
 		printf("[info] samples: volume %llu distance %llu covered pixels %llu over %ld frames\n", (unsigned long long) c.volume_samples,
 		       (unsigned long long) c.distance_samples, (unsigned long long) c.covered_pixels, frames);
-		if (!screenshot.empty()) {        // binary PPM, alpha dropped (the reference's screenshot forces alpha to 255)
+		if (!screenshot.empty() && screenshot.size() >= 4 && screenshot.compare(screenshot.size() - 4, 4, ".png") == 0) {
+			auto fb = subpass.read_framebuffer(cmd);
+			for (size_t p = 0; p < (size_t) width * height; ++p) fb[p * 4 + 3] = 255;        // utils.cpp:141-175: transparency removed
+			write_png_rgba(screenshot, fb.data(), width, height);
+		} else if (!screenshot.empty()) {        // binary PPM, alpha dropped
 			auto  fb = subpass.read_framebuffer(cmd);
 			FILE *f  = fopen(screenshot.c_str(), "wb");
 			if (!f) throw std::runtime_error("cannot open screenshot file");
