@@ -282,6 +282,16 @@ VKV_API int vkv_render_to_host(vkv_volume *vol, const vkv_camera_uniform *cam, c
                                const vkv_transfer_function_uniform *tfu, const vkv_render_options *opt, int width,
                                int height, uint8_t *rgba8_host, vkv_sample_counts *counts_host, void *stream);
 
+/* Pipelined form of vkv_render_to_host for sequences of frames (an orbit, an animation, the benchmark's e2e leg): the call
+ * enqueues the ray casting on `stream` and the copy-out of the finished frame (and counters) on an internal copy stream and
+ * returns; frame k leaves over PCIe while frame k + 1 is being cast (a ring of three device frames decouples them).
+ * `rgba8_host` and `counts_host` must be page-locked and stay valid until vkv_render_to_host_wait(vol, stream) returns, which
+ * is also when their contents are defined.  Renders over the clear colour only (no load_framebuffer / depth_attachment). */
+VKV_API int vkv_render_to_host_async(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_cast_uniform *ray,
+                                     const vkv_transfer_function_uniform *tfu, const vkv_render_options *opt, int width,
+                                     int height, uint8_t *rgba8_host, vkv_sample_counts *counts_host, void *stream);
+VKV_API int vkv_render_to_host_wait(vkv_volume *vol, void *stream);
+
 /* Host-buffer call that also carries the depth attachment and composites: with
  * opt->load_framebuffer the contents of `rgba8_host` (and `depth_host`, float per
  * pixel, reverse-Z, may be NULL unless opt->depth_attachment) are uploaded, the

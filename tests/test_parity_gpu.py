@@ -579,3 +579,25 @@ def test_full_size_properties_config2(ctx):
         loc = orc.distance_map(sub)
         assert (crop <= loc).all()        # more occupied blocks outside the crop can only shorten distances
     vol.close()
+
+
+def test_render_to_host_async_pipeline_equals_blocking_calls(ctx):
+    """vkv_render_to_host_async (copy-out of frame k overlapping the casting of frame k+1, ring of device frames) returns the same
+    frames and counters as one blocking vkv_render_to_host per view."""
+    import torch
+    opt = VolumeOptions(**TF_SETS[0])
+    sc = _scene_for_compositing(ctx, (48, 64, 80), opt, 1, SKIP_DISTANCE)
+    vol, width, height, n = sc["vol"], 192, 128, 7
+    it = scene.image_transform((0.004,) * 3, (80, 64, 48))
+    views = [vol.make_uniforms(scene.look_at_camera((34 * math.cos(0.3 * k), 22, 50 * math.sin(0.3 * k) + 20), aspect=width / height), it, 5.0) for k in range(n)]
+    ropt = RenderOptions(skipping_type=SKIP_DISTANCE, clip_distance=5.0)
+    frames = torch.empty((n, height, width, 4), dtype=torch.uint8).pin_memory()
+    counts = torch.zeros((n, 4), dtype=torch.int64).pin_memory()
+    for k, (cu, ru) in enumerate(views):
+        vol.render_to_host_async(cu, ru, sc["tfu"], ropt, width, height, frames[k].data_ptr(), counts[k].data_ptr())
+    vol.render_to_host_wait()
+    for k, (cu, ru) in enumerate(views):
+        img, c = vol.render_to_host(cu, ru, sc["tfu"], ropt, width, height)
+        assert np.array_equal(frames[k].numpy(), img), k
+        assert counts[k].tolist() == [c.volume_samples, c.distance_samples, c.empty_samples, c.covered_pixels]
+    vol.close()

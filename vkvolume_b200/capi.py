@@ -127,6 +127,9 @@ _SIGNATURES = {
                                    _P, _P, _P, _P]),
     "vkv_render_to_host": (C.c_int, [_P, C.POINTER(CameraUniform), C.POINTER(RayCastUniform), C.POINTER(TransferFunctionUniform),
                                      C.POINTER(RenderOptions), C.c_int, C.c_int, _P, C.POINTER(SampleCounts), _P]),
+    "vkv_render_to_host_async": (C.c_int, [_P, C.POINTER(CameraUniform), C.POINTER(RayCastUniform), C.POINTER(TransferFunctionUniform),
+                                           C.POINTER(RenderOptions), C.c_int, C.c_int, _P, _P, _P]),
+    "vkv_render_to_host_wait": (C.c_int, [_P, _P]),
     "vkv_render_over_host": (C.c_int, [_P, C.POINTER(CameraUniform), C.POINTER(RayCastUniform), C.POINTER(TransferFunctionUniform),
                                        C.POINTER(RenderOptions), C.c_int, C.c_int, _P, _P, C.POINTER(SampleCounts), _P]),
     "vkv_volume_extent": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
@@ -324,6 +327,14 @@ class Volume:
         check(lib().vkv_render_to_host(self.handle, C.byref(cu), C.byref(ru), C.byref(tfu), C.byref(opt), width, height,
                                        _host_ptr(out), C.byref(counts) if want_counts else None, _P(stream)))
         return out, counts
+
+    def render_to_host_async(self, cu, ru, tfu, opt, width, height, rgba_host_ptr: int, counts_host_ptr: int = 0, stream: int = 0):
+        """vkv_render_to_host_async: page-locked destination pointers; contents are defined after render_to_host_wait()."""
+        check(lib().vkv_render_to_host_async(self.handle, C.byref(cu), C.byref(ru), C.byref(tfu), C.byref(opt), width, height,
+                                             _P(rgba_host_ptr), _P(counts_host_ptr), _P(stream)))
+
+    def render_to_host_wait(self, stream: int = 0):
+        check(lib().vkv_render_to_host_wait(self.handle, _P(stream)))
 
     def render_over_host(self, cu, ru, tfu, opt, width, height, rgba: np.ndarray | None = None, depth: np.ndarray | None = None,
                          want_counts=True, stream: int = 0):

@@ -191,6 +191,10 @@ void vkv_volume_destroy(vkv_volume *vol)
 		for (auto &e : vol->band_done) cudaEventDestroy(e);
 		cudaEventDestroy(vol->copies_done);
 	}
+	for (auto *p : vol->d_async_fb) cudaFree(p);
+	cudaFree(vol->d_async_counts);
+	if (vol->async_ready)
+		for (int i = 0; i < vkv_volume::kAsyncSlots; ++i) { cudaEventDestroy(vol->async_rendered[i]); cudaEventDestroy(vol->async_copied[i]); }
 	if (vol->h_count) cudaFreeHost(vol->h_count);
 	delete vol;
 }
@@ -523,6 +527,63 @@ int vkv_render_to_host(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv
 	VKV_CUDA_CHECK(cudaStreamWaitEvent(s, vol->copies_done, 0));
 	VKV_CUDA_CHECK(cudaStreamSynchronize(s));
 	if (counts_host) memcpy(counts_host, vol->h_count, sizeof(vkv_sample_counts));
+	return VKV_OK;
+}
+
+int vkv_render_to_host_async(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_cast_uniform *ray,
+                             const vkv_transfer_function_uniform *tfu, const vkv_render_options *opt, int width, int height,
+                             uint8_t *rgba8_host, vkv_sample_counts *counts_host, void *stream)
+{
+	VKV_REQUIRE(vol && cam && ray && tfu && opt && rgba8_host, VKV_ERR_ARGUMENT, "vkv_render_to_host_async: NULL argument");
+	VKV_REQUIRE(!opt->load_framebuffer && !opt->depth_attachment, VKV_ERR_ARGUMENT, "vkv_render_to_host_async renders over the clear colour only");
+	int rc;
+	if ((rc = check_render(vol, tfu, opt, width, height, 64, 32, 1, false))) return rc;
+	DeviceGuard  guard(vol->ctx->device);
+	cudaStream_t s     = (cudaStream_t) stream;
+	const size_t bytes = (size_t) width * height * 4;
+	constexpr int kSlots = vkv_volume::kAsyncSlots;
+	if (!vol->copy_stream) {
+		VKV_CUDA_CHECK(cudaStreamCreateWithFlags(&vol->copy_stream, cudaStreamNonBlocking));
+		for (auto &e : vol->band_done) VKV_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		VKV_CUDA_CHECK(cudaEventCreateWithFlags(&vol->copies_done, cudaEventDisableTiming));
+	}
+	if (!vol->async_ready) {
+		for (int i = 0; i < kSlots; ++i) {
+			VKV_CUDA_CHECK(cudaEventCreateWithFlags(&vol->async_rendered[i], cudaEventDisableTiming));
+			VKV_CUDA_CHECK(cudaEventCreateWithFlags(&vol->async_copied[i], cudaEventDisableTiming));
+		}
+		VKV_CUDA_CHECK(cudaMalloc(&vol->d_async_counts, kSlots * sizeof(vkv_sample_counts)));
+		vol->async_ready = true;
+	}
+	if (vol->async_fb_bytes < bytes) {
+		VKV_CUDA_CHECK(cudaStreamSynchronize(vol->copy_stream));
+		for (auto *&p : vol->d_async_fb) { cudaFree(p); p = nullptr; }
+		vol->async_fb_bytes = 0;
+		for (auto *&p : vol->d_async_fb) VKV_CUDA_CHECK(cudaMalloc(&p, bytes));
+		vol->async_fb_bytes = bytes;
+		vol->async_seq      = 0;
+	}
+	const int slot = (int) (vol->async_seq % kSlots);
+	// the frame that used this slot kSlots calls ago must have left the device before it is rendered over
+	if (vol->async_seq >= (unsigned) kSlots) VKV_CUDA_CHECK(cudaStreamWaitEvent(s, vol->async_copied[slot], 0));
+	vkv_sample_counts *counts_dev = counts_host ? vol->d_async_counts + slot : nullptr;
+	if (counts_host) VKV_CUDA_CHECK(cudaMemsetAsync(counts_dev, 0, sizeof(vkv_sample_counts), s));
+	if ((rc = launch_render(vol, cam, ray, tfu, opt, width, height, 64, 32, 0, 1, -1, vol->d_async_fb[slot], nullptr, counts_dev, s))) return rc;
+	VKV_CUDA_CHECK(cudaEventRecord(vol->async_rendered[slot], s));
+	VKV_CUDA_CHECK(cudaStreamWaitEvent(vol->copy_stream, vol->async_rendered[slot], 0));
+	VKV_CUDA_CHECK(cudaMemcpyAsync(rgba8_host, vol->d_async_fb[slot], bytes, cudaMemcpyDeviceToHost, vol->copy_stream));
+	if (counts_host) VKV_CUDA_CHECK(cudaMemcpyAsync(counts_host, counts_dev, sizeof(vkv_sample_counts), cudaMemcpyDeviceToHost, vol->copy_stream));
+	VKV_CUDA_CHECK(cudaEventRecord(vol->async_copied[slot], vol->copy_stream));
+	++vol->async_seq;
+	return VKV_OK;
+}
+
+int vkv_render_to_host_wait(vkv_volume *vol, void *stream)
+{
+	VKV_REQUIRE(vol, VKV_ERR_ARGUMENT, "vol is NULL");
+	DeviceGuard guard(vol->ctx->device);
+	VKV_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t) stream));
+	if (vol->copy_stream) VKV_CUDA_CHECK(cudaStreamSynchronize(vol->copy_stream));
 	return VKV_OK;
 }
 

@@ -113,6 +113,14 @@ struct vkv_volume {
 	cudaStream_t        copy_stream = nullptr;         // vkv_render_to_host: D2H copies of finished bands overlap the next band
 	cudaEvent_t         band_done[8]{};
 	cudaEvent_t         copies_done = nullptr;
+	// vkv_render_to_host_async: a ring of device frames so that the copy-out of frame k overlaps the ray casting of frame k + 1
+	static constexpr int kAsyncSlots = 3;
+	uint8_t            *d_async_fb[kAsyncSlots]{};
+	vkv_sample_counts  *d_async_counts = nullptr;        // kAsyncSlots entries
+	size_t              async_fb_bytes = 0;
+	cudaEvent_t         async_rendered[kAsyncSlots]{}, async_copied[kAsyncSlots]{};
+	unsigned            async_seq = 0;
+	bool                async_ready = false;
 	uint64_t            tf_version = 0;                // bumped by every TF-texture write
 	void               *d_ctab = nullptr;              // ray caster: 256x256 float4 premultiplied colour table + the key it was built for
 	uint64_t            ctab_tf_version = ~0ull;
