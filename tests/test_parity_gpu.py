@@ -601,3 +601,30 @@ def test_render_to_host_async_pipeline_equals_blocking_calls(ctx):
         assert np.array_equal(frames[k].numpy(), img), k
         assert counts[k].tolist() == [c.volume_samples, c.distance_samples, c.empty_samples, c.covered_pixels]
     vol.close()
+
+
+@pytest.mark.parametrize("dims", [(1024, 512, 256), (1024, 1024, 160)])
+def test_tma_occupancy_ring_on_wide_volumes_with_gradient(ctx, dims):
+    """Regression (config 4's shape class): 1024-voxel-wide volumes of 128 MB and more with a gradient transfer function.  With a
+    ring of five stages a consumer group could run ahead of an out-of-order bulk copy and consume a slot that was not its own
+    (unspecified launch failure).  The TMA-staged kernel must agree with the register-staged one, map and count."""
+    import os
+    W, H, D = dims
+    vol = capi.Volume(ctx, W, H, D)
+    capi.synth_volume(ctx, 3, 0x5EED0005, W, H, D, vol.device_voxels())
+    vol.upload_device(vol.device_voxels())
+    opt = VolumeOptions(intensity_min=0.15, intensity_max=1.0, gradient_min=0.02, gradient_max=0.2)
+    tfu = capi.transfer_function_uniform(opt)
+    vol.compute_gradient_map(tfu)
+    results = []
+    for no_tma in ("0", "1", "0"):
+        os.environ["VKV_OCC_NO_TMA"] = no_tma if no_tma == "1" else ""
+        if no_tma != "1":
+            os.environ.pop("VKV_OCC_NO_TMA")
+        n = vol.update_transfer_function(opt, SKIP_BLOCK, count=True)
+        results.append((n, vol.download_distance_map(0)))
+    os.environ.pop("VKV_OCC_NO_TMA", None)
+    assert results[0][0] == results[1][0] == results[2][0] and results[0][0] > 0
+    assert np.array_equal(results[0][1], results[1][1]) and np.array_equal(results[0][1], results[2][1])
+    assert 0 < (results[0][1] == 0).mean() < 1
+    vol.close()

@@ -324,8 +324,15 @@ constexpr int kTmaXC       = 1024;                   // voxels of x per task
 constexpr int kTmaRows     = 16;                     // 4 x 4 rows of a block row
 constexpr int kTmaConsumers = 512;                   // two groups of 256
 constexpr int kTmaThreads  = kTmaConsumers + 32;     // + one producer warp
+// The stage count must be EVEN: the two consumer groups take the producer's tasks alternately, so with an even ring every slot
+// belongs to one group for the whole launch.  With an odd ring a slot alternates between the groups, and a group that had already
+// finished its first two tasks could reach a slot whose FIRST fill (another group's task) had not landed yet — bulk copies complete
+// out of order, and on volumes past the TLB reach the first boxes are the slow ones; waiting for an odd phase on a barrier still in
+// phase 0 succeeds at once, the group consumed a stage that was not its own and released it a second time (seen as an unspecified
+// launch failure on 1024-voxel-wide volumes of 128 MB and more with a gradient transfer function, five stages).
 template <bool USE_G> struct TmaCfg {
-	static constexpr int    kStages     = USE_G ? 5 : 10;
+	static constexpr int    kStages     = USE_G ? 6 : 10;
+	static_assert(kStages % 2 == 0, "every ring slot must stay with one consumer group");
 	static constexpr int    kStageBytes = kTmaRows * kTmaXC * (USE_G ? 2 : 1);
 	static constexpr size_t kSmemBytes  = (size_t) kStages * kStageBytes + 2 * kStages * sizeof(uint64_t) + 16;
 };
