@@ -628,3 +628,34 @@ def test_tma_occupancy_ring_on_wide_volumes_with_gradient(ctx, dims):
     assert np.array_equal(results[0][1], results[1][1]) and np.array_equal(results[0][1], results[2][1])
     assert 0 < (results[0][1] == 0).mean() < 1
     vol.close()
+
+
+def test_full_size_properties_config4(ctx):
+    """1024^3 with a gradient transfer function (config 4 size): occupancy map and voxel count bit-exact against the oracle run over
+    the whole downloaded volume, and the distance-map invariants, at three settings of the TF sweep."""
+    W = H = D = 1024
+    vol = capi.Volume(ctx, W, H, D)
+    capi.synth_volume(ctx, 3, 0x5EED0004, W, H, D, vol.device_voxels())
+    vol.upload_device(vol.device_voxels())
+    vol.compute_gradient_map(capi.transfer_function_uniform(VolumeOptions(gradient_min=0.0, gradient_max=0.2)))
+    Vh, Gh = vol.download_voxels(), vol.download_gradient()
+    assert np.array_equal(Gh, orc.gradient_map(Vh, True))        # K1 byte-exact over the whole 1024^3 volume
+    assert np.array_equal(vol.download_gradient_texture(), Gh)   # and the copy the ray caster samples (written by the same kernel)
+    counts = []
+    for k in (0, 7, 24):        # three settings of the sweep (imin = 0.05 + 0.004 k, gradient window on)
+        opt = VolumeOptions(intensity_min=0.05 + 0.004 * k, intensity_max=1.0, gradient_min=0.05, gradient_max=0.25)
+        tfu = capi.transfer_function_uniform(opt)
+        n = vol.update_transfer_function(opt, SKIP_DISTANCE, count=True)
+        counts.append(n)
+        iso = vol.download_distance_map(0)
+        vol.update_transfer_function(opt, SKIP_BLOCK)
+        O = vol.download_distance_map(0)
+        if k == 7:        # the oracle over the full volume (OpenMP): occupancy map and count bit-exact at BASELINE size
+            tf = orc.transfer_function_texture(opt)
+            assert np.array_equal(O, orc.occupancy_map(Vh, Gh, tf, 4, True))
+            assert n == orc.occupied_voxel_count(Vh, Gh, tfu)
+        assert np.array_equal(iso == 0, O == 0)
+        for ax in range(3):
+            assert np.abs(np.diff(iso.astype(np.int16), axis=ax)).max() <= 1
+    assert counts[0] > counts[1] > counts[2] > 0        # a rising intensity threshold shows fewer voxels
+    vol.close()
