@@ -492,8 +492,8 @@ def run_native(args):
             ach = bytes_ / (ms * 1e-3) / 1e9
             return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                     "algorithmic_bytes_per_launch": bytes_, "ms": ms, "peak_source": peak_src}
-        hbm_rooflines["gradient_int_kernel"] = rl(2 * N_vox, float(np.median(t_grad)))
-        hbm_rooflines["gradient_int_kernel"]["note"] = "2 B/voxel algorithmic; the kernel also writes the map into the texture array (+1 B/voxel)"
+        hbm_rooflines["gradient_flat_kernel"] = rl(2 * N_vox, float(np.median(t_grad)))
+        hbm_rooflines["gradient_flat_kernel"]["note"] = "2 B/voxel algorithmic; the kernel also writes the map into the texture array (+1 B/voxel)"
         hbm_rooflines["occupancy_tma_kernel"] = rl((2 if use_g else 1) * N_vox + M_blk, stage_ms["occupancy"])
         hbm_rooflines["occupancy_tma_kernel+count"] = rl((2 if use_g else 1) * N_vox, float(np.median(count_ms)))
         hbm_rooflines["occupancy_tma_kernel+count"]["note"] = "vkv_compute_occupied_voxel_count: memset + kernel + 8-byte D2H + stream sync inside the timed region"
