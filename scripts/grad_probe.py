@@ -12,7 +12,7 @@ import bench
 from vkvolume_b200 import capi
 from vkvolume_b200.capi import VolumeOptions
 
-wl = bench.WORKLOADS["c2"]
+wl = bench.WORKLOADS[os.environ.get("GRAD_PROBE_WORKLOAD", "c2")]
 W, H, D = wl["dim"]
 ctx = capi.Context(0)
 stream = torch.cuda.current_stream().cuda_stream

@@ -445,7 +445,11 @@ int launch_gradient(vkv_volume *vol, bool use_gradient, float modifier, cudaStre
 		const unsigned ntasks = ((vol->dim[0] / 16 + 31) / 32) * vol->dim[1] * vol->dim[2];
 		const unsigned grid   = (ntasks + 7) / 8;
 		const uint64_t chunks = (uint64_t) (vol->dim[0] / 16) * vol->dim[1] * vol->dim[2];
-		if (!getenv("VKV_GRAD_V1") && vol->dim[0] <= 65536 && vol->dim[1] <= 65536 && vol->dim[2] < 65536 && chunks < (1ull << 32)) {
+		// The flat persistent walk wins while the volume's working set (the z +- 1 tap slices, two slices apart) stays in L2; on
+		// multi-gigabyte volumes the row-task kernel, whose warps sweep one row each and keep neighbouring rows together, is up
+		// to 2x faster (measured: 2048x2048x1024 5.4 vs 6.0 ms, 4096x4096x2048 44 vs 86 ms; 832x832x494 0.50 vs 0.37 ms).
+		const bool flat_ok = vol->N <= (2ull << 30) || getenv("VKV_GRAD_FLAT");
+		if (!getenv("VKV_GRAD_V1") && flat_ok && vol->dim[0] <= 65536 && vol->dim[1] <= 65536 && vol->dim[2] < 65536 && chunks < (1ull << 32)) {
 			// persistent: every warp resident at once, each thread walks chunks gid, gid + stride, ...
 			const unsigned nchunks = vol->dim[0] / 16;
 			const char    *e_ctas      = getenv("VKV_GRAD_CTAS");
