@@ -270,7 +270,7 @@ def run_native(args):
             p = C.c_void_p()
             capi.check(capi.lib().vkv_ipc_open(hbuf, C.byref(p)))
             peer_ptr = p.value
-            fb_ptr = peer_ptr + (rank * frame_bytes if frames_mode else 0)        # this rank's slot of rank 0's frame ring
+            fb_ptr = peer_ptr + (sharding.frame_slot_offset(rank, FW, FH) if frames_mode else 0)        # this rank's slot of rank 0's frame ring
     counts_t = torch.zeros(4, dtype=torch.int64, device=dev)
 
     cams = [scene.look_at_camera(orbit_eye(k, 72, wl), aspect=FW / FH) for k in range(72)]        # synthetic inputs: the camera path
@@ -280,7 +280,7 @@ def run_native(args):
 
     def render_step(step, counts_ptr):
         if frames_mode:        # N consecutive views per step, one per rank, each into its slot on rank 0
-            cu, ru = uniforms(step * world + rank)
+            cu, ru = uniforms(sharding.view_of_rank(step, rank, world))
             vol.render(cu, ru, tfu, ropt, FW, FH, fb_ptr, 0, counts_ptr, stream)
             return
         cu, ru = uniforms(step)
@@ -421,14 +421,14 @@ def run_native(args):
         ring = torch.empty((3, FH, FW, 4), dtype=torch.uint8).pin_memory()
         cnt = torch.zeros((ke, 4), dtype=torch.int64).pin_memory()
         for s in range(3):
-            cu, ru = uniforms(s * world + rank)
+            cu, ru = uniforms(sharding.view_of_rank(s, rank, world))
             vol.render_to_host_async(cu, ru, tfu, ropt, FW, FH, ring[s % 3].data_ptr(), cnt[s].data_ptr(), stream)
         vol.render_to_host_wait(stream)
         cnt.zero_()
         barrier()
         t0 = time.perf_counter()
         for s in range(ke):
-            cu, ru = uniforms(s * world + rank)
+            cu, ru = uniforms(sharding.view_of_rank(s, rank, world))
             vol.render_to_host_async(cu, ru, tfu, ropt, FW, FH, ring[s % 3].data_ptr(), cnt[s].data_ptr(), stream)
         vol.render_to_host_wait(stream)
         t1 = time.perf_counter()

@@ -34,6 +34,52 @@ def test_tiles_are_dealt_exactly_once(frame, world):
     assert max(sizes) - min(sizes) <= 1
 
 
+@pytest.mark.parametrize("world,steps", [(2, 5), (8, 9), (1, 4)])
+def test_frames_are_dealt_exactly_once_and_slots_do_not_overlap(world, steps):
+    views = sorted(sharding.view_of_rank(s, r, world) for s in range(steps) for r in range(world))
+    assert views == list(range(steps * world))
+    w, h = 1920, 1080
+    offs = [sharding.frame_slot_offset(r, w, h) for r in range(world)]
+    assert offs == [r * w * h * 4 for r in range(world)] and len(set(offs)) == world
+
+
+FRAMES_WORKER = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, os.environ["VKV_ROOT"]); sys.path.insert(0, os.path.join(os.environ["VKV_ROOT"], "tests"))
+import oracle_api as orc
+from vkvolume_b200 import scene, sharding
+from vkvolume_b200.capi import RenderOptions, VolumeOptions
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+# frames decomposition with the oracle standing in for the ray caster: each rank renders its view of every step into its slot;
+# the ring gathered on rank 0 must equal rank 0's own render of views step*world .. step*world + world - 1
+shape = (20, 24, 28); D, H, W = shape; fw, fh = 48, 32
+V = scene.blobs_volume(shape, seed=9, n_blobs=5)
+opt = VolumeOptions(intensity_min=0.1, intensity_max=1.0, gradient_min=0.0, gradient_max=0.0)
+tfu = orc.transfer_function_uniform(opt); tf = orc.transfer_function_texture(opt)
+(dim_b), _ = orc.map_extent((W, H, D), 4)
+it = scene.image_transform((0.004,) * 3, (W, H, D))
+ropt = RenderOptions(skipping_type=0, clip_distance=2.0)
+def frame(view):
+    cam = scene.look_at_camera((14 + 2 * view, 9, 20 - view), aspect=fw / fh)
+    cu, ru = orc.make_uniforms((W, H, D), dim_b, cam, it, 2.0)
+    return orc.render(V, None, tf, None, dim_b, cu, ru, tfu, ropt, fw, fh)[0]
+for step in range(2):
+    mine = torch.from_numpy(frame(sharding.view_of_rank(step, rank, world)).reshape(-1).copy())
+    ring = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(ring, mine)        # stands in for the peer stores into rank 0's ring
+    if rank == 0:
+        flat = torch.cat(ring).numpy()
+        for r in range(world):
+            o = sharding.frame_slot_offset(r, fw, fh)
+            assert np.array_equal(flat[o:o + fw * fh * 4].reshape(fh, fw, 4), frame(step * world + r)), (step, r)
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
 WORKER = r'''
 import os, sys
 import numpy as np
@@ -76,9 +122,10 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def test_zslab_exchange_world_size_2_gloo(tmp_path):
+@pytest.mark.parametrize("worker", ["zslab", "frames"])
+def test_exchange_world_size_2_gloo(tmp_path, worker):
     script = tmp_path / "worker.py"
-    script.write_text(WORKER)
+    script.write_text(WORKER if worker == "zslab" else FRAMES_WORKER)
     port = _free_port()
     procs = []
     for rank in range(2):

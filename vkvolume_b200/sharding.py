@@ -5,6 +5,9 @@ and on CUDA tensors with NCCL (how bench.py runs it) — there is no compute her
 * Ray casting shards by image tiles: tile t of the row-major tile list goes to rank t % world (round-robin, because
   ESS/ERT make per-pixel cost wildly non-uniform); every rank holds a full replica and stores its tiles straight into
   rank 0's framebuffer (peer mapping), so that path has no collective at all.
+* Frame sequences (an orbit, an animation) shard by frames instead: step s of an N-rank job renders views s*N .. s*N + N - 1, view
+  s*N + r on rank r, which stores it into slot r of a ring of N frames in rank 0's HBM (or delivers it to its own pinned host
+  buffer); again no collective.
 * The TF-change rebuild shards the O(N) occupancy pass by z-slabs of blocks; the slab rows of the occupancy map are
   all-gathered, the voxel count is all-reduced, and every rank then runs the distance transform on the full map.
 """
@@ -26,6 +29,16 @@ def slab_range(rank: int, world: int, depth_blocks: int) -> tuple[int, int]:
 def tiles_of_rank(rank: int, world: int, n_tiles: int) -> range:
     """Tiles rendered by `rank` — what vkv_render_tiles(tile_first=rank, tile_stride=world) covers."""
     return range(rank, n_tiles, world)
+
+
+def view_of_rank(step: int, rank: int, world: int) -> int:
+    """Frames decomposition: the view (index into the frame sequence) `rank` renders at `step`."""
+    return step * world + rank
+
+
+def frame_slot_offset(rank: int, width: int, height: int) -> int:
+    """Byte offset of `rank`'s slot in the ring of RGBA8 frames on rank 0 (slot r holds view step*world + r)."""
+    return rank * width * height * 4
 
 
 def n_tiles(width: int, height: int, tile_w: int, tile_h: int) -> int:
