@@ -394,3 +394,52 @@ def test_worked_skip_example_from_survey():
     assert delta(0.1, 3.25, 3, 2, False) == 18
     assert delta(-0.1, 3.25, 3, 2, False) == 13
     assert delta(0.1, 3.25, 3, 2, True) == 8
+
+
+# ---- compositing over an existing target, depth attachment (volume_render_subpass.cpp:176-190, volume_render.frag:122-165) --------
+def test_load_over_explicit_clear_equals_clear_and_far_depth_changes_nothing():
+    s = _scene()
+    Dm = orc.distance_map(s["O"])
+    args = (s["V"], s["G"], s["tf"], Dm, s["dim_b"], s["cu"], s["ru"], s["tfu"])
+    plain, c0, _, d0 = orc.render(*args, RenderOptions(skipping_type=SKIP_DISTANCE, clip_distance=5.0), 96, 96, want_depth=True)
+    clear = np.zeros((96, 96, 4), np.uint8)
+    clear[..., 3] = 255
+    zero = np.zeros((96, 96), np.float32)
+    over, c1, _, d1 = orc.render(*args, RenderOptions(skipping_type=SKIP_DISTANCE, clip_distance=5.0, load_framebuffer=1), 96, 96,
+                                 rgba_init=clear, depth_init=zero)
+    assert np.array_equal(over, plain) and np.array_equal(d1, d0)
+    assert (c1.volume_samples, c1.distance_samples, c1.covered_pixels) == (c0.volume_samples, c0.distance_samples, c0.covered_pixels)
+    # a depth attachment that holds "far" everywhere (0 in reverse-Z) neither discards nor shortens anything
+    far, c2, rf, d2 = orc.render(*args, RenderOptions(skipping_type=SKIP_DISTANCE, clip_distance=5.0, load_framebuffer=1, depth_attachment=1),
+                                 96, 96, want_float=True, rgba_init=clear, depth_init=zero)
+    assert not (rf[..., 3] == -2.0).any()
+    assert np.array_equal(far, plain) and np.array_equal(d2, d0) and c2.volume_samples == c0.volume_samples
+
+
+def test_depth_attachment_in_front_of_the_volume_discards_everything_and_blend_is_over():
+    s = _scene()
+    args = (s["V"], s["G"], s["tf"], None, s["dim_b"], s["cu"], s["ru"], s["tfu"])
+    rng = np.random.default_rng(2)
+    bg = rng.integers(0, 256, size=(64, 64, 4), dtype=np.uint8)
+    near = np.ones((64, 64), np.float32)        # reverse-Z: 1 = the near plane, in front of every fragment
+    img, c, rf, dp = orc.render(*args, RenderOptions(skipping_type=SKIP_NONE, clip_distance=5.0, load_framebuffer=1, depth_attachment=1), 64, 64,
+                                want_float=True, rgba_init=bg, depth_init=near)
+    cov = rf[..., 3] != -1.0
+    assert cov.sum() > 200 and (rf[..., 3][cov] == -2.0).all()        # every covered fragment discarded
+    assert np.array_equal(img, bg) and np.array_equal(dp, near) and c.volume_samples == 0
+    # the blend itself: rgb = src.rgb + dst.rgb * (1 - src.a) on linear values of an sRGB target, a = src.a * (1 - src.a)
+    img2, _, rf2, _ = orc.render(*args, RenderOptions(skipping_type=SKIP_NONE, clip_distance=5.0, load_framebuffer=1), 64, 64,
+                                 want_float=True, rgba_init=bg, depth_init=np.zeros((64, 64), np.float32))
+    def dec(b):
+        c_ = b.astype(np.float64) / 255.0
+        return np.where(c_ <= 0.04045, c_ / 12.92, ((c_ + 0.055) / 1.055) ** 2.4)
+    def enc(l):
+        l = np.clip(l, 0, 1)
+        return np.where(l <= 0.0031308, 12.92 * l, 1.055 * l ** (1 / 2.4) - 0.055)
+    sa = np.clip(rf2[..., 3:4].astype(np.float64), 0, 1)
+    want = np.floor(np.clip(enc(np.clip(rf2[..., :3], 0, 1) + dec(bg[..., :3]) * (1 - sa)), 0, 1) * 255 + 0.5)
+    got = img2[..., :3].astype(np.float64)
+    assert np.abs(got[cov] - want[cov]).max() <= 1        # fp32 vs fp64 evaluation of the same formula
+    assert np.array_equal(img2[~cov], bg[~cov])
+    a_want = np.floor(sa[..., 0] * (1 - sa[..., 0]) * 255 + 0.5)
+    assert np.abs(img2[..., 3].astype(np.float64)[cov] - a_want[cov]).max() <= 1
