@@ -189,8 +189,10 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 	// With a history (the previous frame of this volume at this frame size) the tiles are issued in decreasing order of the loop
 	// count their longest ray needed last time: the frame time is the critical path of a few hundred long warps (profiles/
 	// r1s_trace.md), so they have to start at t = 0, not whenever the sweep reaches them.
+	// (compiled into the distance-map production variants only: the other modes are throughput-bound and keep their old code)
+	constexpr bool kHist = (SKIP == VKV_SKIP_DISTANCE || SKIP == VKV_SKIP_ANISOTROPIC_DISTANCE) && !OTF && !EXACT && !LOAD;
 	const int seq        = P.seq_base + (int) blockIdx.z;
-	const int local_tile = P.tile_order ? (int) P.tile_order[seq] : centre_out(seq, P.my_tiles);
+	const int local_tile = (kHist && P.tile_order) ? (int) P.tile_order[seq] : centre_out(seq, P.my_tiles);
 	const int tile       = P.tile_first + local_tile * P.tile_stride;
 	const int tile_y = P.tiles_x_magic ? (int) __umulhi((unsigned) tile, P.tiles_x_magic) : tile / P.tiles_x, tile_x = tile - tile_y * P.tiles_x;
 	const int tx0 = tile_x * P.tile_w + (int) blockIdx.x * 16;
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 					int      pre_base = -0x40000000;
 					float pre_v0 = 0.0f, pre_v1 = 0.0f, pre_v2 = 0.0f, pre_v3 = 0.0f, pre_g0 = 1.0f, pre_g1 = 1.0f, pre_g2 = 1.0f, pre_g3 = 1.0f;
 					for (int i = 0; i < n_steps;) {
-						++n_iter;
+						if (kHist || TRACE) ++n_iter;
 						if (TRACE) tc_mark = clock64();
 						const float fi     = (float) i;
 						const float pos[3] = {entry[0] + fi * step[0], entry[1] + fi * step[1], entry[2] + fi * step[2]};
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 							k                = i - pre_base;
 							const bool vmode = !do_skip;
 							const bool need  = vmode && (unsigned) k >= 4u;
-							any_refill       = __any_sync(__activemask(), need);
+							if (SKIP != VKV_SKIP_BLOCK || TRACE) any_refill = __any_sync(__activemask(), need);        // BLOCK refills per lane: no vote
 							if (SKIP == VKV_SKIP_BLOCK ? need : (any_refill && vmode && k != 0)) {
 								pre_base = i;
 								k        = 0;
@@ -520,7 +522,7 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 		}
 	}
 
-	if (P.tile_cost) {
+	if (kHist && P.tile_cost) {
 		const unsigned it_warp = __reduce_max_sync(0xffffffffu, n_iter);
 		if (lane == 0 && it_warp) atomicMax(P.tile_cost + local_tile, it_warp);
 	}
@@ -808,7 +810,7 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 		const char *no_hist  = getenv("VKV_RC_NO_HISTORY");
 		// distance-map modes only: block skipping and ESS off are throughput-bound at every size measured (promotion costs them 2 %)
 		const bool  use_hist = !(no_hist && atoi(no_hist) != 0) && my_tiles >= 64 && my_tiles <= 6000 &&
-		                       (opt->skipping_type == VKV_SKIP_DISTANCE || opt->skipping_type == VKV_SKIP_ANISOTROPIC_DISTANCE);
+		                       (opt->skipping_type == VKV_SKIP_DISTANCE || opt->skipping_type == VKV_SKIP_ANISOTROPIC_DISTANCE) && !otf && !exact && !load;
 		const int   key[8]   = {width, height, tile_w, tile_h, tile_first, tile_stride, my_tiles, opt->skipping_type};
 		if (use_hist) {
 			if (vol->tile_hist_capacity < my_tiles) {
