@@ -600,6 +600,9 @@ def test_render_to_host_async_pipeline_equals_blocking_calls(ctx):
         img, c = vol.render_to_host(cu, ru, sc["tfu"], ropt, width, height)
         assert np.array_equal(frames[k].numpy(), img), k
         assert counts[k].tolist() == [c.volume_samples, c.distance_samples, c.empty_samples, c.covered_pixels]
+    pageable = np.empty((height, width, 4), np.uint8)
+    with pytest.raises(capi.VkvError):        # pageable destinations are refused, not silently made synchronous
+        vol.render_to_host_async(views[0][0], views[0][1], sc["tfu"], ropt, width, height, pageable.ctypes.data)
     vol.close()
 
 

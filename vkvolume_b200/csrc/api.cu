@@ -536,6 +536,15 @@ int vkv_render_to_host_async(vkv_volume *vol, const vkv_camera_uniform *cam, con
 {
 	VKV_REQUIRE(vol && cam && ray && tfu && opt && rgba8_host, VKV_ERR_ARGUMENT, "vkv_render_to_host_async: NULL argument");
 	VKV_REQUIRE(!opt->load_framebuffer && !opt->depth_attachment, VKV_ERR_ARGUMENT, "vkv_render_to_host_async renders over the clear colour only");
+	{
+		// pageable destinations would turn the asynchronous copies into blocking ones (and the caller's buffers may go away): refuse them
+		cudaPointerAttributes a{};
+		const bool fb_pinned = cudaPointerGetAttributes(&a, rgba8_host) == cudaSuccess && a.type == cudaMemoryTypeHost;
+		bool       c_pinned  = true;
+		if (counts_host) c_pinned = cudaPointerGetAttributes(&a, counts_host) == cudaSuccess && a.type == cudaMemoryTypeHost;
+		cudaGetLastError();
+		VKV_REQUIRE(fb_pinned && c_pinned, VKV_ERR_ARGUMENT, "vkv_render_to_host_async: rgba8_host and counts_host must be page-locked host memory");
+	}
 	int rc;
 	if ((rc = check_render(vol, tfu, opt, width, height, 64, 32, 1, false))) return rc;
 	DeviceGuard  guard(vol->ctx->device);
