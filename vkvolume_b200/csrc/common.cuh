@@ -72,6 +72,17 @@ struct vkv_context {
 	cudaDeviceProp prop{};
 };
 
+// cudaFuncSetAttribute applies to the current device only: a process that drives several devices through the C ABI must opt in
+// to the large dynamic shared-memory sizes once per (kernel instantiation, device), not once per process.
+struct PerDeviceOnce {
+	std::atomic<unsigned long long> mask{0ull};
+	bool first(int device)
+	{
+		const unsigned long long bit = 1ull << (device & 63);
+		return (mask.fetch_or(bit) & bit) == 0ull;
+	}
+};
+
 struct vkv_volume {
 	vkv_context *ctx = nullptr;
 	uint32_t     dim[3]{};         // W H D voxels

@@ -632,10 +632,9 @@ static int run_minmax(const vkv_volume *vol, int axis, const uint8_t *src, uint8
 	while (TW > 8 && (size_t) nlev * L * TW > (size_t) 200 * 1024) TW >>= 1;
 	const size_t smem = (size_t) nlev * L * TW;
 	if (smem <= (size_t) 200 * 1024) {
-		static bool configured = false;        // opt in to > 48 KB of dynamic shared memory once per instantiation
-		if (!configured) {
+		static PerDeviceOnce configured;        // opt in to > 48 KB of dynamic shared memory once per instantiation
+		if (configured.first(vol->ctx->device)) {
 			VKV_CUDA_CHECK(cudaFuncSetAttribute(minmax_rmq_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-			configured = true;
 		}
 		const dim3 grid_rmq((Wb + TW - 1) / TW, axis == 1 ? Db : Hb);
 		minmax_rmq_kernel<MODE><<<grid_rmq, 256, smem, s>>>(src, dst0, dst1, Wb, L, line_stride, outer_stride, TW, nlev);
@@ -659,10 +658,9 @@ static int run_ysweep(const vkv_volume *vol, const uint8_t *g, uint8_t *dst0, ui
 		return VKV_OK;        // otherwise the search kernel
 	const int    threads = (int) ((Wb / 4 + 31u) / 32u * 32u);
 	const size_t smem    = (size_t) kSweepSlots * kSweepRows * Wb + 2 * ((size_t) Wb / 4 + 2) * sizeof(uint2) + 16;
-	static bool configured = false;
-	if (!configured) {
+	static PerDeviceOnce configured;
+	if (configured.first(vol->ctx->device)) {
 		VKV_CUDA_CHECK(cudaFuncSetAttribute(ysweep_kernel<XDIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-		configured = true;
 	}
 	ysweep_kernel<XDIR><<<Db, threads, smem, s>>>(g, dst0, dst1, Wb, Hb);
 	VKV_LAUNCHED();
@@ -688,10 +686,9 @@ static int run_zwalk(const vkv_volume *vol, const uint8_t *src, uint8_t *dst0, u
 	if (per_col * TW <= (size_t) 50 * 1024 && Wb >= 64 && L >= 4u * kWalkSeg) TW = 64;
 	const size_t smem = per_col * TW;
 	if (smem > (size_t) 200 * 1024) return VKV_OK;
-	static bool configured = false;
-	if (!configured) {
+	static PerDeviceOnce configured;
+	if (configured.first(vol->ctx->device)) {
 		VKV_CUDA_CHECK(cudaFuncSetAttribute(zwalk_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-		configured = true;
 	}
 	const int  nseg    = (int) ((L + kWalkSeg - 1) / kWalkSeg);
 	const int  threads = std::min(1024, std::max(64, (2 * nseg * TW + 31) / 32 * 32));

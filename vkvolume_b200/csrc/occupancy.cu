@@ -515,11 +515,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1) occupancy_tma_kernel(const __g
 template <bool USE_G, bool COUNT>
 static int launch_tma_inst(vkv_volume *vol, uint8_t *O, uint32_t zb_first, uint32_t zb_count, unsigned long long *count_dev, cudaStream_t s)
 {
-	static bool configured = false;
-	if (!configured) {
+	static PerDeviceOnce configured;
+	if (configured.first(vol->ctx->device)) {
 		VKV_CUDA_CHECK(cudaFuncSetAttribute(occupancy_tma_kernel<USE_G, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 		                                    (int) TmaCfg<USE_G>::kSmemBytes));
-		configured = true;
 	}
 	occupancy_tma_kernel<USE_G, COUNT><<<vol->ctx->sm_count, kTmaThreads, TmaCfg<USE_G>::kSmemBytes, s>>>(
 	    *reinterpret_cast<const CUtensorMap *>(vol->tmap_V), *reinterpret_cast<const CUtensorMap *>(USE_G ? vol->tmap_G : vol->tmap_V), vol->d_mask2,
