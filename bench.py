@@ -65,6 +65,21 @@ UNIT = "Msamples/s"
 TILE_W, TILE_H = 64, 32
 
 
+def sweep_options(wl, k: int):
+    """TF setting k of BASELINE.json config 4's sweep: imin = 0.05 + 0.004 k, the gradient window alternating
+    between off (0, 0) and (0.05, 0.25)."""
+    from vkvolume_b200.capi import VolumeOptions
+    gmin, gmax = ((0.0, 0.0), (0.05, 0.25))[k & 1]
+    return VolumeOptions(intensity_min=0.05 + 0.004 * k, intensity_max=1.0, gradient_min=gmin, gradient_max=gmax)
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def orbit_eye(step: int, n: int, wl) -> tuple:
     """Camera positions on a tilted circle around the volume (world units; node scale 100)."""
     W, H, D = wl["dim"]
@@ -132,6 +147,84 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def tiles_8k_series(ctx, torch, dist, capi, scene, sharding, rank, world, dev, stream, flush_l2, barrier, ev, name="c5s", frames=10):
+    """N > 1, every workload whose headline is not already the tile decomposition: BASELINE.json config 5's sharding on record —
+    one 7680x4320 frame cut into 64x32 tiles dealt round-robin to the ranks (full replica per rank, peer stores into rank 0's
+    frame), beside rank 0 casting the whole frame alone, and a byte-for-byte comparison of the two frames.  `c5s` (2048x2048x1024,
+    same generator and TF as config 5) keeps the set-up to a second; `c5` itself runs through --workload c5."""
+    import ctypes as C
+    from vkvolume_b200.capi import RenderOptions, VolumeOptions
+    wl = WORKLOADS[name]
+    W, H, D = wl["dim"]
+    FW, FH = wl["frame"]
+    vol = capi.Volume(ctx, W, H, D, block_size=4)
+    capi.synth_volume(ctx, wl["kind"], wl["seed"], W, H, D, vol.device_voxels(), stream)
+    vol.upload_device(vol.device_voxels(), stream)
+    opt = VolumeOptions(**wl["tf"])
+    tfu = capi.transfer_function_uniform(opt)
+    vol.compute_gradient_map(tfu, stream)
+    vol.update_transfer_function(opt, wl["skip"], stream=stream)
+    it = scene.image_transform(wl["voxel"], wl["dim"], wl["axis_angle"])
+    ropt = RenderOptions(skipping_type=wl["skip"], clip_distance=wl["clip"], early_ray_termination=1)
+    fb = torch.zeros((FH, FW, 4), dtype=torch.uint8, device=dev) if rank == 0 else None
+    own = torch.zeros((FH, FW, 4), dtype=torch.uint8, device=dev)        # private frame: the single-GPU series
+    handle = [None]
+    if rank == 0:
+        hbuf = (C.c_uint8 * capi.IPC_HANDLE_BYTES)()
+        capi.check(capi.lib().vkv_ipc_export(C.c_void_p(fb.data_ptr()), hbuf))
+        handle = [bytes(hbuf)]
+    dist.broadcast_object_list(handle, src=0)
+    peer = None
+    if rank == 0:
+        target = fb.data_ptr()
+    else:
+        hbuf = (C.c_uint8 * capi.IPC_HANDLE_BYTES).from_buffer_copy(handle[0])
+        p = C.c_void_p()
+        capi.check(capi.lib().vkv_ipc_open(hbuf, C.byref(p)))
+        peer = target = p.value
+    views = [vol.make_uniforms(scene.look_at_camera(orbit_eye(k, 72, wl), aspect=FW / FH), it, wl["clip"]) for k in range(frames + 3)]
+
+    def series(fn):
+        ts = []
+        for k in range(frames + 3):
+            flush_l2()
+            a, b = ev(), ev()
+            a.record()
+            fn(k)
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        t = torch.tensor(ts[3:], dtype=torch.float64, device=dev)
+        return t
+
+    barrier()
+    t_n = series(lambda k: vol.render_tiles(views[k][0], views[k][1], tfu, ropt, FW, FH, TILE_W, TILE_H, rank, world, target, 0, 0, stream))
+    dist.all_reduce(t_n, op=dist.ReduceOp.MAX)        # a frame is done when the slowest rank's tiles are
+    barrier()
+    t_1 = series(lambda k: vol.render(views[k][0], views[k][1], tfu, ropt, FW, FH, own.data_ptr(), 0, 0, stream))
+    dist.all_reduce(t_1, op=dist.ReduceOp.MAX)        # the slowest of N independent single-GPU runs (they run concurrently on one box)
+    # frame check on one view
+    if rank == 0:
+        fb.zero_()
+    barrier()
+    vol.render_tiles(views[5][0], views[5][1], tfu, ropt, FW, FH, TILE_W, TILE_H, rank, world, target, 0, 0, stream)
+    barrier()
+    match = None
+    if rank == 0:
+        vol.render(views[5][0], views[5][1], tfu, ropt, FW, FH, own.data_ptr(), 0, 0, stream)
+        torch.cuda.synchronize()
+        match = bool(torch.equal(own, fb))
+    barrier()
+    if peer:
+        capi.check(capi.lib().vkv_ipc_close(C.c_void_p(peer)))
+    barrier()
+    vol.close()
+    ms_n, ms_1 = float(t_n.median().item()), float(t_1.median().item())
+    return {"workload": wl["name"], "frame": [FW, FH], "tiles": [TILE_W, TILE_H], "frames_timed": frames, "ms_per_frame_N": ms_n, "ms_per_frame_1": ms_1,
+            "speedup": ms_1 / ms_n, "frame_matches": match, "n_gpus": world,
+            "timing": "CUDA events per frame on every rank, max over ranks per frame, median over frames; 256 MiB L2 flush before each frame (untimed)"}
+
+
 # ======================================================================================================
 # native arm
 # ======================================================================================================
@@ -192,8 +285,9 @@ def run_native(args):
         flush_buf.fill_(1)        # 256 MiB write > 126 MB L2
 
     # ---- one-off: gradient map (K1) ------------------------------------------------------------------
+    # (computed with use_gradient = true whatever the workload's TF says — SURVEY A.8.1: harnesses pass true — so that the TF sweep
+    # below can switch the gradient window on; kernels ignore G while tfu.use_gradient is 0)
     t_grad = timed(lambda: vol.compute_gradient_map(capi.transfer_function_uniform(VolumeOptions(gradient_min=0.0, gradient_max=0.2)), stream), reps=3, flush=flush_l2)
-    vol.compute_gradient_map(tfu, stream)        # the map the TF actually asks for (all 255 when gradients are off)
 
     # ---- TF-change rebuild (K2a [+K2b] + K3) ------------------------------------------------------------
     def rebuild_single(count=False, o=opt):
@@ -224,6 +318,23 @@ def run_native(args):
     rebuild = rebuild_sharded if world > 1 else rebuild_single
     rebuild()
     torch.cuda.synchronize()
+    # untimed self-check (N > 1): the z-slab rebuild must reproduce this rank's own single-GPU maps and the voxel count, bit for bit
+    sharded_rebuild_matches = None
+    if world > 1:
+        Wb, Hb, Db = vol.map_extent
+        n_maps = 8 if skip == 3 else 1
+        got = [torch.as_tensor(_DevPtr(vol.device_distance_map(i), Wb * Hb * Db), device=dev).clone() for i in range(n_maps)]
+        got_count = int(count_t.item())
+        want_count = rebuild_single(True)
+        ok = got_count == want_count
+        for i in range(n_maps):
+            ok = ok and bool(torch.equal(got[i], torch.as_tensor(_DevPtr(vol.device_distance_map(i), Wb * Hb * Db), device=dev)))
+        okt = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        sharded_rebuild_matches = bool(okt.item())
+        del got
+        rebuild()
+        torch.cuda.synchronize()
     # sweep: 100 TF changes in config 4's pattern (imin = base + 0.004 k), fewer when asked to be quick
     n_changes = args.tf_changes
     rebuild_ms = []
@@ -242,11 +353,59 @@ def run_native(args):
     # stage breakdown of one rebuild (single-GPU only)
     stage_ms = {}
     if world == 1:
+        occ = lambda: vol.compute_occupancy_slab(tfu, skip, 0, vol.map_extent[2], stream=stream)
         stage_ms["tf_texture_and_masks"] = float(np.median(timed(lambda: vol.update_transfer_function_texture(opt, stream), 5)))
-        stage_ms["occupancy"] = float(np.median(timed(lambda: vol.compute_occupancy_slab(tfu, skip, 0, vol.map_extent[2], stream=stream), 5, flush_l2)))
-        stage_ms["distance"] = float(np.median(timed(lambda: vol.compute_distance_from_occupancy(skip, stream), 5)))
-        vol.compute_occupancy_slab(tfu, skip, 0, vol.map_extent[2], stream=stream)
+        stage_ms["occupancy"] = float(np.median(timed(occ, 5, flush_l2)))
+        # the same kernel timed as a train of 8 launches between one pair of events when its input cannot stay in the L2 (every launch
+        # streams V [and G] from HBM again): takes the ~10 us of event + call overhead per launch out of a 60-90 us kernel
+        bytes_in = (2 if use_g else 1) * N_vox
+        if bytes_in > 2 * 126e6:
+            occ()
+            a, b = ev(), ev()
+            a.record()
+            for _ in range(8):
+                occ()
+            b.record()
+            b.synchronize()
+            stage_ms["occupancy_back_to_back"] = a.elapsed_time(b) / 8
+        # the distance transform consumes (overwrites) the occupancy map: rebuild it, untimed, before every timed repetition
+        stage_ms["distance"] = float(np.median(timed(lambda: vol.compute_distance_from_occupancy(skip, stream), 5, flush=lambda: (occ(), flush_l2()))))
+        occ()
         vol.compute_distance_from_occupancy(skip, stream)
+
+    # ---- BASELINE.json config 4's sweep, as specified: every change = TF texture + occupancy + voxel count
+    # (host-synchronous, as VolumeRender::update_transfer_function logs it) + distance map, then one frame ----------------------
+    tf_sweep = None
+    if world == 1 and args.tf_changes > 0:
+        n_sw = args.tf_changes
+        sweep_fb = torch.zeros((FH, FW, 4), dtype=torch.uint8, device=dev)
+        it_sw = scene.image_transform(wl["voxel"], wl["dim"], wl["axis_angle"])
+        ropt_sw = RenderOptions(skipping_type=skip, clip_distance=wl["clip"], early_ray_termination=1)
+        cam_sw = scene.look_at_camera(orbit_eye(0, 72, wl), aspect=FW / FH)
+        cu_sw, ru_sw = vol.make_uniforms(cam_sw, it_sw, wl["clip"])
+        reb, ren, occ_pct = [], [], []
+        for k in range(n_sw):
+            o = sweep_options(wl, k)
+            u = capi.transfer_function_uniform(o)
+            flush_l2()
+            a, b, c = ev(), ev(), ev()
+            a.record()
+            n_occ = vol.update_transfer_function(o, skip, count=True, stream=stream)
+            b.record()
+            vol.render(cu_sw, ru_sw, u, ropt_sw, FW, FH, sweep_fb.data_ptr(), 0, 0, stream)
+            c.record()
+            c.synchronize()
+            reb.append(a.elapsed_time(b))
+            ren.append(b.elapsed_time(c))
+            occ_pct.append(100.0 * n_occ / N_vox)
+        tf_sweep = {"changes": n_sw, "pattern": "imin = 0.05 + 0.004 k, (gmin, gmax) alternating (0, 0) / (0.05, 0.25); each change: TF texture + occupancy + "
+                                                "voxel count (host-synchronous read-back) + distance map, then one frame of the headline view",
+                    "rebuild_ms": {"median": float(np.median(reb)), "mean": float(np.mean(reb)), "p95": float(np.percentile(reb, 95)),
+                                   "median_gradient_off": float(np.median(reb[0::2])), "median_gradient_on": float(np.median(reb[1::2])) if n_sw > 1 else None},
+                    "render_ms": {"median": float(np.median(ren)), "mean": float(np.mean(ren))},
+                    "occupied_percent_first_last": [occ_pct[0], occ_pct[-1]], "l2": "256 MiB flush write before every change (untimed)"}
+        del sweep_fb
+        rebuild()        # back to the workload's TF
 
     # ---- frame buffer + peer mapping -------------------------------------------------------------------
     it = scene.image_transform(wl["voxel"], wl["dim"], wl["axis_angle"])
@@ -367,7 +526,7 @@ def run_native(args):
                 ts.append(a.elapsed_time(b))
             c = counts_t.tolist()
             modes[mname] = {"ms_per_frame": float(np.mean(ts)), "msamples_per_s": (c[0] + c[1]) / (sum(ts) * 1e-3) / 1e6,
-                            "samples_per_frame": (c[0] + c[1]) / nviews}
+                            "samples_per_frame": (c[0] + c[1]) / nviews, "volume_samples_per_frame": c[0] / nviews}
         vol.update_transfer_function(opt, skip, stream=stream)
 
     # ---- e2e through the host-buffer C-ABI call (rank 0's view at N = 1; tiles + gather at N > 1) ---------------
@@ -461,6 +620,11 @@ def run_native(args):
                "ms_per_frame": tt.item() * 1e3 / ke, "steps": ke,
                "note": "tiles rendered on all ranks with peer stores into rank 0, barrier, rank 0 copies the frame to pinned host memory"}
 
+    # ---- driver-visible tile-sharded 8K series (N > 1; not when the headline already is that decomposition) -----------------
+    tiles_8k = None
+    if world > 1 and (frames_mode or FW * FH < 16_000_000) and not args.no_tiles_8k:
+        tiles_8k = tiles_8k_series(ctx, torch, dist, capi, scene, sharding, rank, world, dev, stream, flush_l2, barrier, ev)
+
     # ---- roofline --------------------------------------------------------------------------------------------------
     hbm_peak, peak_src = measured_peaks()
     gamma = 1 if use_g else 0
@@ -474,9 +638,18 @@ def run_native(args):
             tex_peak = {"error": str(e)}
     roofline = None
     if rank == 0:
+        # Units: the denominator is the FILTERED-FETCH rate of the texture pipe (vkv_bench_tex3d, measured live), so the numerator
+        # counts only what goes through that pipe: n_vol * (1 + gamma) filtered fetches of 8 texels each.  The TF-table read (one
+        # 16-byte read-only load per volume sample) and the skip-map bytes (one byte load per distance sample) use the LSU path and
+        # are reported beside it, as is SURVEY 8(d)'s mixed byte figure for continuity with round 1.
         peak_fetch = tex_peak.get("l2_resident_256") if isinstance(tex_peak, dict) else None
-        achieved = texel_bytes_per_step / (ms_per_step * 1e-3) / 1e9
+        launches_per_step = max(world, 1)
+        fetches_per_launch = n_vol * (1 + gamma) / K / launches_per_step
+        t_launch = ms_per_step * 1e-3
+        fetch_rate = fetches_per_launch / t_launch
+        achieved = fetch_rate * 8 / 1e9
         peak = peak_fetch * 8 / 1e9 if peak_fetch else None
+        survey_bytes = texel_bytes_per_step
         traffic = None
         tj = ROOT / "profiles" / "traffic.json"
         if tj.exists() and args.workload == "c2" and world == 1:
@@ -484,8 +657,19 @@ def run_native(args):
         roofline = {"kernel": "raycast_kernel", "bound": "texture", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": (achieved / peak) if peak else None, "traffic": traffic,
                     "peak_source": "vkv_bench_tex3d measured live: coherent trilinear u8 tex3D fetches/s on an L2-resident 256^3 array x 8 texel bytes per fetch",
-                    "algorithmic_bytes_per_launch": texel_bytes_per_step,
-                    "definition": "n_vol*(8*(1+gamma)+4)+n_dist texel bytes per frame (SURVEY 8(d))"}
+                    "algorithmic_bytes_per_launch": fetches_per_launch * 8,
+                    "definition": "filtered texel bytes = n_vol*(1+gamma) trilinear fetches x 8 texels x 1 B per frame, over the frame time; same fraction as fetches/s over the fetch peak",
+                    "filtered_fetches_per_launch": fetches_per_launch, "achieved_fetches_per_s": fetch_rate, "peak_fetches_per_s": peak_fetch,
+                    "frac_fetch": (fetch_rate / peak_fetch) if peak_fetch else None,
+                    "lsu_side": {"tf_table_bytes_per_launch": n_vol * 16 / K / launches_per_step, "skip_map_bytes_per_launch": n_dist / K / launches_per_step},
+                    "survey_8d_mixed_bytes": {"bytes_per_launch": survey_bytes, "achieved": survey_bytes / t_launch / 1e9,
+                                              "frac_of_texture_byte_peak": (survey_bytes / t_launch / 1e9 / peak) if peak else None,
+                                              "note": "n_vol*(8*(1+gamma)+4)+n_dist: round 1's figure; mixes TF and skip-map bytes into a texture-pipe denominator"},
+                    "regime": "latency-bound with ESS + ERT on (a few dependent fetches per ray); modes.none is the throughput-bound configuration"}
+        if modes.get("none"):
+            mn = modes["none"]
+            fr = mn["volume_samples_per_frame"] * (1 + gamma) / (mn["ms_per_frame"] * 1e-3)
+            roofline["modes_none"] = {"achieved_fetches_per_s": fr, "frac_fetch": (fr / peak_fetch) if peak_fetch else None}
     hbm_rooflines = {}
     if world == 1:
         def rl(bytes_, ms):
@@ -503,7 +687,12 @@ def run_native(args):
     # ---- CPU baseline (oracle port on the host cores; bounded sample) ------------------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = cpu_baseline_from_device(vol, wl, opt, tfu, ropt, it, FW, FH, skip, uniforms)
+        def gpu_frame(view):
+            cu, ru = uniforms(view)
+            vol.render(cu, ru, tfu, ropt, FW, FH, fb_ptr, 0, 0, stream)
+            torch.cuda.synchronize()
+            return fb.cpu().numpy()
+        cpu_baseline = cpu_baseline_from_device(vol, wl, opt, tfu, ropt, it, FW, FH, skip, uniforms, gpu_frame)
 
     if rank == 0:
         line = {
@@ -522,7 +711,8 @@ def run_native(args):
             "ess_rebuild_ms": {"median": float(np.median(rebuild_ms)), "mean": float(np.mean(rebuild_ms)), "p95": float(np.percentile(rebuild_ms, 95)),
                                "changes": n_changes, "stages": stage_ms, "sharded_z_slabs": world > 1},
             "occupied_voxels": occupied, "occupied_percent": 100.0 * occupied / N_vox,
-            "modes": modes, "tiles_match_single_gpu_frame": tiles_match, "e2e": e2e, "gpu_launches": int(launches), "wall_s_timed_region": wall,
+            "modes": modes, "tiles_match_single_gpu_frame": tiles_match, "sharded_rebuild_matches": sharded_rebuild_matches,
+            "tiles_8k": tiles_8k, "tf_sweep": tf_sweep, "e2e": e2e, "gpu_launches": int(launches), "wall_s_timed_region": wall,
             "clocks": sampler.summary(), "roofline": roofline, "rooflines_hbm": hbm_rooflines, "tex3d_fetch_per_s": tex_peak,
             "cpu_baseline": cpu_baseline,
         }
@@ -552,19 +742,22 @@ def cpu_render_sample(orc, V, G, tf, maps, dim_b, tfu, ropt, FW, FH, uniforms_fn
     per8 = time.perf_counter() - t0
     rows = int(min(FH, max(8, 8 * budget_s / max(per8, 1e-4))))
     y0 = max(0, FH // 2 - rows // 2)
-    n, dt, views = 0, 0.0, 0
+    n, dt, views, kept = 0, 0.0, 0, []
     while dt < budget_s and views < 720:
         cu, ru = uniforms_fn(views)
         t0 = time.perf_counter()
-        _, c, _, _ = orc.render(V, G, tf, maps, dim_b, cu, ru, tfu, ropt, FW, FH, y_first=y0, y_count=rows)
+        img, c, _, _ = orc.render(V, G, tf, maps, dim_b, cu, ru, tfu, ropt, FW, FH, y_first=y0, y_count=rows)
         dt += time.perf_counter() - t0
         n += c.volume_samples + c.distance_samples
+        if len(kept) < 8 and views % 9 == 0:
+            kept.append((views, img[y0:y0 + rows].copy()))
         views += 1
-    return n / dt / 1e6, dt, rows, n, views
+    return n / dt / 1e6, dt, rows, n, views, y0, kept
 
 
-def cpu_baseline_from_device(vol, wl, opt, tfu, ropt, it, FW, FH, skip, uniforms_fn):
+def cpu_baseline_from_device(vol, wl, opt, tfu, ropt, it, FW, FH, skip, uniforms_fn, gpu_frame_fn=None):
     orc = _oracle()
+    orc.set_num_threads(host_cores())        # all host cores, whatever OMP_NUM_THREADS the launcher exported
     V = vol.download_voxels()
     G = vol.download_gradient() if tfu.use_gradient else None
     tf = vol.download_transfer_function()
@@ -573,9 +766,23 @@ def cpu_baseline_from_device(vol, wl, opt, tfu, ropt, it, FW, FH, skip, uniforms
         maps = np.stack([vol.download_distance_map(i) for i in range(8)])
     elif skip != 0:
         maps = vol.download_distance_map(0)
-    v, dt, rows, n, views = cpu_render_sample(orc, V, G, tf, maps, vol.map_extent, tfu, ropt, FW, FH, uniforms_fn)
-    return {"value": v, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
-            "sample": f"oracle ray caster (OpenMP, {orc.num_threads()} threads) on {rows} of {FH} rows of {views} orbit views of the same workload: {n} samples in {dt:.2f} s"}
+    v, dt, rows, n, views, y0, frames = cpu_render_sample(orc, V, G, tf, maps, vol.map_extent, tfu, ropt, FW, FH, uniforms_fn)
+    out = {"value": v, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+           "sample": f"oracle ray caster (OpenMP, {orc.num_threads()} threads) on {rows} of {FH} rows of {views} orbit views of the same workload: {n} samples in {dt:.2f} s"}
+    # the frames the oracle just rendered are compared (untimed) with the GPU's frames of the same views — the north-star bar
+    if gpu_frame_fn is not None and frames:
+        fr, ps, fa = [], [], []
+        for view, ref in frames:
+            img = gpu_frame_fn(view)[y0:y0 + rows]
+            d = np.abs(img[..., :3].astype(np.int16) - ref[..., :3].astype(np.int16)).max(axis=2)
+            fr.append(float((d <= 1).mean()))
+            fa.append(float((np.abs(img[..., 3].astype(np.int16) - ref[..., 3].astype(np.int16)) <= 1).mean()))
+            mse = float(np.mean((img[..., :3].astype(np.float64) - ref[..., :3].astype(np.float64)) ** 2))
+            ps.append(99.0 if mse == 0 else 10 * math.log10(255.0 ** 2 / mse))
+        out["frame_parity"] = {"views_compared": len(frames), "rows": [y0, y0 + rows], "frac_within_1": min(fr), "psnr": min(ps), "alpha_frac_within_1": min(fa),
+                               "bar": "<= 1/255 per channel on >= 99.9 % of pixels, PSNR >= 50 dB (minimum over the views compared; hardware filter vs the oracle)",
+                               "passes": bool(min(fr) >= 0.999 and min(ps) >= 50.0)}
+    return out
 
 
 def run_reference(args):
@@ -584,6 +791,12 @@ def run_reference(args):
     if rank != 0:
         return
     orc = _oracle()
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: the CPU arm must use the whole host at every N, or the
+    # ratios the driver computes at N > 1 are against one core.  Set explicitly, then verified below.
+    cores = host_cores()
+    orc.set_num_threads(cores)
+    if orc.num_threads() != cores:
+        raise RuntimeError(f"the oracle runs on {orc.num_threads()} threads, the host has {cores} cores: refusing to emit a line")
     from vkvolume_b200 import scene
     from vkvolume_b200.capi import RenderOptions, VolumeOptions
     wl = WORKLOADS[args.workload]
@@ -676,6 +889,7 @@ def main():
     ap.add_argument("--tf-changes", type=int, default=100)
     ap.add_argument("--quick", action="store_true", help="skip the per-mode table")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tiles-8k", action="store_true", help="N > 1: skip the extra tile-sharded 8K series")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = 6 if args.steps is None else args.steps

@@ -9,6 +9,15 @@
  * Every entry point below names the reference interface it replaces (file:line,
  * relative to the reference repository root).
  *
+ * Stream model: a vkv_volume's device state (TF texture, masks, colour table,
+ * tile-scheduling history, counters, maps, scratch frames) belongs to one stream
+ * at a time, like the reference's single in-flight command buffer.  A call that
+ * arrives on a different stream than the volume's previous call is ordered, by
+ * the library, after everything that previous stream had been given (an event
+ * record + wait): alternating streams on one volume serialises, it never races.
+ * Different volumes are independent.  Calling into ONE volume from several host
+ * threads at the same time is not supported (the reference is single-threaded).
+ *
  * Rules of the boundary: plain C, opaque handles, plain pointers and sizes, int
  * status codes (0 == VKV_OK) with a thread-local message behind vkv_last_error();
  * nothing throws across it.  There is NO CPU fallback: every compute entry point
@@ -251,6 +260,12 @@ VKV_API int vkv_update_transfer_function(vkv_volume *vol, const vkv_volume_optio
 /* Host maths of VolumeRenderSubpass::draw (src/volume_render_subpass.cpp:219-249). */
 VKV_API int vkv_make_uniforms(const vkv_volume *vol, const vkv_camera_desc *cam, const float image_transform[16],
                               float clip_distance, vkv_camera_uniform *cam_out, vkv_ray_cast_uniform *ray_out);
+/* The same host maths from the extents alone (volume extent W,H,D and map extent
+ * ceil(dim / block_size), src/volume_render_subpass.cpp:243-249): needs no device
+ * and no volume handle. */
+VKV_API int vkv_make_uniforms_for_extent(const uint32_t extent[3], const uint32_t map_extent[3], const vkv_camera_desc *cam,
+                                         const float image_transform[16], float clip_distance, vkv_camera_uniform *cam_out,
+                                         vkv_ray_cast_uniform *ray_out);
 
 /* VolumeRenderSubpass::draw (src/volume_render_subpass.cpp:159-294) + both vertex
  * shaders + shaders/volume_render.frag + the fixed-function blend / sRGB store
@@ -333,7 +348,13 @@ VKV_API int vkv_volume_upload_gradient(vkv_volume *vol, const uint8_t *gradient,
  * calls vkv_compute_distance_from_occupancy on every rank. */
 VKV_API int vkv_compute_occupancy_slab(vkv_volume *vol, const vkv_transfer_function_uniform *tfu, int skipping_type,
                                        uint32_t zb_first, uint32_t zb_count, uint64_t *count_dev, void *stream);
+/* K3 alone: consumes (overwrites) the occupancy map in map `n_maps - 1`, as the reference does
+ * (src/compute_distance_map.cpp:142-175, quirk A.8.3).  Fails with VKV_ERR_STATE when that map does not hold a fresh
+ * occupancy map (e.g. on a second call in a row). */
 VKV_API int vkv_compute_distance_from_occupancy(vkv_volume *vol, int skipping_type, void *stream);
+/* For callers that write an occupancy map (0 = occupied, 255 = empty) into vkv_volume_device_distance_map(vol, n_maps - 1)
+ * themselves — e.g. rows gathered from other ranks into a map this rank ran no slab of: declares it present. */
+VKV_API int vkv_volume_mark_occupancy_present(vkv_volume *vol, int skipping_type);
 
 /* ---- cross-process peer mapping (CUDA IPC) for the fused tile gather --------
  * The blob is the CUDA IPC handle of the allocation containing dev_ptr plus dev_ptr's byte offset inside it, so

@@ -662,3 +662,51 @@ def test_full_size_properties_config4(ctx):
             assert np.abs(np.diff(iso.astype(np.int16), axis=ax)).max() <= 1
     assert counts[0] > counts[1] > counts[2] > 0        # a rising intensity threshold shows fewer voxels
     vol.close()
+
+
+def test_distance_from_occupancy_needs_a_fresh_occupancy_map(ctx):
+    """K3 consumes the occupancy map in place (quirk A.8.3): running it twice in a row must fail loudly instead of transforming a
+    distance map and calling the result valid."""
+    O = np.where(np.random.default_rng(3).random((12, 16, 20)) < 0.02, 0, 255).astype(np.uint8)
+    vol, tfu = _volume_with_occupancy(ctx, O)
+    vol.compute_occupancy_slab(tfu, SKIP_DISTANCE, 0, vol.map_extent[2])
+    vol.compute_distance_from_occupancy(SKIP_DISTANCE)
+    want = orc.distance_map(O)
+    assert np.array_equal(vol.download_distance_map(0), want)
+    with pytest.raises(capi.VkvError, match="does not hold an occupancy map"):
+        vol.compute_distance_from_occupancy(SKIP_DISTANCE)
+    assert np.array_equal(vol.download_distance_map(0), want)        # untouched by the refused call
+    vol.compute_occupancy_slab(tfu, SKIP_BLOCK, 0, vol.map_extent[2])
+    vol.compute_distance_from_occupancy(SKIP_BLOCK)                   # block mode leaves the occupancy map in place: repeatable
+    vol.compute_distance_from_occupancy(SKIP_BLOCK)
+    assert np.array_equal(vol.download_distance_map(0), O)
+    vol.close()
+
+
+def test_two_streams_alternating_on_one_volume_are_ordered(ctx):
+    """A volume's colour table, tile history and counters are shared state: renders issued alternately on two streams with
+    different sampling / alpha factors (each forces a rebuild of the colour table) must give the frames the same calls give on one
+    stream — the library orders a call on a new stream after the volume's previous stream (include/vkv.h, stream model)."""
+    import torch
+    sc = _scene_for_compositing(ctx, (48, 64, 80), VolumeOptions(**TF_SETS[0]), 1, SKIP_DISTANCE)
+    vol, width, height = sc["vol"], 512, 384
+    it = scene.image_transform((0.004,) * 3, (80, 64, 48))
+    cu, ru = vol.make_uniforms(scene.look_at_camera((34, 22, 50), aspect=width / height), it, 5.0)
+    ropt = RenderOptions(skipping_type=SKIP_DISTANCE, clip_distance=5.0)
+    tfus = [capi.transfer_function_uniform(VolumeOptions(sampling_factor=sf, voxel_alpha_factor=af, **TF_SETS[0])) for sf, af in ((1.0, 1.0), (2.0, 0.6))]
+    want = []
+    for u in tfus:
+        fb = torch.zeros((height, width, 4), dtype=torch.uint8, device="cuda")
+        vol.render(cu, ru, u, ropt, width, height, fb.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        want.append(fb)
+    assert not torch.equal(want[0], want[1])
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    frames = [torch.zeros((height, width, 4), dtype=torch.uint8, device="cuda") for _ in range(12)]
+    torch.cuda.synchronize()
+    for k, fb in enumerate(frames):
+        vol.render(cu, ru, tfus[k & 1], ropt, width, height, fb.data_ptr(), stream=streams[k & 1].cuda_stream)
+    torch.cuda.synchronize()
+    for k, fb in enumerate(frames):
+        assert torch.equal(fb, want[k & 1]), k
+    vol.close()

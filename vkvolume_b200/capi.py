@@ -120,6 +120,8 @@ _SIGNATURES = {
     "vkv_update_transfer_function": (C.c_int, [_P, C.POINTER(VolumeOptions), C.c_int, C.POINTER(C.c_uint64), _P]),
     "vkv_make_uniforms": (C.c_int, [_P, C.POINTER(CameraDesc), C.POINTER(C.c_float), C.c_float,
                                     C.POINTER(CameraUniform), C.POINTER(RayCastUniform)]),
+    "vkv_make_uniforms_for_extent": (C.c_int, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(CameraDesc), C.POINTER(C.c_float),
+                                               C.c_float, C.POINTER(CameraUniform), C.POINTER(RayCastUniform)]),
     "vkv_render": (C.c_int, [_P, C.POINTER(CameraUniform), C.POINTER(RayCastUniform), C.POINTER(TransferFunctionUniform),
                              C.POINTER(RenderOptions), C.c_int, C.c_int, _P, _P, _P, _P]),
     "vkv_render_tiles": (C.c_int, [_P, C.POINTER(CameraUniform), C.POINTER(RayCastUniform), C.POINTER(TransferFunctionUniform),
@@ -148,6 +150,7 @@ _SIGNATURES = {
     "vkv_volume_upload_gradient": (C.c_int, [_P, _P, _P]),
     "vkv_compute_occupancy_slab": (C.c_int, [_P, C.POINTER(TransferFunctionUniform), C.c_int, C.c_uint32, C.c_uint32, _P, _P]),
     "vkv_compute_distance_from_occupancy": (C.c_int, [_P, C.c_int, _P]),
+    "vkv_volume_mark_occupancy_present": (C.c_int, [_P, C.c_int]),
     "vkv_ipc_export": (C.c_int, [_P, _P]),
     "vkv_ipc_open": (C.c_int, [_P, C.POINTER(_P)]),
     "vkv_ipc_close": (C.c_int, [_P]),
@@ -380,6 +383,9 @@ class Volume:
     def device_voxels(self) -> int:
         return lib().vkv_volume_device_voxels(self.handle) or 0
 
+    def device_gradient(self) -> int:
+        return lib().vkv_volume_device_gradient(self.handle) or 0
+
     def device_distance_map(self, idx: int = 0) -> int:
         return lib().vkv_volume_device_distance_map(self.handle, idx) or 0
 
@@ -399,6 +405,15 @@ def transfer_function_uniform(options: VolumeOptions) -> TransferFunctionUniform
     u = TransferFunctionUniform()
     check(lib().vkv_transfer_function_uniform_from_options(C.byref(options), C.byref(u)))
     return u
+
+
+def make_uniforms_for_extent(extent, map_extent, cam: CameraDesc, image_transform, clip_distance: float):
+    """vkv_make_uniforms_for_extent: the host maths of VolumeRenderSubpass::draw without a device or a volume handle."""
+    cu, ru = CameraUniform(), RayCastUniform()
+    it = (C.c_float * 16)(*[float(x) for x in image_transform])
+    check(lib().vkv_make_uniforms_for_extent((C.c_uint32 * 3)(*extent), (C.c_uint32 * 3)(*map_extent), C.byref(cam), it,
+                                             clip_distance, C.byref(cu), C.byref(ru)))
+    return cu, ru
 
 
 def load_header(path: str) -> VolumeHeader:

@@ -52,6 +52,24 @@ static int make_texture(cudaArray_t arr, cudaTextureObject_t *out)
 	return VKV_OK;
 }
 
+// Stream model of the boundary: a stream is a command buffer and a vkv_volume's device state (TF texture and masks, colour table,
+// tile history, counters, maps, scratch frames) belongs to ONE stream at a time, like the reference's single in-flight command
+// buffer (src/volume_render.cpp:292-327).  A call that arrives on another stream than the volume's previous call is ordered after
+// everything that stream had been given (one event record + wait): alternating streams serialises, it never races.  Calls on one
+// volume from several HOST threads at once are not supported (the reference is single-threaded).
+static cudaStream_t ordered_stream(vkv_volume *vol, void *stream)
+{
+	cudaStream_t s = (cudaStream_t) stream;
+	if (vol->last_stream_valid && vol->last_stream != s) {
+		if (!vol->order_event) cudaEventCreateWithFlags(&vol->order_event, cudaEventDisableTiming);
+		if (vol->order_event && cudaEventRecord(vol->order_event, vol->last_stream) == cudaSuccess) cudaStreamWaitEvent(s, vol->order_event, 0);
+		else (void) cudaGetLastError();        // the previous stream no longer exists: its work finished when it was destroyed
+	}
+	vol->last_stream       = s;
+	vol->last_stream_valid = true;
+	return s;
+}
+
 struct DeviceGuard {
 	int prev = -1;
 	explicit DeviceGuard(int dev)
@@ -83,7 +101,7 @@ int vkv_context_create(int device, vkv_context **out)
 	int n = 0;
 	VKV_CUDA_CHECK(cudaGetDeviceCount(&n));
 	VKV_REQUIRE(device >= 0 && device < n, VKV_ERR_ARGUMENT, "vkv_context_create: no such CUDA device");
-	VKV_CUDA_CHECK(cudaSetDevice(device));
+	DeviceGuard guard(device);        // the caller's current device is restored on every return path
 	auto *ctx = new (std::nothrow) vkv_context();
 	VKV_REQUIRE(ctx, VKV_ERR_NOMEM, "out of host memory");
 	ctx->device = device;
@@ -196,6 +214,7 @@ void vkv_volume_destroy(vkv_volume *vol)
 	if (vol->async_ready)
 		for (int i = 0; i < vkv_volume::kAsyncSlots; ++i) { cudaEventDestroy(vol->async_rendered[i]); cudaEventDestroy(vol->async_copied[i]); }
 	if (vol->h_count) cudaFreeHost(vol->h_count);
+	if (vol->order_event) cudaEventDestroy(vol->order_event);
 	delete vol;
 }
 
@@ -203,7 +222,7 @@ int vkv_volume_upload(vkv_volume *vol, const uint8_t *voxels, void *stream)
 {
 	VKV_REQUIRE(vol && voxels, VKV_ERR_ARGUMENT, "vkv_volume_upload: NULL argument");
 	DeviceGuard  guard(vol->ctx->device);
-	cudaStream_t s = (cudaStream_t) stream;
+	cudaStream_t s = ordered_stream(vol, stream);
 	VKV_CUDA_CHECK(cudaMemcpyAsync(vol->d_V, voxels, vol->N, cudaMemcpyHostToDevice, s));
 	vol->has_V = true;
 	return sync_arrays_from_linear(vol, false, s);
@@ -213,7 +232,7 @@ int vkv_volume_upload_device(vkv_volume *vol, const uint8_t *voxels_dev, void *s
 {
 	VKV_REQUIRE(vol && voxels_dev, VKV_ERR_ARGUMENT, "vkv_volume_upload_device: NULL argument");
 	DeviceGuard  guard(vol->ctx->device);
-	cudaStream_t s = (cudaStream_t) stream;
+	cudaStream_t s = ordered_stream(vol, stream);
 	if (voxels_dev != vol->d_V) VKV_CUDA_CHECK(cudaMemcpyAsync(vol->d_V, voxels_dev, vol->N, cudaMemcpyDeviceToDevice, s));
 	vol->has_V = true;
 	return sync_arrays_from_linear(vol, false, s);
@@ -224,7 +243,7 @@ int vkv_volume_upload_gradient(vkv_volume *vol, const uint8_t *gradient, void *s
 	VKV_REQUIRE(vol && gradient, VKV_ERR_ARGUMENT, "vkv_volume_upload_gradient: NULL argument");
 	VKV_REQUIRE(vol->d_G, VKV_ERR_STATE, "volume was created without a precomputed gradient map");
 	DeviceGuard  guard(vol->ctx->device);
-	cudaStream_t s = (cudaStream_t) stream;
+	cudaStream_t s = ordered_stream(vol, stream);
 	VKV_CUDA_CHECK(cudaMemcpyAsync(vol->d_G, gradient, vol->N, cudaMemcpyDefault, s));
 	vol->has_G = true;
 	return sync_arrays_from_linear(vol, true, s);
@@ -246,7 +265,7 @@ int vkv_volume_upload_raw(vkv_volume *vol, const void *raw, size_t raw_bytes, co
 	const size_t expect = vol->N * (kind >= 2 ? 2 : 1);
 	VKV_REQUIRE(raw_bytes == expect, VKV_ERR_IO, "File size does not match expected size for the given image format/dimensions");
 	DeviceGuard  guard(vol->ctx->device);
-	cudaStream_t s   = (cudaStream_t) stream;
+	cudaStream_t s   = ordered_stream(vol, stream);
 	void        *tmp = nullptr;
 	VKV_CUDA_CHECK(cudaMallocAsync(&tmp, raw_bytes, s));
 	VKV_CUDA_CHECK(cudaMemcpyAsync(tmp, raw, raw_bytes, cudaMemcpyHostToDevice, s));
@@ -289,7 +308,7 @@ int vkv_volume_update_transfer_function_texture(vkv_volume *vol, const vkv_volum
 {
 	VKV_REQUIRE(vol && opt, VKV_ERR_ARGUMENT, "NULL argument");
 	DeviceGuard  guard(vol->ctx->device);
-	cudaStream_t s = (cudaStream_t) stream;
+	cudaStream_t s = ordered_stream(vol, stream);
 	int          rc;
 	(void) rc;
 	return launch_tf_texture(vol, opt, s);        // texture, masks and bounds in one kernel
@@ -299,7 +318,7 @@ int vkv_volume_set_transfer_function_texture(vkv_volume *vol, const uint8_t *rgb
 {
 	VKV_REQUIRE(vol && rgba, VKV_ERR_ARGUMENT, "NULL argument");
 	DeviceGuard  guard(vol->ctx->device);
-	cudaStream_t s = (cudaStream_t) stream;
+	cudaStream_t s = ordered_stream(vol, stream);
 	VKV_CUDA_CHECK(cudaMemcpyAsync(vol->d_tf, rgba, 256 * 256 * 4, cudaMemcpyHostToDevice, s));
 	vol->has_tf = true;
 	++vol->tf_version;
@@ -312,7 +331,7 @@ int vkv_compute_gradient_map(vkv_volume *vol, const vkv_transfer_function_unifor
 	VKV_REQUIRE(vol->has_V, VKV_ERR_STATE, "vkv_compute_gradient_map: no voxels uploaded");
 	VKV_REQUIRE(vol->d_G, VKV_ERR_STATE, "volume was created without a precomputed gradient map");
 	DeviceGuard  guard(vol->ctx->device);
-	cudaStream_t s = (cudaStream_t) stream;
+	cudaStream_t s = ordered_stream(vol, stream);
 	int          rc;
 	// quirk A.8.1: the map is all 1.0 when use_gradient is false at this moment
 	if ((rc = launch_gradient(vol, tfu->use_gradient != 0, tfu->grad_magnitude_modifier, s))) return rc;
@@ -340,7 +359,7 @@ int vkv_compute_occupied_voxel_count(vkv_volume *vol, const vkv_transfer_functio
 	int rc;
 	if ((rc = check_gradient_inputs(vol, tfu))) return rc;
 	DeviceGuard  guard(vol->ctx->device);
-	cudaStream_t s = (cudaStream_t) stream;
+	cudaStream_t s = ordered_stream(vol, stream);
 	if ((rc = ensure_analytic_mask(vol, tfu, s))) return rc;
 	VKV_CUDA_CHECK(cudaMemsetAsync(vol->d_count, 0, sizeof(unsigned long long), s));
 	if ((rc = launch_occupancy(vol, tfu, true, nullptr, 0, vol->dim_b[2], vol->d_count, s))) return rc;
@@ -364,13 +383,25 @@ int vkv_compute_occupancy_slab(vkv_volume *vol, const vkv_transfer_function_unif
 	int rc;
 	if ((rc = check_gradient_inputs(vol, tfu))) return rc;
 	DeviceGuard  guard(vol->ctx->device);
-	cudaStream_t s = (cudaStream_t) stream;
+	cudaStream_t s = ordered_stream(vol, stream);
 	const int    n = n_maps_for(skipping_type);
 	if ((rc = vkv_volume_set_number_of_distance_maps(vol, n))) return rc;
 	if (count_dev && (rc = ensure_analytic_mask(vol, tfu, s))) return rc;
 	vol->maps_valid_for = -1;
-	return launch_occupancy(vol, tfu, count_dev != nullptr, vol->d_maps[n - 1], zb_first, zb_count,
-	                        reinterpret_cast<unsigned long long *>(count_dev), s);
+	rc = launch_occupancy(vol, tfu, count_dev != nullptr, vol->d_maps[n - 1], zb_first, zb_count,
+	                      reinterpret_cast<unsigned long long *>(count_dev), s);
+	if (!rc) vol->occupancy_in_map = n - 1;        // map n-1 holds occupancy (rows of this and earlier slabs) until K3 consumes it
+	return rc;
+}
+
+int vkv_volume_mark_occupancy_present(vkv_volume *vol, int skipping_type)
+{
+	VKV_REQUIRE(vol, VKV_ERR_ARGUMENT, "NULL argument");
+	VKV_REQUIRE(skipping_type >= 0 && skipping_type <= 3, VKV_ERR_ARGUMENT, "bad skipping type");
+	VKV_REQUIRE((int) vol->d_maps.size() >= n_maps_for(skipping_type), VKV_ERR_STATE, "the maps of this skipping type are not allocated");
+	vol->occupancy_in_map = n_maps_for(skipping_type) - 1;
+	vol->maps_valid_for   = -1;
+	return VKV_OK;
 }
 
 int vkv_compute_distance_from_occupancy(vkv_volume *vol, int skipping_type, void *stream)
@@ -378,8 +409,13 @@ int vkv_compute_distance_from_occupancy(vkv_volume *vol, int skipping_type, void
 	VKV_REQUIRE(vol, VKV_ERR_ARGUMENT, "NULL argument");
 	VKV_REQUIRE(skipping_type >= 0 && skipping_type <= 3, VKV_ERR_ARGUMENT, "bad skipping type");
 	VKV_REQUIRE((int) vol->d_maps.size() >= n_maps_for(skipping_type), VKV_ERR_STATE, "occupancy map not computed");
+	// K3 consumes the occupancy map in place (map n-1, reference quirk A.8.3): a second call without a fresh occupancy pass
+	// would transform a distance map and call the result valid
+	VKV_REQUIRE(vol->occupancy_in_map == n_maps_for(skipping_type) - 1, VKV_ERR_STATE,
+	            "vkv_compute_distance_from_occupancy: map n-1 does not hold an occupancy map (run vkv_compute_occupancy_slab first)");
 	DeviceGuard guard(vol->ctx->device);
-	int         rc = launch_distance(vol, skipping_type, (cudaStream_t) stream);
+	int         rc = launch_distance(vol, skipping_type, ordered_stream(vol, stream));
+	if (skipping_type == VKV_SKIP_DISTANCE || skipping_type == VKV_SKIP_ANISOTROPIC_DISTANCE) vol->occupancy_in_map = -1;
 	if (!rc) vol->maps_valid_for = skipping_type;
 	return rc;
 }
@@ -395,7 +431,7 @@ int vkv_update_transfer_function(vkv_volume *vol, const vkv_volume_options *opt,
 {
 	VKV_REQUIRE(vol && opt, VKV_ERR_ARGUMENT, "NULL argument");
 	DeviceGuard  guard(vol->ctx->device);
-	cudaStream_t s = (cudaStream_t) stream;
+	cudaStream_t s = ordered_stream(vol, stream);
 	int          rc;
 	if ((rc = vkv_volume_update_transfer_function_texture(vol, opt, stream))) return rc;
 	vkv_transfer_function_uniform u;
@@ -445,7 +481,7 @@ int vkv_render_tiles(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_r
 	if ((rc = check_render(vol, tfu, opt, width, height, tile_w, tile_h, tile_stride, depth_dev != nullptr))) return rc;
 	DeviceGuard guard(vol->ctx->device);
 	return launch_render(vol, cam, ray, tfu, opt, width, height, tile_w, tile_h, tile_first, tile_stride, -1, rgba8_dev, depth_dev,
-	                     counts_dev, (cudaStream_t) stream);
+	                     counts_dev, ordered_stream(vol, stream));
 }
 
 int vkv_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_cast_uniform *ray, const vkv_transfer_function_uniform *tfu,
@@ -465,7 +501,7 @@ int vkv_render_to_host(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv
 	int rc;
 	if ((rc = check_render(vol, tfu, opt, width, height, TW, TH, 1, false))) return rc;
 	DeviceGuard  guard(vol->ctx->device);
-	cudaStream_t s     = (cudaStream_t) stream;
+	cudaStream_t s     = ordered_stream(vol, stream);
 	const size_t bytes = (size_t) width * height * 4;
 	// Page-locked destination (cudaHostAlloc / cudaHostRegister / torch pin_memory): the ray caster's epilogue stores
 	// the RGBA8 pixels straight into it over PCIe, so the transfer of finished pixels overlaps the rays still marching
@@ -548,7 +584,7 @@ int vkv_render_to_host_async(vkv_volume *vol, const vkv_camera_uniform *cam, con
 	int rc;
 	if ((rc = check_render(vol, tfu, opt, width, height, 64, 32, 1, false))) return rc;
 	DeviceGuard  guard(vol->ctx->device);
-	cudaStream_t s     = (cudaStream_t) stream;
+	cudaStream_t s     = ordered_stream(vol, stream);
 	const size_t bytes = (size_t) width * height * 4;
 	constexpr int kSlots = vkv_volume::kAsyncSlots;
 	if (!vol->copy_stream) {
@@ -604,7 +640,7 @@ int vkv_render_over_host(vkv_volume *vol, const vkv_camera_uniform *cam, const v
 	int rc;
 	if ((rc = check_render(vol, tfu, opt, width, height, 64, 32, 1, depth_host != nullptr))) return rc;
 	DeviceGuard  guard(vol->ctx->device);
-	cudaStream_t s      = (cudaStream_t) stream;
+	cudaStream_t s      = ordered_stream(vol, stream);
 	const size_t px     = (size_t) width * height;
 	const size_t fbytes = px * 4, dbytes = depth_host ? px * sizeof(float) : 0;
 	// one scratch allocation: colour, then depth

@@ -115,6 +115,7 @@ struct vkv_volume {
 	uint8_t               *d_swap = nullptr;
 	uint8_t               *d_tmp  = nullptr;        // second scratch map (anisotropic x-pass results)
 	int                    maps_valid_for = -1;     // skipping type the maps currently hold
+	int                    occupancy_in_map = -1;   // index of the map that holds a fresh occupancy map (K3 consumes it), or -1
 
 	unsigned long long *d_count = nullptr;        // device-side count + render counters
 	unsigned long long *h_count = nullptr;        // pinned
@@ -144,6 +145,10 @@ struct vkv_volume {
 	bool                tile_hist_valid = false;
 	int                *h_tile_promote = nullptr;        // pinned + mapped: the last ordering pass's decision (1 = long tiles promoted)
 	int                 tile_order_holdoff = 0;          // frames to go before the ordering pass is tried again
+	// the stream of the volume's previous call (api.cu ordered_stream): a call on another stream is ordered after it
+	cudaStream_t        last_stream = nullptr;
+	bool                last_stream_valid = false;
+	cudaEvent_t         order_event = nullptr;
 };
 
 namespace vkv {

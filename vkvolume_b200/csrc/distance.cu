@@ -348,13 +348,21 @@ __device__ __forceinline__ void d_mbar_expect_tx(uint64_t *bar, unsigned bytes)
 }
 __device__ __forceinline__ void d_mbar_wait(uint64_t *bar, unsigned parity)
 {
-	unsigned ok, spins = 0;
+	unsigned           ok, spins = 0;
+	unsigned long long t0 = 0ull;
 	do {
 		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
 		             : "=r"(ok)
 		             : "r"(d_smem_u32(bar)), "r"(parity)
 		             : "memory");
-		if (!ok && ++spins > (1u << 26)) __trap();        // a lost arrival must surface as an error, never as a hung GPU
+		// a lost arrival must surface as an error, never as a hung GPU — but only after 20 s of WALL time (%globaltimer), so that
+		// time-slicing, a debugger, compute-sanitizer or first-touch page migration cannot trip it (a spin count could)
+		if (!ok && (++spins & 1023u) == 0u) {
+			unsigned long long now;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+			if (t0 == 0ull) t0 = now;
+			else if (now - t0 > 20000000000ull) __trap();
+		}
 	} while (!ok);
 }
 __device__ __forceinline__ void d_tma_load_1d(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar)

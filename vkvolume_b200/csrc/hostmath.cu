@@ -6,10 +6,12 @@
 using namespace vkv;
 using namespace vkvm;
 
-extern "C" int vkv_make_uniforms(const vkv_volume *vol, const vkv_camera_desc *cam, const float image_transform[16],
-                                 float clip_distance, vkv_camera_uniform *cu, vkv_ray_cast_uniform *ru)
+extern "C" int vkv_make_uniforms_for_extent(const uint32_t extent[3], const uint32_t map_extent[3], const vkv_camera_desc *cam,
+                                            const float image_transform[16], float clip_distance, vkv_camera_uniform *cu,
+                                            vkv_ray_cast_uniform *ru)
 {
-	VKV_REQUIRE(vol && cam && image_transform && cu && ru, VKV_ERR_ARGUMENT, "vkv_make_uniforms: NULL argument");
+	VKV_REQUIRE(extent && map_extent && cam && image_transform && cu && ru, VKV_ERR_ARGUMENT, "vkv_make_uniforms: NULL argument");
+	VKV_REQUIRE(map_extent[0] && map_extent[1] && map_extent[2], VKV_ERR_ARGUMENT, "vkv_make_uniforms: empty map extent");
 	// camera.get_view(): inverse of the camera node's world matrix T*R*S, S = 1
 	// (VS/framework/scene_graph/components/camera.cpp:36-45, transform.cpp:92-97)
 	const Mat4 cam_world = translate(cam->translation[0], cam->translation[1], cam->translation[2]) *
@@ -51,8 +53,15 @@ extern "C" int vkv_make_uniforms(const vkv_volume *vol, const vkv_camera_desc *c
 		ru->cam_pos_tex[i] = (float) cam_tex[i];
 	}
 	ru->front_index = (ru->plane_tex[0] < 0 ? 1 : 0) + (ru->plane_tex[1] < 0 ? 2 : 0) + (ru->plane_tex[2] < 0 ? 4 : 0);
-	for (int a = 0; a < 3; ++a) ru->block_size[a] = (float) rnd_up(vol->dim[a], vol->dim_b[a]);
+	for (int a = 0; a < 3; ++a) ru->block_size[a] = (float) rnd_up(extent[a], map_extent[a]);
 	ru->block_size[3] = 0.0f;
 	ru->_pad[0] = ru->_pad[1] = ru->_pad[2] = 0;
 	return VKV_OK;
+}
+
+extern "C" int vkv_make_uniforms(const vkv_volume *vol, const vkv_camera_desc *cam, const float image_transform[16],
+                                 float clip_distance, vkv_camera_uniform *cu, vkv_ray_cast_uniform *ru)
+{
+	VKV_REQUIRE(vol, VKV_ERR_ARGUMENT, "vkv_make_uniforms: NULL argument");
+	return vkv_make_uniforms_for_extent(vol->dim, vol->dim_b, cam, image_transform, clip_distance, cu, ru);
 }
