@@ -69,6 +69,9 @@ def main():
               f"  with skip load {it_d[i]}  with tex batch {it_r[i]}  mixed {it_m[i]}  mean live lanes {lanes[i]}"
               f"  | kcycles head {t[i, 3] / 1e3:.1f} issue {t[i, 4] / 1e3:.1f} skip branch {t[i, 5] / 1e3:.1f} sample branch {t[i, 6] / 1e3:.1f}")
     act = it_ > 0
+    for thr in (16, 24, 32, 48, 64, 96, 128, 160):
+        m = it_ >= thr
+        print(f"  warps with >= {thr:3d} iterations: {int(m.sum()):6d}   live lanes (mean x warps) {int(lanes[m].sum()):7d}   iterations in them {int(it_[m].sum())}")
     print(f"all marching warps: iterations {it_[act].sum()}  with skip load {it_d[act].sum()}  with tex batch {it_r[act].sum()}  mixed {it_m[act].sum()}  mean live lanes {(lanes[act] * it_[act]).sum() / it_[act].sum():.1f}")
     print(f"marching warps {act.sum()}  mean iterations {it_[act].mean():.1f}  mean ns/iter {dur[act].sum() / it_[act].sum():.0f}")
     # concurrency over time (warps in flight, whole GPU) in 5 us buckets

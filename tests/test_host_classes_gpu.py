@@ -106,4 +106,4 @@ def test_host_classes_outputs_match_the_oracle(tmp_path, skipmode, two_volumes):
     same_hit = (depth > 0) == (rdepth > 0)
     assert same_hit.mean() >= 0.999
     assert np.isclose(depth[same_hit], rdepth[same_hit], rtol=1e-4, atol=1e-6).mean() >= 0.995        # hardware filter: the last contributing sample moves on a few rays
-    assert (ref[..., :3].max(axis=2) > 0).mean() > 0.05        # something was drawn
+    assert (ref[..., :3].max(axis=2) > 0).mean() > 0.02        # something was drawn

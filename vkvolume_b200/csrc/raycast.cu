@@ -66,6 +66,8 @@ struct RayParams {
 	float         *depth;
 	unsigned long long *counts;     // vkv_sample_counts or null
 	unsigned long long *trace;      // debug (VKV_RC_TRACE): per warp {start ns, end ns, loop iterations} or null
+	const TFBounds *bounds;         // conservative byte ranges of the visible TF texels (tf.cu): samples outside are empty without a table read
+	int    flags;                   // debug (VKV_RC_FLAGS): experiment switches, 0 in production
 };
 
 __device__ __forceinline__ float clampf_(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
@@ -249,7 +251,13 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 				if (d[k] == 0.0) {
 					if (P.o[k] < 0.0 || P.o[k] > 1.0) hit = false;
 				} else {
-					double t0 = (0.0 - P.o[k]) / d[k], t1 = (1.0 - P.o[k]) / d[k];
+					double t0, t1;
+					if (P.flags & 2) {
+						const double r = 1.0 / d[k];
+						t0 = (0.0 - P.o[k]) * r; t1 = (1.0 - P.o[k]) * r;
+					} else {
+						t0 = (0.0 - P.o[k]) / d[k]; t1 = (1.0 - P.o[k]) / d[k];
+					}
 					if (t0 > t1) { const double t = t0; t0 = t1; t1 = t; }
 					if (t0 > tn) tn = t0;
 					if (t1 < tf) tf = t1;
@@ -357,6 +365,10 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 					const float dim_inv[3] = {1.0f / P.dimf[0], 1.0f / P.dimf[1], 1.0f / P.dimf[2]};
 					// look-ahead cache of hardware-filtered samples i .. i+3: consecutive volume samples are the common case
 					// inside occupied regions, and one batch of independent fetches replaces four dependent round trips
+					// conservative visible rectangle of the TF texture in (intensity texel, gradient texel): a sample outside it is
+					// empty (alpha byte 0) and needs no colour-table read — on the long grazing rays most samples are
+					const TFRange tb    = P.use_gradient ? P.bounds->tex_all : P.bounds->tex_row255;
+					const unsigned tb_vspan = tb.v_hi - tb.v_lo, tb_gspan = tb.g_hi - tb.g_lo;
 					int      pre_base = -0x40000000;
 					float pre_v0 = 0.0f, pre_v1 = 0.0f, pre_v2 = 0.0f, pre_v3 = 0.0f, pre_g0 = 1.0f, pre_g1 = 1.0f, pre_g2 = 1.0f, pre_g3 = 1.0f;
 					for (int i = 0; i < n_steps;) {
@@ -458,7 +470,9 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 								intensity = pick4_(k, pre_v0, pre_v1, pre_v2, pre_v3);
 								if (P.use_gradient) gradient = pick4_(k, pre_g0, pre_g1, pre_g2, pre_g3);
 							}
-							const float4 c = __ldg(P.ctab + tf_texel(gradient) * 256 + tf_texel(intensity));
+							const int ti = tf_texel(intensity), tg = tf_texel(gradient);
+							float4    c  = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
+							if (!(P.flags & 1) || ((unsigned) ti - tb.v_lo <= tb_vspan && (unsigned) tg - tb.g_lo <= tb_gspan)) c = __ldg(P.ctab + tg * 256 + ti);
 							voxel_occupied = c.w >= 0.0f;
 							if (voxel_occupied) {
 								if (SKIP != VKV_SKIP_NONE) idx_last = idx;
@@ -788,6 +802,11 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 	P.rgba8  = rgba8;
 	P.depth  = depth;
 	P.counts = reinterpret_cast<unsigned long long *>(counts);
+	P.bounds = vol->d_bounds;
+	{
+		const char *fl = getenv("VKV_RC_FLAGS");
+		P.flags        = fl ? atoi(fl) : 0;
+	}
 
 	const bool exact = opt->filter == VKV_FILTER_EXACT;
 	// on-the-fly gradients (volume created without a gradient map); the variant always counts, into scratch if need be
