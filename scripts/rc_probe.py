@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Debug probe (GPU box): A/B the ray caster's VKV_RC_FLAGS on the headline frame (24 orbit views, L2 flushed)."""
+"""Debug probe (GPU box): where a ray-cast frame's time goes — set-up only (TEST_RAY_ENTRY view: entry geometry + epilogue, no
+march) against the full frame, per skip mode, 24 orbit views with the L2 flushed."""
 import argparse
 import os
 import sys
@@ -17,19 +18,10 @@ from vkvolume_b200.capi import RenderOptions, VolumeOptions  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="c2")
-    ap.add_argument("--flags", default="0,1,2,3")
-    ap.add_argument("--skips", default="2,1,3,0")
-    ap.add_argument("--env", default="VKV_RC_FLAGS")
-    ap.add_argument("--view-step", type=int, default=3, help="orbit views between consecutive frames (bench.py: 1 = 5 degrees)")
+    ap.add_argument("--skips", default="2")
+    ap.add_argument("--tests", default="1,0")
     a = ap.parse_args()
     import torch
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        _h = pynvml.nvmlDeviceGetHandleByIndex(0)
-        clk = lambda: pynvml.nvmlDeviceGetClockInfo(_h, pynvml.NVML_CLOCK_SM)
-    except Exception:
-        clk = lambda: -1
     wl = bench.WORKLOADS[a.workload]
     W, H, D = wl["dim"]
     FW, FH = wl["frame"]
@@ -44,13 +36,11 @@ def main():
     fb = torch.zeros((FH, FW, 4), dtype=torch.uint8, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     counts = torch.zeros(4, dtype=torch.int64, device="cuda")
-    views = [vol.make_uniforms(scene.look_at_camera(bench.orbit_eye(v, 72, wl), aspect=FW / FH), it, wl["clip"]) for v in range(0, 24 * a.view_step, a.view_step)]
+    views = [vol.make_uniforms(scene.look_at_camera(bench.orbit_eye(v, 72, wl), aspect=FW / FH), it, wl["clip"]) for v in range(0, 72, 3)]
     for skip in [int(x) for x in a.skips.split(",")]:
         vol.update_transfer_function(opt, skip)
-        ropt = RenderOptions(skipping_type=skip, clip_distance=wl["clip"], early_ray_termination=1)
-        ref = None
-        for fl in a.flags.split(","):
-            os.environ[a.env] = fl
+        for test in [int(x) for x in a.tests.split(",")]:
+            ropt = RenderOptions(skipping_type=skip, clip_distance=wl["clip"], early_ray_termination=1, test=test)
             ts = []
             counts.zero_()
             for rep in range(2):
@@ -64,11 +54,7 @@ def main():
                     if rep == 1:
                         ts.append(e0.elapsed_time(e1))
             c = counts.tolist()
-            frame = fb.clone()
-            same = "ref" if ref is None else ("same frame" if torch.equal(frame, ref[0]) and c == ref[1] else f"DIFFERENT ({int((frame != ref[0]).sum())} bytes, counts {c} vs {ref[1]})")
-            if ref is None:
-                ref = (frame, c)
-            print(f"[sm {clk()} MHz] skip {skip} {a.env}={fl}: mean {np.mean(ts):.4f} ms  min {np.min(ts):.4f}  max {np.max(ts):.4f}   samples/frame {(c[0] + c[1]) / len(views):.0f}  [{same}]", flush=True)
+            print(f"skip {skip} test {test}: mean {np.mean(ts):.4f} ms  min {np.min(ts):.4f}  max {np.max(ts):.4f}  covered/frame {c[3] / len(views):.0f} samples/frame {(c[0] + c[1]) / len(views):.0f}", flush=True)
 
 
 if __name__ == "__main__":

@@ -144,7 +144,7 @@ def _check_frames(w, skip, views, expect_history):
         # the previous orbit view first, then this one twice: the frame compared is the third of a sequence (tile history live)
         img, counts, launches = w.render_sequence([v - 1, v, v], ropt)
         if expect_history:
-            assert launches == 2, f"expected tile_order_kernel + raycast_kernel on a frame with history, saw {launches} launches"
+            assert launches >= 2, f"expected tile_order_kernel + raycast_kernel (+ raycast_long_kernel) on a frame with history, saw {launches} launches"
         cu, ru = w.uniforms(v)
         ref, rc, _, _ = orc.render(w.V, w.G, w.tf, maps, vol.map_extent, cu, ru, w.tfu, ropt, w.FW, w.FH)
         frac, p, frac_a, p_a = frame_bar_rgba(img, ref)

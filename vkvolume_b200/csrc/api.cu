@@ -215,6 +215,8 @@ void vkv_volume_destroy(vkv_volume *vol)
 		for (int i = 0; i < vkv_volume::kAsyncSlots; ++i) { cudaEventDestroy(vol->async_rendered[i]); cudaEventDestroy(vol->async_copied[i]); }
 	if (vol->h_count) cudaFreeHost(vol->h_count);
 	if (vol->order_event) cudaEventDestroy(vol->order_event);
+	cudaFree(vol->d_lq); cudaFree(vol->d_lrays);
+	if (vol->h_long_hint) cudaFreeHost(vol->h_long_hint);
 	delete vol;
 }
 

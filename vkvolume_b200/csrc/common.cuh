@@ -145,6 +145,10 @@ struct vkv_volume {
 	bool                tile_hist_valid = false;
 	int                *h_tile_promote = nullptr;        // pinned + mapped: the last ordering pass's decision (1 = long tiles promoted)
 	int                 tile_order_holdoff = 0;          // frames to go before the ordering pass is tried again
+	void               *d_lq = nullptr, *d_lrays = nullptr;        // ray caster: long-ray queue header + records (raycast.cu)
+	int                 long_cap = 0;
+	int                *h_long_hint = nullptr;        // pinned + mapped: long rays of the last frame that used the hand-over
+	int                 long_holdoff = 0;             // frames to go before the hand-over is tried again
 	// the stream of the volume's previous call (api.cu ordered_stream): a call on another stream is ordered after it
 	cudaStream_t        last_stream = nullptr;
 	bool                last_stream_valid = false;

@@ -30,6 +30,23 @@
 
 namespace vkv {
 
+// Long rays (distance-map modes, production variants): a ray still marching after `long_T` loop iterations is suspended — its
+// march state goes into a queue — and finished by raycast_long_kernel, one ray per WARP (see there).
+struct LongRay {
+	unsigned p;                 // pixel index py * width + px
+	int      i, i_min, i_first_hit, n_steps;
+	unsigned idx_last, occupied, pad;
+	float    out[4];
+	float    entry[3], step[3], pad2[2];        // written as five float4 by raycast_kernel, read the same way
+};
+static_assert(sizeof(LongRay) == 80, "LongRay layout");
+struct LongQueue {
+	unsigned count;             // rays pushed by raycast_kernel (may exceed capacity: the excess was not suspended)
+	unsigned head;              // next ray to pop in raycast_long_kernel
+	unsigned done;              // CTAs of raycast_long_kernel that have exited (the last one resets the queue)
+	unsigned capacity;
+};
+
 struct RayParams {
 	double o[3];                    // camera position, texture space
 	double d0[3], ddx[3], ddy[3];   // far-plane direction of pixel (px,py): d0 + px*ddx + py*ddy
@@ -66,6 +83,11 @@ struct RayParams {
 	float         *depth;
 	unsigned long long *counts;     // vkv_sample_counts or null
 	unsigned long long *trace;      // debug (VKV_RC_TRACE): per warp {start ns, end ns, loop iterations} or null
+	LongQueue *lq;                  // long-ray queue or null
+	LongRay   *lrays;
+	int        long_T;              // suspend after this many loop iterations (0: never)
+	int        long_cap;            // records the queue holds
+	int       *long_hint;           // mapped host int: rays the last frame handed over (raycast_long_kernel writes it)
 	const TFBounds *bounds;         // conservative byte ranges of the visible TF texels (tf.cu): samples outside are empty without a table read
 	int    flags;                   // debug (VKV_RC_FLAGS): experiment switches, 0 in production
 };
@@ -139,6 +161,22 @@ __device__ __forceinline__ float srgb_decode(unsigned b)
 __device__ __forceinline__ unsigned unorm8(float c) { return (unsigned) (clampf_(c, 0.0f, 1.0f) * 255.0f + 0.5f); }
 
 
+// Blend over the render-pass clear (0,0,0,1) / depth 0 and store: rgb = src.rgb, a = src.a * (1 - src.a)
+// (volume_render_subpass.cpp:176-190), R8G8B8A8_SRGB encode; pixels that fail the depth test keep the clear values.
+__device__ __forceinline__ unsigned pack_over_clear(bool pass, const float out[4])
+{
+	unsigned packed = 0xff000000u;
+	if (pass) {
+		// the built-in transfer function is grey (volume_component.cpp:250-261): one encode serves the three channels
+		const unsigned er = unorm8(srgb_encode(clampf_(out[0], 0.0f, 1.0f)));
+		const bool     grey = out[1] == out[0] && out[2] == out[0];
+		const unsigned eg = grey ? er : unorm8(srgb_encode(clampf_(out[1], 0.0f, 1.0f)));
+		const unsigned eb = grey ? er : unorm8(srgb_encode(clampf_(out[2], 0.0f, 1.0f)));
+		packed = er | (eg << 8) | (eb << 16) | (unorm8(out[3] * (1.0f - out[3])) << 24);
+	}
+	return packed;
+}
+
 // Per TF texel: the fragment shader's `color` after opacity correction and premultiplication
 // (volume_render.frag:279-285): ca = clamp(voxel_alpha_factor * (1 - pow(1 - a, 1/sampling_factor)), 0, 1),
 // rgb = (byte / 255) * ca.  w = -1 marks texels whose alpha byte is 0 (voxel_occupied = false).
@@ -193,6 +231,9 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 	// r1s_trace.md), so they have to start at t = 0, not whenever the sweep reaches them.
 	// (compiled into the distance-map production variants only: the other modes are throughput-bound and keep their old code)
 	constexpr bool kHist = (SKIP == VKV_SKIP_DISTANCE || SKIP == VKV_SKIP_ANISOTROPIC_DISTANCE) && !OTF && !EXACT && !LOAD;
+	// the same variants hand their long rays to raycast_long_kernel (P.long_T loop iterations into the march; 0: never)
+	constexpr bool kLong = kHist;
+	bool           suspended = false;
 	const int seq        = P.seq_base + (int) blockIdx.z;
 	const int local_tile = (kHist && P.tile_order) ? (int) P.tile_order[seq] : centre_out(seq, P.my_tiles);
 	const int tile       = P.tile_first + local_tile * P.tile_stride;
@@ -371,7 +412,12 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 					const unsigned tb_vspan = tb.v_hi - tb.v_lo, tb_gspan = tb.g_hi - tb.g_lo;
 					int      pre_base = -0x40000000;
 					float pre_v0 = 0.0f, pre_v1 = 0.0f, pre_v2 = 0.0f, pre_v3 = 0.0f, pre_g0 = 1.0f, pre_g1 = 1.0f, pre_g2 = 1.0f, pre_g3 = 1.0f;
-					for (int i = 0; i < n_steps;) {
+					// trips this lane may spend in the march before it is handed to raycast_long_kernel (kLong variants; never otherwise)
+					unsigned trip_limit = (kLong && P.long_T > 0) ? (unsigned) P.long_T : 0xffffffffu;
+					bool     ert_done   = false;
+					int      i          = 0;
+					for (;;) {
+					for (; i < n_steps && (!kLong || n_iter < trip_limit);) {
 						if (kHist || TRACE) ++n_iter;
 						if (TRACE) tc_mark = clock64();
 						const float fi     = (float) i;
@@ -480,7 +526,8 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 								out[0] = out[0] + w * c.x; out[1] = out[1] + w * c.y; out[2] = out[2] + w * c.z; out[3] = out[3] + w * c.w;
 								if (c.w > 0.0f) i_first_hit = i;
 								if (out[3] > 0.99f && P.ert) {
-									out[3] = 1.0f;
+									out[3]   = 1.0f;
+									ert_done = true;
 									break;
 								}
 							} else {
@@ -490,6 +537,28 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 							if (SKIP != VKV_SKIP_NONE) i_min = i;
 							if (TRACE) { const long long c = clock64(); tc_v += c - tc_mark; tc_mark = c; }
 						}
+					}
+					if (!kLong || ert_done || i >= n_steps) break;
+					{
+						// the trip limit was reached with the ray still marching.  Every such lane of the warp arrives here in the same trip
+						// (they count trips together): one atomic for the warp, one 80-byte record per lane
+						const unsigned am     = __activemask();
+						const int      leader = __ffs(am) - 1;
+						unsigned       slot   = 0u;
+						if (lane == leader) slot = atomicAdd(&P.lq->count, (unsigned) __popc(am));
+						slot = __shfl_sync(am, slot, leader) + (unsigned) __popc(am & ((1u << lane) - 1u));
+						if (slot < (unsigned) P.long_cap) {
+							float4 *r = reinterpret_cast<float4 *>(P.lrays + slot);
+							r[0] = make_float4(__uint_as_float((unsigned) p), __int_as_float(i), __int_as_float(i_min), __int_as_float(i_first_hit));
+							r[1] = make_float4(__int_as_float(n_steps), __uint_as_float(idx_last), __uint_as_float(voxel_occupied ? 1u : 0u), 0.0f);
+							r[2] = make_float4(out[0], out[1], out[2], out[3]);
+							r[3] = make_float4(entry[0], entry[1], entry[2], step[0]);
+							r[4] = make_float4(step[1], step[2], 0.0f, 0.0f);
+							suspended = true;
+							break;
+						}
+						trip_limit = 0xffffffffu;        // queue full: this ray finishes here
+					}
 					}
 					if (P.depth && out[3] > 0.0f && i_first_hit < n_steps) {
 						const double pm[3] = {(double) (entry[0] + step[0] * (float) i_first_hit) - 0.5,
@@ -512,17 +581,10 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 		// (volume_render_subpass.cpp:176-190); R8G8B8A8_SRGB store.  Without LOAD the destination is the clear colour
 		// (0,0,0,1) / depth 0 and uncovered pixels are written with it.
 		const bool pass = covered && !discarded && frag_depth >= dst_depth;
-		if (!LOAD) {
-			unsigned packed = 0xff000000u;
-			if (pass) {
-				// the built-in transfer function is grey (volume_component.cpp:250-261): one encode serves the three channels
-				const unsigned er = unorm8(srgb_encode(clampf_(out[0], 0.0f, 1.0f)));
-				const bool     grey = out[1] == out[0] && out[2] == out[0];
-				const unsigned eg = grey ? er : unorm8(srgb_encode(clampf_(out[1], 0.0f, 1.0f)));
-				const unsigned eb = grey ? er : unorm8(srgb_encode(clampf_(out[2], 0.0f, 1.0f)));
-				packed = er | (eg << 8) | (eb << 16) | (unorm8(out[3] * (1.0f - out[3])) << 24);
-			}
-			reinterpret_cast<unsigned *>(P.rgba8)[p] = packed;
+		if (kLong && suspended) {
+			// raycast_long_kernel finishes this ray and stores its pixel
+		} else if (!LOAD) {
+			reinterpret_cast<unsigned *>(P.rgba8)[p] = pack_over_clear(pass, out);
 			if (P.depth) P.depth[p] = pass ? frag_depth : 0.0f;
 		} else if (pass) {
 			const unsigned d8 = reinterpret_cast<const unsigned *>(P.rgba8)[p];
@@ -573,6 +635,194 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 #pragma unroll
 			for (int w = 0; w < kRcWarps; ++w) t += s_cnt[w][threadIdx.x];
 			if (t) atomicAdd(P.counts + threadIdx.x, t);
+		}
+	}
+}
+
+// ---- long rays: one ray per warp, 32 lattice steps at a time -------------------------------------------------------------
+// A ray's march is a serial state machine (skip-map hop -> next position -> hop ...), ~1300 cycles per trip when 20 rays share a
+// warp in lockstep: a frame's time used to be the ~180 trips of its longest rays (profiles/r1s_trace.md).  What a step of the
+// machine READS, however, depends on the step index alone (pos = entry + i * step): so a warp takes one suspended ray and
+// evaluates 32 consecutive lattice steps at once — lane l looks at step base + l: block index, skip-map byte, the hop that byte
+// would cause, the filtered sample(s) and its colour-table entry, 32 independent fetches instead of a 32-deep dependent chain —
+// parks them in shared memory and then REPLAYS the shader's state machine over the window with no memory access at all
+// (a few ALU instructions per visited step, every lane computing the same state).  The replay visits exactly the steps
+// the serial march visits, in the same order, with the same fp32 operations: frames and counters are bit-identical to the
+// one-kernel march (tests/test_parity_gpu.py::test_long_ray_pass_is_bit_identical).
+__device__ __forceinline__ void store_over_clear(const RayParams &P, size_t p, bool pass, const float out[4], float frag_depth)
+{
+	reinterpret_cast<unsigned *>(P.rgba8)[p] = pack_over_clear(pass, out);
+	if (P.depth) P.depth[p] = pass ? frag_depth : 0.0f;
+}
+constexpr int kLongWarps = 8, kLongWindow = 64;
+template <int SKIP>
+__global__ void __launch_bounds__(32 * kLongWarps) raycast_long_kernel(const __grid_constant__ RayParams P)
+{
+	__shared__ float4   s_c[kLongWarps][kLongWindow];
+	__shared__ unsigned s_idx[kLongWarps][kLongWindow];
+	__shared__ int      s_hop[kLongWarps][kLongWindow];        // > 0: trips the skip-map byte of this step's block lets the ray jump; 0: the block is occupied
+	const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const unsigned n_rays = min(P.lq->count, (unsigned) P.long_cap);
+	unsigned long long c_vol = 0ull, c_dist = 0ull, c_empty = 0ull;
+	const int     back      = (int) ceilf(P.sampling_factor);
+	const int     dim_b1[3] = {P.dim_b[0] - 1, P.dim_b[1] - 1, P.dim_b[2] - 1};
+	const TFRange tb        = P.use_gradient ? P.bounds->tex_all : P.bounds->tex_row255;
+	const unsigned tb_vspan = tb.v_hi - tb.v_lo, tb_gspan = tb.g_hi - tb.g_lo;
+	for (;;) {
+		unsigned j = 0u;
+		if (lane == 0) j = atomicAdd(&P.lq->head, 1u);
+		j = __shfl_sync(0xffffffffu, j, 0);
+		if (j >= n_rays) break;
+		const float4 *r  = reinterpret_cast<const float4 *>(P.lrays + j);
+		const float4  r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3], r4 = r[4];
+		const unsigned p = __float_as_uint(r0.x);
+		int            i = __float_as_int(r0.y), i_min = __float_as_int(r0.z), i_first_hit = __float_as_int(r0.w);
+		const int      n_steps = __float_as_int(r1.x);
+		unsigned       idx_last = __float_as_uint(r1.y);
+		bool           voxel_occupied = __float_as_uint(r1.z) != 0u;
+		float          out[4]   = {r2.x, r2.y, r2.z, r2.w};
+		const float    entry[3] = {r3.x, r3.y, r3.z}, step[3] = {r3.w, r4.x, r4.y};
+		float          sdt_inv[3];
+#pragma unroll
+		for (int k = 0; k < 3; ++k) {
+			const float sdt = step[k] * P.dimf[k] / P.block_size[k];
+			sdt_inv[k]      = 1.0f / sdt;
+		}
+		const bool neg[3] = {sdt_inv[0] < 0.0f, sdt_inv[1] < 0.0f, sdt_inv[2] < 0.0f};
+		const uint8_t *__restrict__ Dm = P.map_ptrs[0];
+		if (SKIP == VKV_SKIP_ANISOTROPIC_DISTANCE) Dm = P.map_ptrs[(step[2] < 0 ? 1 : 0) + (step[1] < 0 ? 2 : 0) + (step[0] < 0 ? 4 : 0)];        // sign(step) == sign(dir)
+		unsigned n_vol = 0u, n_dist = 0u, n_empty = 0u;
+		bool     done = false;
+		while (i < n_steps && !done) {
+			// the window starts where a step back (volume_render.frag:253-261) from the current step could land
+			const int base = max(i - back, i_min);
+			unsigned  my_idx[2];
+			bool      my_vis[2];
+#pragma unroll
+			for (int h = 0; h < 2; ++h) {
+				const int   slot   = 32 * h + lane;
+				const float fi     = (float) (base + slot);
+				const float pos[3] = {entry[0] + fi * step[0], entry[1] + fi * step[1], entry[2] + fi * step[2]};
+				float       u[3];
+				int         u_i[3];
+#pragma unroll
+				for (int k = 0; k < 3; ++k) {
+					u[k]   = P.vol_to_map[k] * pos[k];
+					u_i[k] = clamp0_((int) u[k], dim_b1[k]);
+				}
+				const unsigned idx  = ((unsigned) u_i[2] * (unsigned) P.dim_b[1] + (unsigned) u_i[1]) * (unsigned) P.dim_b[0] + (unsigned) u_i[0];
+				const unsigned dist = __ldg(Dm + idx);
+				const float    intensity = tex3D<float>(P.tex_v, pos[0], pos[1], pos[2]);
+				const float    gradient  = P.use_gradient ? tex3D<float>(P.tex_g, pos[0], pos[1], pos[2]) : 1.0f;
+				int            hop       = 0;
+				if (dist > 0u) {
+					float       dxyz[3];
+					const float fd = (float) dist, omfd = 1.0f - fd;
+#pragma unroll
+					for (int k = 0; k < 3; ++k) {
+						const float rr  = clampf_((float) u_i[k] - u[k], -1.0f, 0.0f);
+						const float bse = neg[k] ? omfd : fd;
+						dxyz[k]         = (bse + rr) * sdt_inv[k];
+					}
+					hop = max((int) ceilf(fminf(fminf(dxyz[0], dxyz[1]), dxyz[2])), 1);
+				}
+				const int ti = tf_texel(intensity), tg = tf_texel(gradient);
+				float4    c  = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
+				if ((unsigned) ti - tb.v_lo <= tb_vspan && (unsigned) tg - tb.g_lo <= tb_gspan) c = __ldg(P.ctab + tg * 256 + ti);
+				s_idx[warp][slot] = idx;
+				s_hop[warp][slot] = hop;
+				s_c[warp][slot]   = c;
+				my_idx[h]         = idx;
+				my_vis[h]         = c.w >= 0.0f;
+			}
+			// bit k of a mask speaks for step base + k
+			const unsigned long long m_vis = (unsigned long long) __ballot_sync(0xffffffffu, my_vis[0]) | ((unsigned long long) __ballot_sync(0xffffffffu, my_vis[1]) << 32);
+			auto same_mask = [&](unsigned ref) {
+				return (unsigned long long) __ballot_sync(0xffffffffu, my_idx[0] == ref) | ((unsigned long long) __ballot_sync(0xffffffffu, my_idx[1] == ref) << 32);
+			};
+			unsigned long long m_same = same_mask(idx_last);
+			__syncwarp();
+			// Replay of the fragment shader's loop body (volume_render.frag:215-312) over the window; every lane carries the same state.
+			// One trip of this loop is one EVENT of the march: a skip-map consultation, a visible sample, or a whole run of empty
+			// samples (the common case on a ray that grazes the surface: nothing but the counters changes along it).
+			while (i < n_steps) {
+				const int k = i - base;
+				if (k >= kLongWindow) break;
+				if (!voxel_occupied && !((m_same >> k) & 1ull)) {
+					++n_dist;
+					const int hop = s_hop[warp][k];
+					if (hop > 0) {
+						i += hop;
+					} else {
+						voxel_occupied = true;
+						idx_last       = s_idx[warp][k];
+						m_same         = same_mask(idx_last);
+						i              = max(i - back, i_min);
+					}
+				} else if ((m_vis >> k) & 1ull) {
+					++n_vol;
+					const float4   c   = s_c[warp][k];
+					const unsigned idx = s_idx[warp][k];
+					voxel_occupied = true;
+					if (idx != idx_last) {
+						idx_last = idx;
+						m_same   = same_mask(idx_last);
+					}
+					const float w = 1.0f - out[3];
+					out[0] = out[0] + w * c.x; out[1] = out[1] + w * c.y; out[2] = out[2] + w * c.z; out[3] = out[3] + w * c.w;
+					if (c.w > 0.0f) i_first_hit = i;
+					if (out[3] > 0.99f && P.ert) {
+						out[3] = 1.0f;
+						done   = true;
+						break;
+					}
+					++i;
+					i_min = i;
+				} else {
+					// step k is sampled and empty; the steps after it are sampled too for as long as they stay in block idx_last
+					// (voxel_occupied is false from here on) and are empty themselves
+					const unsigned long long run = ~m_vis & (m_same | (1ull << k));
+					const unsigned long long t   = ~(run >> k);
+					int                      L   = t ? __ffsll((long long) t) - 1 : kLongWindow - k;
+					L                            = min(L, n_steps - i);
+					n_vol += (unsigned) L;
+					n_empty += (unsigned) L;
+					i += L;
+					i_min          = i;
+					voxel_occupied = false;
+				}
+			}
+			__syncwarp();
+		}
+		c_vol += n_vol; c_dist += n_dist; c_empty += n_empty;
+		if (lane == 0) {
+			float frag_depth = 0.0f;
+			if (P.depth && out[3] > 0.0f && i_first_hit < n_steps) {
+				const double pm[3] = {(double) (entry[0] + step[0] * (float) i_first_hit) - 0.5,
+				                      (double) (entry[1] + step[1] * (float) i_first_hit) - 0.5,
+				                      (double) (entry[2] + step[2] * (float) i_first_hit) - 0.5};
+				const double z = P.pvm_z[0] * pm[0] + P.pvm_z[1] * pm[1] + P.pvm_z[2] * pm[2] + P.pvm_z[3];
+				const double w = P.pvm_w[0] * pm[0] + P.pvm_w[1] * pm[1] + P.pvm_w[2] * pm[2] + P.pvm_w[3];
+				frag_depth     = (float) (z / w);
+			}
+			store_over_clear(P, (size_t) p, frag_depth >= 0.0f, out, frag_depth);
+		}
+	}
+	if (P.counts && lane == 0 && (c_vol | c_dist | c_empty)) {
+		atomicAdd(P.counts + 0, c_vol);
+		atomicAdd(P.counts + 1, c_dist);
+		atomicAdd(P.counts + 2, c_empty);
+	}
+	// the last CTA out publishes the frame's long-ray count (host-visible hint, read a frame or more later without synchronising)
+	// and resets the queue for the next frame (every CTA read `count` before it got here)
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		if (atomicAdd(&P.lq->done, 1u) == gridDim.x - 1u) {
+			if (P.long_hint) *P.long_hint = (int) min(P.lq->count, 0x7fffffffu);
+			P.lq->count = 0u;
+			P.lq->head  = 0u;
+			P.lq->done  = 0u;
 		}
 	}
 }
@@ -812,6 +1062,43 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 	// on-the-fly gradients (volume created without a gradient map); the variant always counts, into scratch if need be
 	const bool otf = P.use_gradient && !vol->precomputed_gradient;
 	const bool load = opt->load_framebuffer != 0;
+	// long rays go to raycast_long_kernel (distance-map production variants, plain view): VKV_RC_LONG_T=<trips> moves the hand-over
+	// point, 0 keeps every ray in the one-kernel march
+	int long_T = 64;
+	if (const char *lt = getenv("VKV_RC_LONG_T")) long_T = atoi(lt);
+	const bool use_long = long_T > 0 && (opt->skipping_type == VKV_SKIP_DISTANCE || opt->skipping_type == VKV_SKIP_ANISOTROPIC_DISTANCE) && !otf &&
+	                      !exact && !load && opt->test == VKV_TEST_NONE && !getenv("VKV_RC_TRACE");
+	// Frames with MANY long rays are throughput-bound: one ray per warp costs them more issue slots than it saves latency (measured:
+	// 256^3 blobs at 512x512, +115 %).  The hand-over is therefore kept only while the previous frame's count stayed below
+	// kLongMaxRays; a frame above it switches it off for 32 frames, then it is tried again.
+	constexpr int kLongMaxRays = 20000;
+	if (use_long && vol->h_long_hint) {
+		if (vol->long_holdoff == 0 && *static_cast<volatile int *>(vol->h_long_hint) > kLongMaxRays && !getenv("VKV_RC_LONG_ALWAYS")) {
+			vol->long_holdoff = 32;
+			*vol->h_long_hint = 0;
+		}
+	}
+	const bool long_now = use_long && vol->long_holdoff == 0;
+	if (use_long && vol->long_holdoff > 0) --vol->long_holdoff;
+	if (long_now) {
+		if (!vol->h_long_hint) {
+			VKV_CUDA_CHECK(cudaHostAlloc(&vol->h_long_hint, sizeof(int), cudaHostAllocMapped));
+			*vol->h_long_hint = 0;
+		}
+		if (!vol->d_lq) {
+			constexpr int kCap = 1 << 18;        // 262 144 rays x 80 B = 21 MB; a frame with more long rays keeps the rest in the march
+			VKV_CUDA_CHECK(cudaMalloc(&vol->d_lq, sizeof(LongQueue)));
+			VKV_CUDA_CHECK(cudaMemsetAsync(vol->d_lq, 0, sizeof(LongQueue), s));
+			VKV_CUDA_CHECK(cudaMalloc(&vol->d_lrays, (size_t) kCap * sizeof(LongRay)));
+			vol->long_cap = kCap;
+		}
+		P.lq       = static_cast<LongQueue *>(vol->d_lq);
+		P.lrays    = static_cast<LongRay *>(vol->d_lrays);
+		P.long_T   = long_T;
+		P.long_cap = vol->long_cap;
+		P.long_hint = vol->h_long_hint;
+		if (getenv("VKV_RC_DEBUG")) fprintf(stderr, "[vkv] long rays last frame: %d\n", *vol->h_long_hint);
+	}
 	if ((otf || load) && !P.counts) P.counts = reinterpret_cast<unsigned long long *>(vol->d_counts_scratch);
 	// gridDim.z is limited to 65535: launch the tile list in chunks (one chunk up to 134 Mpixel with 64x32 tiles)
 	// debug: VKV_RC_TRACE=<file> dumps per-warp {start ns, end ns, loop iterations} of this launch (synchronous; never set in production)
@@ -892,6 +1179,12 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 			default: VKV_RC(VKV_SKIP_ANISOTROPIC_DISTANCE); break;
 		}
 #undef VKV_RC
+		VKV_LAUNCHED();
+	}
+	if (long_now) {
+		const unsigned grid2 = (unsigned) vol->ctx->sm_count * 4u;
+		if (opt->skipping_type == VKV_SKIP_DISTANCE) raycast_long_kernel<VKV_SKIP_DISTANCE><<<grid2, 32 * kLongWarps, 0, s>>>(P);
+		else raycast_long_kernel<VKV_SKIP_ANISOTROPIC_DISTANCE><<<grid2, 32 * kLongWarps, 0, s>>>(P);
 		VKV_LAUNCHED();
 	}
 	if (d_trace) {
