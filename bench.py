@@ -50,9 +50,10 @@ WORKLOADS = {
     "c3": dict(dim=(1024, 1024, 795), kind=2, seed=0x5EED0003, voxel=(0.0003, 0.0003, 0.0007), axis_angle=(1, 0, 0, 90),
                tf=dict(intensity_min=0.2, intensity_max=0.8, gradient_min=0.0, gradient_max=0.0), frame=(1920, 1080), skip=3, clip=2.0,
                inside=True, name="aniso1024: 1024x1024x795 anisotropic voxels, camera inside + clip plane, anisotropic distance maps"),
-    "c4": dict(dim=(1024, 1024, 1024), kind=0, seed=0x5EED0004, voxel=(0.001, 0.001, 0.001), axis_angle=(1, 0, 0, 0),
+    # (kind 3, the noise-modulated blobs: the plain blobs of kind 0 are so smooth at 1024^3 that the sweep's gradient window shows nothing)
+    "c4": dict(dim=(1024, 1024, 1024), kind=3, seed=0x5EED0004, voxel=(0.001, 0.001, 0.001), axis_angle=(1, 0, 0, 0),
                tf=dict(intensity_min=0.1, intensity_max=1.0, gradient_min=0.05, gradient_max=0.25), frame=(1920, 1080), skip=2, clip=5.0,
-               name="tf_sweep1024: 1024^3 blobs, TF sweep"),
+               name="tf_sweep1024: 1024^3 noise-modulated blobs, TF sweep"),
     "c5": dict(dim=(4096, 4096, 2048), kind=3, seed=0x5EED0005, voxel=(0.00025, 0.00025, 0.00025), axis_angle=(1, 0, 0, 0),
                tf=dict(intensity_min=0.15, intensity_max=1.0, gradient_min=0.0, gradient_max=0.0), frame=(7680, 4320), skip=2, clip=5.0,
                name="big4096: 4096x4096x2048 u8 (34 GB), 7680x4320, ESS distance, ERT on"),

@@ -710,3 +710,47 @@ def test_two_streams_alternating_on_one_volume_are_ordered(ctx):
     for k, fb in enumerate(frames):
         assert torch.equal(fb, want[k & 1]), k
     vol.close()
+
+
+@pytest.mark.parametrize("skip", [SKIP_DISTANCE, SKIP_ANISOTROPIC_DISTANCE])
+def test_long_ray_pass_is_bit_identical(ctx, skip):
+    """Rays still marching after VKV_RC_LONG_T loop trips are suspended and finished by raycast_long_kernel (one ray per warp, 64
+    lattice steps evaluated at once, the shader's state machine replayed over them).  The replay visits the same steps in the same
+    order with the same arithmetic: frames, depth and all four counters are identical whatever the hand-over point — never (0),
+    the default (64), or almost at once (6: nearly every ray of the frame goes through the queue)."""
+    import os
+    import torch
+    shape, width, height = (96, 128, 160), 512, 384
+    D, H, W = shape
+    opt = VolumeOptions(**TF_SETS[0])
+    tfu = capi.transfer_function_uniform(opt)
+    vol = capi.Volume(ctx, W, H, D)
+    vol.upload(scene.blobs_volume(shape, seed=8, n_blobs=20))
+    vol.compute_gradient_map(tfu)
+    vol.update_transfer_function(opt, skip)
+    it = scene.image_transform((0.004,) * 3, (W, H, D))
+    ropt = RenderOptions(skipping_type=skip, clip_distance=5.0)
+    stream = torch.cuda.current_stream().cuda_stream
+    results = {}
+    try:
+        for T in ("0", "64", "6"):
+            os.environ["VKV_RC_LONG_T"] = T
+            os.environ["VKV_RC_LONG_ALWAYS"] = "1"
+            frames = []
+            for eye in ((70, 40, 100), (72, 44, 98), (-60, 80, 90)):
+                cu, ru = vol.make_uniforms(scene.look_at_camera(eye, aspect=width / height), it, 5.0)
+                fb = torch.zeros((height, width, 4), dtype=torch.uint8, device="cuda")
+                depth = torch.zeros((height, width), dtype=torch.float32, device="cuda")
+                counts = torch.zeros(4, dtype=torch.int64, device="cuda")
+                vol.render(cu, ru, tfu, ropt, width, height, fb.data_ptr(), depth.data_ptr(), counts.data_ptr(), stream)
+                torch.cuda.synchronize()
+                frames.append((fb, depth, counts.tolist()))
+            results[T] = frames
+    finally:
+        os.environ.pop("VKV_RC_LONG_T", None)
+        os.environ.pop("VKV_RC_LONG_ALWAYS", None)
+    for T in ("64", "6"):
+        for (fa, da, ca), (fb_, db, cb) in zip(results["0"], results[T]):
+            assert torch.equal(fa, fb_) and torch.equal(da, db) and ca == cb, T
+    assert results["0"][0][2][0] > 100000 and results["0"][0][2][3] > 10000        # a real frame: samples taken, pixels covered
+    vol.close()

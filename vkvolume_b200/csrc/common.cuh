@@ -149,6 +149,7 @@ struct vkv_volume {
 	int                 long_cap = 0;
 	int                *h_long_hint = nullptr;        // pinned + mapped: long rays of the last frame that used the hand-over
 	int                 long_holdoff = 0;             // frames to go before the hand-over is tried again
+	unsigned            long_seq = 0;                 // launch sequence number: tags the queue records of a launch
 	// the stream of the volume's previous call (api.cu ordered_stream): a call on another stream is ordered after it
 	cudaStream_t        last_stream = nullptr;
 	bool                last_stream_valid = false;

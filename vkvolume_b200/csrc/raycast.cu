@@ -41,10 +41,10 @@ struct LongRay {
 };
 static_assert(sizeof(LongRay) == 80, "LongRay layout");
 struct LongQueue {
-	unsigned count;             // rays pushed by raycast_kernel (may exceed capacity: the excess was not suspended)
-	unsigned head;              // next ray to pop in raycast_long_kernel
+	unsigned count;             // slots reserved by raycast_kernel (may exceed capacity: the excess was not suspended)
+	unsigned head;              // next slot to hand out
 	unsigned done;              // CTAs of raycast_long_kernel that have exited (the last one resets the queue)
-	unsigned capacity;
+	unsigned pad;
 };
 
 struct RayParams {
@@ -152,6 +152,16 @@ __device__ __forceinline__ float gradient_otf(cudaTextureObject_t tex, const uin
 }
 
 __device__ __forceinline__ float srgb_encode(float c) { return c <= 0.0031308f ? 12.92f * c : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f; }
+// The hardware-filter production variants (kFast in rc_cast_pixel) take the liberties every Vulkan driver takes with the reference's
+// GLSL: multiply-adds contracted (GLSL allows it without `precise`), divisions and pow at the 2-3 ulp the Vulkan spec asks of
+// them.  The EXACT-filter variants keep the oracle's operation-for-operation arithmetic (-fmad=false, IEEE division).
+template <bool FAST> __device__ __forceinline__ float madf_(float a, float b, float c) { return FAST ? __fmaf_rn(a, b, c) : a * b + c; }
+template <bool FAST> __device__ __forceinline__ float divf_(float a, float b) { return FAST ? __fdividef(a, b) : a / b; }
+template <bool FAST> __device__ __forceinline__ float srgb_encode_(float c)
+{
+	if (!FAST) return srgb_encode(c);
+	return c <= 0.0031308f ? 12.92f * c : __fmaf_rn(1.055f, __powf(c, 1.0f / 2.4f), -0.055f);
+}
 // R8G8B8A8_SRGB load (sRGB EOTF of the Vulkan specification): what the blender reads back from the attachment
 __device__ __forceinline__ float srgb_decode(unsigned b)
 {
@@ -163,15 +173,16 @@ __device__ __forceinline__ unsigned unorm8(float c) { return (unsigned) (clampf_
 
 // Blend over the render-pass clear (0,0,0,1) / depth 0 and store: rgb = src.rgb, a = src.a * (1 - src.a)
 // (volume_render_subpass.cpp:176-190), R8G8B8A8_SRGB encode; pixels that fail the depth test keep the clear values.
+template <bool FAST>
 __device__ __forceinline__ unsigned pack_over_clear(bool pass, const float out[4])
 {
 	unsigned packed = 0xff000000u;
 	if (pass) {
 		// the built-in transfer function is grey (volume_component.cpp:250-261): one encode serves the three channels
-		const unsigned er = unorm8(srgb_encode(clampf_(out[0], 0.0f, 1.0f)));
+		const unsigned er = unorm8(srgb_encode_<FAST>(clampf_(out[0], 0.0f, 1.0f)));
 		const bool     grey = out[1] == out[0] && out[2] == out[0];
-		const unsigned eg = grey ? er : unorm8(srgb_encode(clampf_(out[1], 0.0f, 1.0f)));
-		const unsigned eb = grey ? er : unorm8(srgb_encode(clampf_(out[2], 0.0f, 1.0f)));
+		const unsigned eg = grey ? er : unorm8(srgb_encode_<FAST>(clampf_(out[1], 0.0f, 1.0f)));
+		const unsigned eb = grey ? er : unorm8(srgb_encode_<FAST>(clampf_(out[2], 0.0f, 1.0f)));
 		packed = er | (eg << 8) | (eb << 16) | (unorm8(out[3] * (1.0f - out[3])) << 24);
 	}
 	return packed;
@@ -207,55 +218,219 @@ constexpr int kRcWarps = VKV_RC_WARPS, kRcThreads = 32 * kRcWarps, kRcRows = 2 *
 #ifndef VKV_RC_MIN_CTAS
 #define VKV_RC_MIN_CTAS 16
 #endif
+// ---- long rays: one ray per warp, 64 lattice steps at a time -------------------------------------------------------------
+// A ray's march is a serial state machine (skip-map hop -> next position -> hop ...), ~1300 cycles per trip when 20 rays share a
+// warp in lockstep: a frame's time used to be the ~180 trips of its longest rays (profiles/r1s_trace.md).  What a step of the
+// machine READS, however, depends on the step index alone (pos = entry + i * step): so a warp takes one suspended ray and
+// evaluates 32 consecutive lattice steps at once — lane l looks at step base + l: block index, skip-map byte, the hop that byte
+// would cause, the filtered sample(s) and its colour-table entry, 32 independent fetches instead of a 32-deep dependent chain —
+// parks them in shared memory and then REPLAYS the shader's state machine over the window with no memory access at all
+// (a few ALU instructions per visited step, every lane computing the same state).  The replay visits exactly the steps
+// the serial march visits, in the same order, with the same fp32 operations: frames and counters are bit-identical to the
+// one-kernel march (tests/test_parity_gpu.py::test_long_ray_pass_is_bit_identical).
+__device__ __forceinline__ void store_over_clear(const RayParams &P, size_t p, bool pass, const float out[4], float frag_depth)
+{
+	reinterpret_cast<unsigned *>(P.rgba8)[p] = pack_over_clear<true>(pass, out);        // long rays exist in the kFast variants only
+	if (P.depth) P.depth[p] = pass ? frag_depth : 0.0f;
+}
+// 1 / (map cells the ray advances per trip along axis k): sdi of the shader (volume_render.frag:229)
+template <bool FAST> __device__ __forceinline__ float sdt_inv_(const RayParams &P, float step_k, int k)
+{
+	if (FAST) return __fdividef(1.0f, step_k * P.vol_to_map[k]);
+	const float sdt = step_k * P.dimf[k] / P.block_size[k];
+	return 1.0f / sdt;
+}
+constexpr int kLongWindow = 64;
+struct LongConsts {
+	int      back, dim_b1[3];
+	TFRange  tb;
+	unsigned tb_vspan, tb_gspan;
+};
+__device__ __forceinline__ LongConsts long_consts(const RayParams &P)
+{
+	LongConsts L;
+	L.back      = (int) ceilf(P.sampling_factor);
+	L.dim_b1[0] = P.dim_b[0] - 1; L.dim_b1[1] = P.dim_b[1] - 1; L.dim_b1[2] = P.dim_b[2] - 1;
+	L.tb        = P.use_gradient ? P.bounds->tex_all : P.bounds->tex_row255;
+	L.tb_vspan  = L.tb.v_hi - L.tb.v_lo;
+	L.tb_gspan  = L.tb.g_hi - L.tb.g_lo;
+	return L;
+}
+
+// Finishes suspended ray j with the whole warp.  s_c / s_idx / s_hop: this warp's kLongWindow-entry shared-memory window.
+template <int SKIP>
+__device__ __forceinline__ void rc_long_ray(const RayParams &P, const LongConsts &LC, const unsigned j, const int lane, float4 *s_c, unsigned *s_idx, int *s_hop,
+                                            unsigned long long &c_vol, unsigned long long &c_dist, unsigned long long &c_empty)
+{
+	const int      back = LC.back;
+	const int      dim_b1[3] = {LC.dim_b1[0], LC.dim_b1[1], LC.dim_b1[2]};
+	const TFRange  tb = LC.tb;
+	const unsigned tb_vspan = LC.tb_vspan, tb_gspan = LC.tb_gspan;
+	const float4 *r = reinterpret_cast<const float4 *>(P.lrays + j);
+	const float4 r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3], r4 = r[4];
+	const unsigned p = __float_as_uint(r0.x);
+	int            i = __float_as_int(r0.y), i_min = __float_as_int(r0.z), i_first_hit = __float_as_int(r0.w);
+	const int      n_steps = __float_as_int(r1.x);
+	unsigned       idx_last = __float_as_uint(r1.y);
+	bool           voxel_occupied = __float_as_uint(r1.z) != 0u;
+	float          out[4]   = {r2.x, r2.y, r2.z, r2.w};
+	const float    entry[3] = {r3.x, r3.y, r3.z}, step[3] = {r3.w, r4.x, r4.y};
+	float          sdt_inv[3];
+#pragma unroll
+	for (int k = 0; k < 3; ++k) sdt_inv[k] = sdt_inv_<true>(P, step[k], k);        // the same arithmetic as the march that suspended the ray
+	const bool neg[3] = {sdt_inv[0] < 0.0f, sdt_inv[1] < 0.0f, sdt_inv[2] < 0.0f};
+	const uint8_t *__restrict__ Dm = P.map_ptrs[0];
+	if (SKIP == VKV_SKIP_ANISOTROPIC_DISTANCE) Dm = P.map_ptrs[(step[2] < 0 ? 1 : 0) + (step[1] < 0 ? 2 : 0) + (step[0] < 0 ? 4 : 0)];        // sign(step) == sign(dir)
+	unsigned n_vol = 0u, n_dist = 0u, n_empty = 0u;
+	bool     done = false;
+	while (i < n_steps && !done) {
+		// the window starts where a step back (volume_render.frag:253-261) from the current step could land
+		const int base = max(i - back, i_min);
+		unsigned  my_idx[2];
+		bool      my_vis[2];
+#pragma unroll
+		for (int h = 0; h < 2; ++h) {
+			const int   slot   = 32 * h + lane;
+			const float fi     = (float) (base + slot);
+			const float pos[3] = {__fmaf_rn(fi, step[0], entry[0]), __fmaf_rn(fi, step[1], entry[1]), __fmaf_rn(fi, step[2], entry[2])};
+			float       u[3];
+			int         u_i[3];
+#pragma unroll
+			for (int k = 0; k < 3; ++k) {
+				u[k]   = P.vol_to_map[k] * pos[k];
+				u_i[k] = clamp0_((int) u[k], dim_b1[k]);
+			}
+			const unsigned idx  = ((unsigned) u_i[2] * (unsigned) P.dim_b[1] + (unsigned) u_i[1]) * (unsigned) P.dim_b[0] + (unsigned) u_i[0];
+			const unsigned dist = __ldg(Dm + idx);
+			const float    intensity = tex3D<float>(P.tex_v, pos[0], pos[1], pos[2]);
+			const float    gradient  = P.use_gradient ? tex3D<float>(P.tex_g, pos[0], pos[1], pos[2]) : 1.0f;
+			int            hop       = 0;
+			if (dist > 0u) {
+				float       dxyz[3];
+				const float fd = (float) dist, omfd = 1.0f - fd;
+#pragma unroll
+				for (int k = 0; k < 3; ++k) {
+					const float rr  = clampf_((float) u_i[k] - u[k], -1.0f, 0.0f);
+					const float bse = neg[k] ? omfd : fd;
+					dxyz[k]         = (bse + rr) * sdt_inv[k];
+				}
+				hop = max((int) ceilf(fminf(fminf(dxyz[0], dxyz[1]), dxyz[2])), 1);
+			}
+			const int ti = tf_texel(intensity), tg = tf_texel(gradient);
+			float4    c  = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
+			if ((unsigned) ti - tb.v_lo <= tb_vspan && (unsigned) tg - tb.g_lo <= tb_gspan) c = __ldg(P.ctab + tg * 256 + ti);
+			s_idx[slot] = idx;
+			s_hop[slot] = hop;
+			s_c[slot]   = c;
+			my_idx[h]         = idx;
+			my_vis[h]         = c.w >= 0.0f;
+		}
+		// bit k of a mask speaks for step base + k
+		const unsigned long long m_vis = (unsigned long long) __ballot_sync(0xffffffffu, my_vis[0]) | ((unsigned long long) __ballot_sync(0xffffffffu, my_vis[1]) << 32);
+		auto same_mask = [&](unsigned ref) {
+			return (unsigned long long) __ballot_sync(0xffffffffu, my_idx[0] == ref) | ((unsigned long long) __ballot_sync(0xffffffffu, my_idx[1] == ref) << 32);
+		};
+		unsigned long long m_same = same_mask(idx_last);
+		__syncwarp();
+		// Replay of the fragment shader's loop body (volume_render.frag:215-312) over the window; every lane carries the same state.
+		// One trip of this loop is one EVENT of the march: a skip-map consultation, a visible sample, or a whole run of empty
+		// samples (the common case on a ray that grazes the surface: nothing but the counters changes along it).
+		while (i < n_steps) {
+			const int k = i - base;
+			if (k >= kLongWindow) break;
+			if (!voxel_occupied && !((m_same >> k) & 1ull)) {
+				++n_dist;
+				const int hop = s_hop[k];
+				if (hop > 0) {
+					i += hop;
+				} else {
+					voxel_occupied = true;
+					idx_last       = s_idx[k];
+					m_same         = same_mask(idx_last);
+					i              = max(i - back, i_min);
+				}
+			} else if ((m_vis >> k) & 1ull) {
+				++n_vol;
+				const float4   c   = s_c[k];
+				const unsigned idx = s_idx[k];
+				voxel_occupied = true;
+				if (idx != idx_last) {
+					idx_last = idx;
+					m_same   = same_mask(idx_last);
+				}
+				const float w = 1.0f - out[3];
+				out[0] = __fmaf_rn(w, c.x, out[0]); out[1] = __fmaf_rn(w, c.y, out[1]); out[2] = __fmaf_rn(w, c.z, out[2]); out[3] = __fmaf_rn(w, c.w, out[3]);
+				if (c.w > 0.0f) i_first_hit = i;
+				if (out[3] > 0.99f && P.ert) {
+					out[3] = 1.0f;
+					done   = true;
+					break;
+				}
+				++i;
+				i_min = i;
+			} else {
+				// step k is sampled and empty; the steps after it are sampled too for as long as they stay in block idx_last
+				// (voxel_occupied is false from here on) and are empty themselves
+				const unsigned long long run = ~m_vis & (m_same | (1ull << k));
+				const unsigned long long t   = ~(run >> k);
+				int                      L   = t ? __ffsll((long long) t) - 1 : kLongWindow - k;
+				L                            = min(L, n_steps - i);
+				n_vol += (unsigned) L;
+				n_empty += (unsigned) L;
+				i += L;
+				i_min          = i;
+				voxel_occupied = false;
+			}
+		}
+		__syncwarp();
+	}
+	c_vol += n_vol; c_dist += n_dist; c_empty += n_empty;
+	if (lane == 0) {
+		float frag_depth = 0.0f;
+		if (P.depth && out[3] > 0.0f && i_first_hit < n_steps) {
+			const double pm[3] = {(double) (entry[0] + step[0] * (float) i_first_hit) - 0.5,
+			                      (double) (entry[1] + step[1] * (float) i_first_hit) - 0.5,
+			                      (double) (entry[2] + step[2] * (float) i_first_hit) - 0.5};
+			const double z = P.pvm_z[0] * pm[0] + P.pvm_z[1] * pm[1] + P.pvm_z[2] * pm[2] + P.pvm_z[3];
+			const double w = P.pvm_w[0] * pm[0] + P.pvm_w[1] * pm[1] + P.pvm_w[2] * pm[2] + P.pvm_w[3];
+			frag_depth     = (float) (z / w);
+		}
+		store_over_clear(P, (size_t) p, frag_depth >= 0.0f, out, frag_depth);
+	}
+}
+
 // A CTA is two warps = a 16x4 pixel tile; small CTAs keep the register file busy while long rays finish.
 // grid = (CTAs per tile in x, CTAs per tile in y, tiles of this launch).
 // OTF: the volume has no gradient map; gradients come from gradient_otf (always instantiated with COUNT).
 // TRACE: debug instantiation (VKV_RC_TRACE) that also records the per-warp timeline.
 // LOAD: blend and depth-test over the existing contents of the target (vkv_render_options::load_framebuffer) instead of the
 // render-pass clear, and honour depth_attachment; these instantiations always count (COUNT).
-template <int SKIP, bool EXACT, bool COUNT, bool OTF = false, bool TRACE = false, bool LOAD = false>
-__global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CTAS) * 2 / kRcWarps) raycast_kernel(const __grid_constant__ RayParams P)
-{
-	__shared__ unsigned long long s_cnt[kRcWarps][4];
+struct RcTraceAcc {        // TRACE instantiation only
+	unsigned  tr_lanes = 0, tr_d = 0, tr_r = 0, tr_mixed = 0;
+	long long tc_top = 0, tc_req = 0, tc_d = 0, tc_v = 0, tc_mark = 0;        // cycles per loop section
+};
 
-	// CTA -> tile -> pixel
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	unsigned long long t_start = 0;
-	unsigned           n_iter  = 0, tr_lanes = 0, tr_d = 0, tr_r = 0, tr_mixed = 0;
-	long long          tc_top = 0, tc_req = 0, tc_d = 0, tc_v = 0, tc_mark = 0;        // trace: cycles per loop section
-	if (TRACE) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
-	// Tiles are issued from the middle of this launch's tile list outwards (m, m-1, m+1, m-2, ...): the long rays sit
-	// near the image centre, so their latency chains start at t = 0 and the cheap border tiles fill the tail.
-	// With a history (the previous frame of this volume at this frame size) the tiles are issued in decreasing order of the loop
-	// count their longest ray needed last time: the frame time is the critical path of a few hundred long warps (profiles/
-	// r1s_trace.md), so they have to start at t = 0, not whenever the sweep reaches them.
+// One pixel: analytic ray entry, the fragment shader's march, blend + store.  Counters accumulate into the caller's (a persistent
+// warp casts many pixel blocks); n_iter_out is the number of loop trips this lane made (tile cost, trace).
+// OTF: the volume has no gradient map; gradients come from gradient_otf (always instantiated with COUNT).
+// TRACE: debug instantiation (VKV_RC_TRACE) that also records the per-warp timeline.
+// LOAD: blend and depth-test over the existing contents of the target (vkv_render_options::load_framebuffer) instead of the
+// render-pass clear, and honour depth_attachment; these instantiations always count (COUNT).
+template <int SKIP, bool EXACT, bool COUNT, bool OTF, bool TRACE, bool LOAD>
+__device__ __forceinline__ void rc_cast_pixel(const RayParams &P, const int px, const int py, const int lane, unsigned &n_vol, unsigned &n_dist,
+                                              unsigned &n_empty, unsigned &covered_acc, unsigned &n_iter_out, RcTraceAcc &tr)
+{
 	// (compiled into the distance-map production variants only: the other modes are throughput-bound and keep their old code)
 	constexpr bool kHist = (SKIP == VKV_SKIP_DISTANCE || SKIP == VKV_SKIP_ANISOTROPIC_DISTANCE) && !OTF && !EXACT && !LOAD;
-	// the same variants hand their long rays to raycast_long_kernel (P.long_T loop iterations into the march; 0: never)
+	// the same variants hand their long rays over (P.long_T loop iterations into the march; 0: never)
 	constexpr bool kLong = kHist;
-	bool           suspended = false;
-	const int seq        = P.seq_base + (int) blockIdx.z;
-	const int local_tile = (kHist && P.tile_order) ? (int) P.tile_order[seq] : centre_out(seq, P.my_tiles);
-	const int tile       = P.tile_first + local_tile * P.tile_stride;
-	const int tile_y = P.tiles_x_magic ? (int) __umulhi((unsigned) tile, P.tiles_x_magic) : tile / P.tiles_x, tile_x = tile - tile_y * P.tiles_x;
-	const int tx0 = tile_x * P.tile_w + (int) blockIdx.x * 16;
-	const int ty0 = tile_y * P.tile_h + (int) blockIdx.y * kRcRows;
-	const int px = tx0 + (warp & 1) * 8 + (lane & 7);
-	const int py = ty0 + (warp >> 1) * 4 + (lane >> 3);
+	// hardware-filter production variants: contracted multiply-adds, 2-ulp divisions, fp32 entry point away from the silhouette
+	constexpr bool kFast = !EXACT && !OTF && !LOAD;
 	const bool   in_frame = px < P.width && py < P.height;
 	const size_t p        = (size_t) py * P.width + px;
-
-	// CTA-uniform rejection against the projected bounds of the unit cube: such pixels keep the clear colour
-	// (0,0,0,1) (render_pipeline.cpp:38) and depth 0.
-	if (tx0 > P.bbox[2] || tx0 + 15 < P.bbox[0] || ty0 > P.bbox[3] || ty0 + kRcRows - 1 < P.bbox[1]) {
-		if (in_frame && !LOAD) {
-			reinterpret_cast<unsigned *>(P.rgba8)[p] = 0xff000000u;
-			if (P.depth) P.depth[p] = 0.0f;
-		}
-		return;
-	}
-
-	unsigned n_vol = 0, n_dist = 0, n_empty = 0, covered = 0;
+	unsigned covered = 0u;        // this pixel
+	unsigned n_iter  = 0u;
+	bool     suspended = false;
 	float    out[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 	float    frag_depth = 0.0f;
 	float    dst_depth  = 0.0f;        // what the depth attachment holds (LOAD) or the clear value
@@ -265,7 +440,8 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 		if (LOAD && P.depth) dst_depth = P.depth[p];
 		// ---- analytic ray entry (replaces both vertex shaders + rasteriser) ----
 		// (1) conservative fp32 rejection (approximate divisions; only ever used to say "certainly misses")
-		bool maybe = px >= P.bbox[0] && px <= P.bbox[2] && py >= P.bbox[1] && py <= P.bbox[3];
+		bool  maybe = px >= P.bbox[0] && px <= P.bbox[2] && py >= P.bbox[1] && py <= P.bbox[3];
+		float entry_fast[3] = {0.0f, 0.0f, 0.0f};
 		if (maybe) {
 			float tnf = -INFINITY, tff = INFINITY, sdf = 0.0f;
 #pragma unroll
@@ -279,9 +455,18 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 			}
 			const float t0f = fmaxf(fmaxf(tnf, __fdividef(-P.fs0, sdf)), 0.0f);
 			// reject only when the miss is far outside fp32 rounding (relative 1e-3); NaNs fall through to fp64
-			if (t0f > tff + 1e-3f * (fabsf(tff) + fabsf(t0f)) + 1e-6f) maybe = false;
+			const float band = 1e-3f * (fabsf(tff) + fabsf(t0f)) + 1e-6f;
+			if (t0f > tff + band) maybe = false;
+			// kFast: a hit that is as far from the silhouette on the other side takes its entry point from the same fp32 numbers
+			// (error ~1e-7 of the box: 1e-4 voxel); only the band in between (a pixel or two wide) pays for fp64
+			else if (kFast && t0f < tff - band && sdf > 1e-12f) {
+				covered = 1;
+				maybe   = false;
+#pragma unroll
+				for (int k = 0; k < 3; ++k) entry_fast[k] = __fmaf_rn(t0f, P.fd0[k] + (float) px * P.fddx[k] + (float) py * P.fddy[k], P.fo[k]);
+			}
 		}
-		float entry[3] = {0.0f, 0.0f, 0.0f};
+		float entry[3] = {entry_fast[0], entry_fast[1], entry_fast[2]};
 		if (maybe) {
 			// (2) exact decision and entry point in fp64
 			double d[3], tn = -INFINITY, tf = INFINITY;
@@ -293,7 +478,7 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 					if (P.o[k] < 0.0 || P.o[k] > 1.0) hit = false;
 				} else {
 					double t0, t1;
-					if (P.flags & 2) {
+					if (kFast) {
 						const double r = 1.0 / d[k];
 						t0 = (0.0 - P.o[k]) * r; t1 = (1.0 - P.o[k]) * r;
 					} else {
@@ -334,11 +519,12 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 			// ---- fragment shader main() (volume_render.frag:117-336) ----
 			const float dv[3] = {entry[0] - P.cam_pos_tex[0], entry[1] - P.cam_pos_tex[1], entry[2] - P.cam_pos_tex[2]};
 			const float dl    = sqrtf((dv[0] * dv[0] + dv[1] * dv[1]) + dv[2] * dv[2]);
-			const float dir[3] = {dv[0] / dl, dv[1] / dl, dv[2] / dl};
+			const float dli    = kFast ? __fdividef(1.0f, dl) : 0.0f;
+			const float dir[3] = {kFast ? dv[0] * dli : dv[0] / dl, kFast ? dv[1] * dli : dv[1] / dl, kFast ? dv[2] * dli : dv[2] / dl};
 			float t2[3];
 #pragma unroll
 			for (int k = 0; k < 3; ++k) {
-				const float inv   = 1.0f / dir[k];
+				const float inv   = divf_<kFast>(1.0f, dir[k]);
 				const float t_min = -entry[k] * inv, t_max = (1.0f - entry[k]) * inv;
 				t2[k]             = fmaxf(t_min, t_max);
 			}
@@ -375,7 +561,7 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 				const int n_steps = (int) ceilf((float) P.dim_max * ray_distance * P.sampling_factor);
 				float     step[3];
 #pragma unroll
-				for (int k = 0; k < 3; ++k) step[k] = dir[k] * ray_distance / ((float) n_steps - 1.0f);
+				for (int k = 0; k < 3; ++k) step[k] = divf_<kFast>(dir[k] * ray_distance, (float) n_steps - 1.0f);
 				bool inside = true;
 #pragma unroll
 				for (int k = 0; k < 3; ++k) {
@@ -385,10 +571,7 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 				if (inside) {
 					float sdt_inv[3];
 #pragma unroll
-					for (int k = 0; k < 3; ++k) {
-						const float sdt = step[k] * P.dimf[k] / P.block_size[k];
-						sdt_inv[k]      = 1.0f / sdt;
-					}
+					for (int k = 0; k < 3; ++k) sdt_inv[k] = sdt_inv_<kFast>(P, step[k], k);
 					// (st + sg * dist) of the shader is an exact small integer: dist when the ray advances along +k, 1 - dist along -k
 					// (BLOCK_SKIP: 1 or 0).  sdt_inv is finite, non-zero and not NaN here (the `inside` test above saw to that).
 					const bool neg[3] = {sdt_inv[0] < 0.0f, sdt_inv[1] < 0.0f, sdt_inv[2] < 0.0f};
@@ -419,9 +602,9 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 					for (;;) {
 					for (; i < n_steps && (!kLong || n_iter < trip_limit);) {
 						if (kHist || TRACE) ++n_iter;
-						if (TRACE) tc_mark = clock64();
+						if (TRACE) tr.tc_mark = clock64();
 						const float fi     = (float) i;
-						const float pos[3] = {entry[0] + fi * step[0], entry[1] + fi * step[1], entry[2] + fi * step[2]};
+						const float pos[3] = {madf_<kFast>(fi, step[0], entry[0]), madf_<kFast>(fi, step[1], entry[1]), madf_<kFast>(fi, step[2], entry[2])};
 						float    u[3];
 						int      u_i[3] = {0, 0, 0};
 						unsigned idx    = 0u;
@@ -442,7 +625,7 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 						// iteration with its lanes out of phase.  (Fetching early returns the same value: positions depend on the step
 						// index alone.)  BLOCK mode is texture-throughput-bound rather than latency-bound (measured: alignment costs 10 %
 						// there and gains 10 % with the distance maps), so its lanes refill on their own.
-						if (TRACE) { const long long c = clock64(); tc_top += c - tc_mark; tc_mark = c; }
+						if (TRACE) { const long long c = clock64(); tr.tc_top += c - tr.tc_mark; tr.tc_mark = c; }
 						constexpr bool kLookAhead = !OTF && !EXACT;
 						unsigned       dist       = 0u;
 						int            k          = 0;
@@ -457,9 +640,9 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 								pre_base = i;
 								k        = 0;
 								const float f1 = (float) (i + 1), f2 = (float) (i + 2), f3 = (float) (i + 3);
-								const float q1[3] = {entry[0] + f1 * step[0], entry[1] + f1 * step[1], entry[2] + f1 * step[2]};
-								const float q2[3] = {entry[0] + f2 * step[0], entry[1] + f2 * step[1], entry[2] + f2 * step[2]};
-								const float q3[3] = {entry[0] + f3 * step[0], entry[1] + f3 * step[1], entry[2] + f3 * step[2]};
+								const float q1[3] = {madf_<kFast>(f1, step[0], entry[0]), madf_<kFast>(f1, step[1], entry[1]), madf_<kFast>(f1, step[2], entry[2])};
+								const float q2[3] = {madf_<kFast>(f2, step[0], entry[0]), madf_<kFast>(f2, step[1], entry[1]), madf_<kFast>(f2, step[2], entry[2])};
+								const float q3[3] = {madf_<kFast>(f3, step[0], entry[0]), madf_<kFast>(f3, step[1], entry[1]), madf_<kFast>(f3, step[2], entry[2])};
 								pre_v0 = tex3D<float>(P.tex_v, pos[0], pos[1], pos[2]);
 								pre_v1 = tex3D<float>(P.tex_v, q1[0], q1[1], q1[2]);
 								pre_v2 = tex3D<float>(P.tex_v, q2[0], q2[1], q2[2]);
@@ -473,12 +656,12 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 							}
 						}
 						if (TRACE) {
-							{ const long long c = clock64(); tc_req += c - tc_mark; tc_mark = c; }
+							{ const long long c = clock64(); tr.tc_req += c - tr.tc_mark; tr.tc_mark = c; }
 							const unsigned am = __activemask();
-							tr_lanes += __popc(am);
-							tr_d += __any_sync(am, do_skip) ? 1u : 0u;
-							tr_r += any_refill ? 1u : 0u;
-							tr_mixed += (__any_sync(am, do_skip) && __any_sync(am, !do_skip)) ? 1u : 0u;
+							tr.tr_lanes += __popc(am);
+							tr.tr_d += __any_sync(am, do_skip) ? 1u : 0u;
+							tr.tr_r += any_refill ? 1u : 0u;
+							tr.tr_mixed += (__any_sync(am, do_skip) && __any_sync(am, !do_skip)) ? 1u : 0u;
 						}
 						if (SKIP != VKV_SKIP_NONE && do_skip) {
 							++n_dist;
@@ -500,9 +683,9 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 								idx_last       = idx;
 								i              = max(i - back, i_min);
 							}
-							if (TRACE) { const long long c = clock64(); tc_d += c - tc_mark; tc_mark = c; }
+							if (TRACE) { const long long c = clock64(); tr.tc_d += c - tr.tc_mark; tr.tc_mark = c; }
 						} else {
-							if (TRACE) tc_mark = clock64();
+							if (TRACE) tr.tc_mark = clock64();
 							++n_vol;
 							float intensity, gradient = 1.0f;
 							if (OTF) {
@@ -523,7 +706,7 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 							if (voxel_occupied) {
 								if (SKIP != VKV_SKIP_NONE) idx_last = idx;
 								const float w = 1.0f - out[3];
-								out[0] = out[0] + w * c.x; out[1] = out[1] + w * c.y; out[2] = out[2] + w * c.z; out[3] = out[3] + w * c.w;
+								out[0] = madf_<kFast>(w, c.x, out[0]); out[1] = madf_<kFast>(w, c.y, out[1]); out[2] = madf_<kFast>(w, c.z, out[2]); out[3] = madf_<kFast>(w, c.w, out[3]);
 								if (c.w > 0.0f) i_first_hit = i;
 								if (out[3] > 0.99f && P.ert) {
 									out[3]   = 1.0f;
@@ -535,7 +718,7 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 							}
 							++i;
 							if (SKIP != VKV_SKIP_NONE) i_min = i;
-							if (TRACE) { const long long c = clock64(); tc_v += c - tc_mark; tc_mark = c; }
+							if (TRACE) { const long long c = clock64(); tr.tc_v += c - tr.tc_mark; tr.tc_mark = c; }
 						}
 					}
 					if (!kLong || ert_done || i >= n_steps) break;
@@ -550,10 +733,10 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 						if (slot < (unsigned) P.long_cap) {
 							float4 *r = reinterpret_cast<float4 *>(P.lrays + slot);
 							r[0] = make_float4(__uint_as_float((unsigned) p), __int_as_float(i), __int_as_float(i_min), __int_as_float(i_first_hit));
-							r[1] = make_float4(__int_as_float(n_steps), __uint_as_float(idx_last), __uint_as_float(voxel_occupied ? 1u : 0u), 0.0f);
 							r[2] = make_float4(out[0], out[1], out[2], out[3]);
 							r[3] = make_float4(entry[0], entry[1], entry[2], step[0]);
 							r[4] = make_float4(step[1], step[2], 0.0f, 0.0f);
+							r[1] = make_float4(__int_as_float(n_steps), __uint_as_float(idx_last), __uint_as_float(voxel_occupied ? 1u : 0u), 0.0f);
 							suspended = true;
 							break;
 						}
@@ -584,7 +767,7 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 		if (kLong && suspended) {
 			// raycast_long_kernel finishes this ray and stores its pixel
 		} else if (!LOAD) {
-			reinterpret_cast<unsigned *>(P.rgba8)[p] = pack_over_clear(pass, out);
+			reinterpret_cast<unsigned *>(P.rgba8)[p] = pack_over_clear<kFast>(pass, out);
 			if (P.depth) P.depth[p] = pass ? frag_depth : 0.0f;
 		} else if (pass) {
 			const unsigned d8 = reinterpret_cast<const unsigned *>(P.rgba8)[p];
@@ -597,6 +780,53 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 			if (P.depth) P.depth[p] = frag_depth;
 		}
 	}
+	covered_acc += covered;
+	n_iter_out = n_iter;
+}
+
+// A CTA is two warps = a 16x4 pixel tile; small CTAs keep the register file busy while long rays finish.
+// grid = (CTAs per tile in x, CTAs per tile in y, tiles of this launch).
+template <int SKIP, bool EXACT, bool COUNT, bool OTF = false, bool TRACE = false, bool LOAD = false>
+__global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CTAS) * 2 / kRcWarps) raycast_kernel(const __grid_constant__ RayParams P)
+{
+	__shared__ unsigned long long s_cnt[kRcWarps][4];
+
+	// CTA -> tile -> pixel
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	unsigned long long t_start = 0;
+	unsigned           n_iter  = 0;
+	RcTraceAcc         tr;
+	if (TRACE) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+	// Tiles are issued from the middle of this launch's tile list outwards (m, m-1, m+1, m-2, ...): the long rays sit
+	// near the image centre, so their latency chains start at t = 0 and the cheap border tiles fill the tail.
+	// With a history (the previous frame of this volume at this frame size) the tiles are issued in decreasing order of the loop
+	// count their longest ray needed last time: the frame time is the critical path of a few hundred long warps (profiles/
+	// r1s_trace.md), so they have to start at t = 0, not whenever the sweep reaches them.
+	// (compiled into the distance-map production variants only: the other modes are throughput-bound and keep their old code)
+	constexpr bool kHist = (SKIP == VKV_SKIP_DISTANCE || SKIP == VKV_SKIP_ANISOTROPIC_DISTANCE) && !OTF && !EXACT && !LOAD;
+	const int seq        = P.seq_base + (int) blockIdx.z;
+	const int local_tile = (kHist && P.tile_order) ? (int) P.tile_order[seq] : centre_out(seq, P.my_tiles);
+	const int tile       = P.tile_first + local_tile * P.tile_stride;
+	const int tile_y = P.tiles_x_magic ? (int) __umulhi((unsigned) tile, P.tiles_x_magic) : tile / P.tiles_x, tile_x = tile - tile_y * P.tiles_x;
+	const int tx0 = tile_x * P.tile_w + (int) blockIdx.x * 16;
+	const int ty0 = tile_y * P.tile_h + (int) blockIdx.y * kRcRows;
+	const int px = tx0 + (warp & 1) * 8 + (lane & 7);
+	const int py = ty0 + (warp >> 1) * 4 + (lane >> 3);
+	const bool   in_frame = px < P.width && py < P.height;
+	const size_t p        = (size_t) py * P.width + px;
+
+	// CTA-uniform rejection against the projected bounds of the unit cube: such pixels keep the clear colour
+	// (0,0,0,1) (render_pipeline.cpp:38) and depth 0.
+	if (tx0 > P.bbox[2] || tx0 + 15 < P.bbox[0] || ty0 > P.bbox[3] || ty0 + kRcRows - 1 < P.bbox[1]) {
+		if (in_frame && !LOAD) {
+			reinterpret_cast<unsigned *>(P.rgba8)[p] = 0xff000000u;
+			if (P.depth) P.depth[p] = 0.0f;
+		}
+		return;
+	}
+
+	unsigned n_vol = 0, n_dist = 0, n_empty = 0, covered = 0;
+	rc_cast_pixel<SKIP, EXACT, COUNT, OTF, TRACE, LOAD>(P, px, py, lane, n_vol, n_dist, n_empty, covered, n_iter, tr);
 
 	if (kHist && P.tile_cost) {
 		const unsigned it_warp = __reduce_max_sync(0xffffffffu, n_iter);
@@ -608,10 +838,10 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 		// per-warp record (kTraceWords u64): start ns, end ns, {iterations | with a skip-map load | with a texture batch | with both kinds
 		// of lane | mean live lanes}, then cycles of the longest-lived lanes in: loop head, request issue, skip branch, sample branch
 		const unsigned it_max = __reduce_max_sync(0xffffffffu, n_iter);
-		const unsigned m_d = __reduce_max_sync(0xffffffffu, tr_d), m_r = __reduce_max_sync(0xffffffffu, tr_r), m_m = __reduce_max_sync(0xffffffffu, tr_mixed);
-		const unsigned m_l = __reduce_max_sync(0xffffffffu, tr_lanes);
-		const unsigned c_top = __reduce_max_sync(0xffffffffu, (unsigned) tc_top), c_req = __reduce_max_sync(0xffffffffu, (unsigned) tc_req);
-		const unsigned c_d = __reduce_max_sync(0xffffffffu, (unsigned) tc_d), c_v = __reduce_max_sync(0xffffffffu, (unsigned) tc_v);
+		const unsigned m_d = __reduce_max_sync(0xffffffffu, tr.tr_d), m_r = __reduce_max_sync(0xffffffffu, tr.tr_r), m_m = __reduce_max_sync(0xffffffffu, tr.tr_mixed);
+		const unsigned m_l = __reduce_max_sync(0xffffffffu, tr.tr_lanes);
+		const unsigned c_top = __reduce_max_sync(0xffffffffu, (unsigned) tr.tc_top), c_req = __reduce_max_sync(0xffffffffu, (unsigned) tr.tc_req);
+		const unsigned c_d = __reduce_max_sync(0xffffffffu, (unsigned) tr.tc_d), c_v = __reduce_max_sync(0xffffffffu, (unsigned) tr.tc_v);
 		if (lane == 0) {
 			const size_t w = (((size_t) blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * kRcWarps + warp;
 			unsigned long long *t = P.trace + w * kTraceWords;
@@ -639,22 +869,7 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 	}
 }
 
-// ---- long rays: one ray per warp, 32 lattice steps at a time -------------------------------------------------------------
-// A ray's march is a serial state machine (skip-map hop -> next position -> hop ...), ~1300 cycles per trip when 20 rays share a
-// warp in lockstep: a frame's time used to be the ~180 trips of its longest rays (profiles/r1s_trace.md).  What a step of the
-// machine READS, however, depends on the step index alone (pos = entry + i * step): so a warp takes one suspended ray and
-// evaluates 32 consecutive lattice steps at once — lane l looks at step base + l: block index, skip-map byte, the hop that byte
-// would cause, the filtered sample(s) and its colour-table entry, 32 independent fetches instead of a 32-deep dependent chain —
-// parks them in shared memory and then REPLAYS the shader's state machine over the window with no memory access at all
-// (a few ALU instructions per visited step, every lane computing the same state).  The replay visits exactly the steps
-// the serial march visits, in the same order, with the same fp32 operations: frames and counters are bit-identical to the
-// one-kernel march (tests/test_parity_gpu.py::test_long_ray_pass_is_bit_identical).
-__device__ __forceinline__ void store_over_clear(const RayParams &P, size_t p, bool pass, const float out[4], float frag_depth)
-{
-	reinterpret_cast<unsigned *>(P.rgba8)[p] = pack_over_clear(pass, out);
-	if (P.depth) P.depth[p] = pass ? frag_depth : 0.0f;
-}
-constexpr int kLongWarps = 8, kLongWindow = 64;
+constexpr int kLongWarps = 8;
 template <int SKIP>
 __global__ void __launch_bounds__(32 * kLongWarps) raycast_long_kernel(const __grid_constant__ RayParams P)
 {
@@ -664,149 +879,13 @@ __global__ void __launch_bounds__(32 * kLongWarps) raycast_long_kernel(const __g
 	const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const unsigned n_rays = min(P.lq->count, (unsigned) P.long_cap);
 	unsigned long long c_vol = 0ull, c_dist = 0ull, c_empty = 0ull;
-	const int     back      = (int) ceilf(P.sampling_factor);
-	const int     dim_b1[3] = {P.dim_b[0] - 1, P.dim_b[1] - 1, P.dim_b[2] - 1};
-	const TFRange tb        = P.use_gradient ? P.bounds->tex_all : P.bounds->tex_row255;
-	const unsigned tb_vspan = tb.v_hi - tb.v_lo, tb_gspan = tb.g_hi - tb.g_lo;
+	const LongConsts LC = long_consts(P);
 	for (;;) {
 		unsigned j = 0u;
 		if (lane == 0) j = atomicAdd(&P.lq->head, 1u);
 		j = __shfl_sync(0xffffffffu, j, 0);
 		if (j >= n_rays) break;
-		const float4 *r  = reinterpret_cast<const float4 *>(P.lrays + j);
-		const float4  r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3], r4 = r[4];
-		const unsigned p = __float_as_uint(r0.x);
-		int            i = __float_as_int(r0.y), i_min = __float_as_int(r0.z), i_first_hit = __float_as_int(r0.w);
-		const int      n_steps = __float_as_int(r1.x);
-		unsigned       idx_last = __float_as_uint(r1.y);
-		bool           voxel_occupied = __float_as_uint(r1.z) != 0u;
-		float          out[4]   = {r2.x, r2.y, r2.z, r2.w};
-		const float    entry[3] = {r3.x, r3.y, r3.z}, step[3] = {r3.w, r4.x, r4.y};
-		float          sdt_inv[3];
-#pragma unroll
-		for (int k = 0; k < 3; ++k) {
-			const float sdt = step[k] * P.dimf[k] / P.block_size[k];
-			sdt_inv[k]      = 1.0f / sdt;
-		}
-		const bool neg[3] = {sdt_inv[0] < 0.0f, sdt_inv[1] < 0.0f, sdt_inv[2] < 0.0f};
-		const uint8_t *__restrict__ Dm = P.map_ptrs[0];
-		if (SKIP == VKV_SKIP_ANISOTROPIC_DISTANCE) Dm = P.map_ptrs[(step[2] < 0 ? 1 : 0) + (step[1] < 0 ? 2 : 0) + (step[0] < 0 ? 4 : 0)];        // sign(step) == sign(dir)
-		unsigned n_vol = 0u, n_dist = 0u, n_empty = 0u;
-		bool     done = false;
-		while (i < n_steps && !done) {
-			// the window starts where a step back (volume_render.frag:253-261) from the current step could land
-			const int base = max(i - back, i_min);
-			unsigned  my_idx[2];
-			bool      my_vis[2];
-#pragma unroll
-			for (int h = 0; h < 2; ++h) {
-				const int   slot   = 32 * h + lane;
-				const float fi     = (float) (base + slot);
-				const float pos[3] = {entry[0] + fi * step[0], entry[1] + fi * step[1], entry[2] + fi * step[2]};
-				float       u[3];
-				int         u_i[3];
-#pragma unroll
-				for (int k = 0; k < 3; ++k) {
-					u[k]   = P.vol_to_map[k] * pos[k];
-					u_i[k] = clamp0_((int) u[k], dim_b1[k]);
-				}
-				const unsigned idx  = ((unsigned) u_i[2] * (unsigned) P.dim_b[1] + (unsigned) u_i[1]) * (unsigned) P.dim_b[0] + (unsigned) u_i[0];
-				const unsigned dist = __ldg(Dm + idx);
-				const float    intensity = tex3D<float>(P.tex_v, pos[0], pos[1], pos[2]);
-				const float    gradient  = P.use_gradient ? tex3D<float>(P.tex_g, pos[0], pos[1], pos[2]) : 1.0f;
-				int            hop       = 0;
-				if (dist > 0u) {
-					float       dxyz[3];
-					const float fd = (float) dist, omfd = 1.0f - fd;
-#pragma unroll
-					for (int k = 0; k < 3; ++k) {
-						const float rr  = clampf_((float) u_i[k] - u[k], -1.0f, 0.0f);
-						const float bse = neg[k] ? omfd : fd;
-						dxyz[k]         = (bse + rr) * sdt_inv[k];
-					}
-					hop = max((int) ceilf(fminf(fminf(dxyz[0], dxyz[1]), dxyz[2])), 1);
-				}
-				const int ti = tf_texel(intensity), tg = tf_texel(gradient);
-				float4    c  = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
-				if ((unsigned) ti - tb.v_lo <= tb_vspan && (unsigned) tg - tb.g_lo <= tb_gspan) c = __ldg(P.ctab + tg * 256 + ti);
-				s_idx[warp][slot] = idx;
-				s_hop[warp][slot] = hop;
-				s_c[warp][slot]   = c;
-				my_idx[h]         = idx;
-				my_vis[h]         = c.w >= 0.0f;
-			}
-			// bit k of a mask speaks for step base + k
-			const unsigned long long m_vis = (unsigned long long) __ballot_sync(0xffffffffu, my_vis[0]) | ((unsigned long long) __ballot_sync(0xffffffffu, my_vis[1]) << 32);
-			auto same_mask = [&](unsigned ref) {
-				return (unsigned long long) __ballot_sync(0xffffffffu, my_idx[0] == ref) | ((unsigned long long) __ballot_sync(0xffffffffu, my_idx[1] == ref) << 32);
-			};
-			unsigned long long m_same = same_mask(idx_last);
-			__syncwarp();
-			// Replay of the fragment shader's loop body (volume_render.frag:215-312) over the window; every lane carries the same state.
-			// One trip of this loop is one EVENT of the march: a skip-map consultation, a visible sample, or a whole run of empty
-			// samples (the common case on a ray that grazes the surface: nothing but the counters changes along it).
-			while (i < n_steps) {
-				const int k = i - base;
-				if (k >= kLongWindow) break;
-				if (!voxel_occupied && !((m_same >> k) & 1ull)) {
-					++n_dist;
-					const int hop = s_hop[warp][k];
-					if (hop > 0) {
-						i += hop;
-					} else {
-						voxel_occupied = true;
-						idx_last       = s_idx[warp][k];
-						m_same         = same_mask(idx_last);
-						i              = max(i - back, i_min);
-					}
-				} else if ((m_vis >> k) & 1ull) {
-					++n_vol;
-					const float4   c   = s_c[warp][k];
-					const unsigned idx = s_idx[warp][k];
-					voxel_occupied = true;
-					if (idx != idx_last) {
-						idx_last = idx;
-						m_same   = same_mask(idx_last);
-					}
-					const float w = 1.0f - out[3];
-					out[0] = out[0] + w * c.x; out[1] = out[1] + w * c.y; out[2] = out[2] + w * c.z; out[3] = out[3] + w * c.w;
-					if (c.w > 0.0f) i_first_hit = i;
-					if (out[3] > 0.99f && P.ert) {
-						out[3] = 1.0f;
-						done   = true;
-						break;
-					}
-					++i;
-					i_min = i;
-				} else {
-					// step k is sampled and empty; the steps after it are sampled too for as long as they stay in block idx_last
-					// (voxel_occupied is false from here on) and are empty themselves
-					const unsigned long long run = ~m_vis & (m_same | (1ull << k));
-					const unsigned long long t   = ~(run >> k);
-					int                      L   = t ? __ffsll((long long) t) - 1 : kLongWindow - k;
-					L                            = min(L, n_steps - i);
-					n_vol += (unsigned) L;
-					n_empty += (unsigned) L;
-					i += L;
-					i_min          = i;
-					voxel_occupied = false;
-				}
-			}
-			__syncwarp();
-		}
-		c_vol += n_vol; c_dist += n_dist; c_empty += n_empty;
-		if (lane == 0) {
-			float frag_depth = 0.0f;
-			if (P.depth && out[3] > 0.0f && i_first_hit < n_steps) {
-				const double pm[3] = {(double) (entry[0] + step[0] * (float) i_first_hit) - 0.5,
-				                      (double) (entry[1] + step[1] * (float) i_first_hit) - 0.5,
-				                      (double) (entry[2] + step[2] * (float) i_first_hit) - 0.5};
-				const double z = P.pvm_z[0] * pm[0] + P.pvm_z[1] * pm[1] + P.pvm_z[2] * pm[2] + P.pvm_z[3];
-				const double w = P.pvm_w[0] * pm[0] + P.pvm_w[1] * pm[1] + P.pvm_w[2] * pm[2] + P.pvm_w[3];
-				frag_depth     = (float) (z / w);
-			}
-			store_over_clear(P, (size_t) p, frag_depth >= 0.0f, out, frag_depth);
-		}
+		rc_long_ray<SKIP>(P, LC, j, lane, s_c[warp], s_idx[warp], s_hop[warp], c_vol, c_dist, c_empty);
 	}
 	if (P.counts && lane == 0 && (c_vol | c_dist | c_empty)) {
 		atomicAdd(P.counts + 0, c_vol);
@@ -1097,6 +1176,7 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 		P.long_T   = long_T;
 		P.long_cap = vol->long_cap;
 		P.long_hint = vol->h_long_hint;
+
 		if (getenv("VKV_RC_DEBUG")) fprintf(stderr, "[vkv] long rays last frame: %d\n", *vol->h_long_hint);
 	}
 	if ((otf || load) && !P.counts) P.counts = reinterpret_cast<unsigned long long *>(vol->d_counts_scratch);
