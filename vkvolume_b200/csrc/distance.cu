@@ -128,9 +128,17 @@ __global__ void __launch_bounds__(256) xpass_vec4_kernel(const uint8_t *__restri
 	__syncwarp();
 	for (uint64_t row = (uint64_t) blockIdx.x * 8 + warp; row < nrows; row += (uint64_t) gridDim.x * 8) {
 		const uint8_t *src = O + row * Wb;
-		for (uint32_t sgm = 0; sgm < nseg; ++sgm) {
+		// the whole row is requested before any of it is looked at: one DRAM round trip per row, not one per 128 cells
+		unsigned cw[kRowWordsMax / 4];
+#pragma unroll
+		for (uint32_t sgm = 0; sgm < (uint32_t) (kRowWordsMax / 4); ++sgm) {
 			const uint32_t x = sgm * 128 + lane * 4;
-			const unsigned c = x < Wb ? __ldg(reinterpret_cast<const unsigned *>(src + x)) : 0xffffffffu;
+			cw[sgm]          = (sgm < nseg && x < Wb) ? __ldg(reinterpret_cast<const unsigned *>(src + x)) : 0xffffffffu;
+		}
+#pragma unroll
+		for (uint32_t sgm = 0; sgm < (uint32_t) (kRowWordsMax / 4); ++sgm) {
+			if (sgm >= nseg) break;
+			const unsigned c = cw[sgm];
 			unsigned       t = (c & 0x7f7f7f7fu) + 0x7f7f7f7fu;        // exact zero-byte detector -> 0x80 per zero byte
 			t                = ~(t | c | 0x7f7f7f7fu);
 			const unsigned y = t >> 7;
