@@ -298,23 +298,17 @@ def run_native(args):
     slab = sharding.slab_size(vol.map_extent[2], world)
     if world > 1:
         Wb, Hb, Db = vol.map_extent
-        map_idx = 7 if skip == 3 else 0
         vol.set_number_of_distance_maps(8 if skip == 3 else 1)
-        gather_buf = torch.empty(world * slab * Wb * Hb, dtype=torch.uint8, device=dev)
-        count_t = torch.zeros(1, dtype=torch.int64, device=dev)
+        # the library's own group: peer mappings of every rank's map / xy-intermediate / signal block (CUDA IPC)
+        handles = [None] * world
+        dist.all_gather_object(handles, vol.group_export())
+        vol.group_open(rank, world, handles)
+    last_sharded_count = [None]
 
-    def rebuild_sharded(o=opt):
-        """z-slab occupancy on every rank -> all-gather of the slab rows -> local distance transform."""
-        Wb, Hb, Db = vol.map_extent
-        vol.update_transfer_function_texture(o, stream)
-        u = capi.transfer_function_uniform(o)
-        z0, zc = sharding.slab_range(rank, world, Db)
-        count_t.zero_()
-        vol.compute_occupancy_slab(u, skip, z0, zc, count_dev=count_t.data_ptr(), stream=stream)
-        full = torch.as_tensor(_DevPtr(vol.device_distance_map(map_idx), Wb * Hb * Db), device=dev)
-        sharding.all_gather_occupancy(full, rank, world, (Wb, Hb, Db), gather_buf)
-        sharding.all_reduce_count(count_t)
-        vol.compute_distance_from_occupancy(skip, stream)
+    def rebuild_sharded(o=opt, count=False):
+        """vkv_update_transfer_function_sharded: z-slab occupancy (+ count), x/y distance passes on the slab, exchange of the slabs over
+        NVLink peer memory, z pass on the rank's block rows, exchange of the rows; barriers in peer memory, no NCCL on the data path."""
+        last_sharded_count[0] = vol.update_transfer_function_sharded(o, skip, count=count, stream=stream)
 
     rebuild = rebuild_sharded if world > 1 else rebuild_single
     rebuild()
@@ -324,8 +318,10 @@ def run_native(args):
     if world > 1:
         Wb, Hb, Db = vol.map_extent
         n_maps = 8 if skip == 3 else 1
+        rebuild_sharded(count=True)
+        torch.cuda.synchronize()
         got = [torch.as_tensor(_DevPtr(vol.device_distance_map(i), Wb * Hb * Db), device=dev).clone() for i in range(n_maps)]
-        got_count = int(count_t.item())
+        got_count = int(last_sharded_count[0])
         want_count = rebuild_single(True)
         ok = got_count == want_count
         for i in range(n_maps):
@@ -721,6 +717,9 @@ def run_native(args):
     if world > 1:
         if peer_ptr:
             capi.check(capi.lib().vkv_ipc_close(__import__("ctypes").c_void_p(peer_ptr)))
+        torch.cuda.synchronize()
+        dist.barrier()
+        vol.group_close()
         dist.barrier()
         dist.destroy_process_group()
 

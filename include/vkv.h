@@ -356,6 +356,24 @@ VKV_API int vkv_compute_distance_from_occupancy(vkv_volume *vol, int skipping_ty
  * themselves — e.g. rows gathered from other ranks into a map this rank ran no slab of: declares it present. */
 VKV_API int vkv_volume_mark_occupancy_present(vkv_volume *vol, int skipping_type);
 
+/* ---- multi-GPU group: the TF-change rebuild sharded over the GPUs of one node ----
+ * One process per GPU, every rank with a full replica of V and G.  vkv_update_transfer_function_sharded is
+ * vkv_update_transfer_function (src/volume_render.cpp:392-445) with the work cut up: occupancy (+ count) on
+ * the rank's z-slab of blocks; for the isotropic distance map the x and y passes of shaders/distance_map.comp on that slab,
+ * an exchange of the xy-intermediate slabs, the z pass on the rank's share of the block rows and an exchange of the result
+ * rows; every rank ends up with the whole map (and the whole count).  The exchanges are peer copies over NVLink into the
+ * other ranks' buffers and the barriers are signal words in peer memory: nothing leaves the caller's stream, no host round
+ * trip, no collective library on the data path.  Set-up: every rank calls vkv_volume_group_export, the application hands
+ * all ranks' handle blobs to every rank (any transport: MPI, torch.distributed, a file), every rank calls
+ * vkv_volume_group_open with the blobs in rank order.  All ranks must then make the same sequence of sharded calls
+ * (it is a collective).  At most 8 ranks. */
+#define VKV_GROUP_HANDLE_BYTES (3 * 72)
+VKV_API int vkv_volume_group_export(vkv_volume *vol, uint8_t handles_out[VKV_GROUP_HANDLE_BYTES]);
+VKV_API int vkv_volume_group_open(vkv_volume *vol, int rank, int world, const uint8_t *all_handles);
+VKV_API int vkv_volume_group_close(vkv_volume *vol);
+VKV_API int vkv_update_transfer_function_sharded(vkv_volume *vol, const vkv_volume_options *opt, int skipping_type,
+                                                 uint64_t *count_out, void *stream);
+
 /* ---- cross-process peer mapping (CUDA IPC) for the fused tile gather --------
  * The blob is the CUDA IPC handle of the allocation containing dev_ptr plus dev_ptr's byte offset inside it, so
  * interior pointers (sub-allocations of a framework's caching allocator) map to the same bytes in the peer. */

@@ -1,6 +1,6 @@
 """Multi-GPU parity on real devices (pytest -m gpu; skipped when the box has a single GPU).
 
-Two ranks under torchrun + NCCL, one per GPU, exactly as bench.py --gpus 2 runs them:
+Two (and four) ranks under torchrun + NCCL, one per GPU, exactly as bench.py --gpus N runs them:
 * image-tile sharded ray casting with the gather fused into the kernel's epilogue (peer stores into rank 0's
   framebuffer through a CUDA-IPC mapping) must reproduce the single-GPU frame byte for byte;
 * the z-slab sharded TF-change rebuild (slab occupancy + count, all-gather of the slab rows, u64 all-reduce, local
@@ -31,7 +31,7 @@ dev = torch.device("cuda", lr)
 dist.init_process_group("nccl", device_id=dev)
 stream = torch.cuda.current_stream().cuda_stream
 ctx = capi.Context(lr)
-W, H, D = 208, 160, 118            # 52 x 40 x 30 blocks (ragged last slice): slabs of 15 block slices
+W, H, D = 208, 160, 118            # 52 x 40 x 30 blocks (ragged last slice): slabs of 15 block slices (2 ranks) or 8, 8, 8, 6 (4 ranks)
 FW, FH = 640, 360
 failures = []
 for skip, tf in ((capi.SKIP_DISTANCE, dict(intensity_min=0.1, intensity_max=1.0, gradient_min=0.0, gradient_max=0.2)),
@@ -67,6 +67,25 @@ for skip, tf in ((capi.SKIP_DISTANCE, dict(intensity_min=0.1, intensity_max=1.0,
     for i in range(n_maps):
         if not np.array_equal(vol.download_distance_map(i), single[i]):
             failures.append(f"skip {skip}: sharded map {i} differs from the single-GPU map")
+    # the same rebuild through the library's own group: exchanges by peer copies over NVLink, barriers in peer memory, no NCCL
+    # on the data path (vkv_update_transfer_function_sharded); twice in a row, with and without the count
+    handles = [None] * world
+    dist.all_gather_object(handles, vol.group_export())
+    vol.group_open(rank, world, handles)
+    for rep, want_count in enumerate((True, False, True)):
+        torch.as_tensor(type("P", (), {"__cuda_array_interface__": {"shape": (Wb * Hb * Db,), "typestr": "|u1",
+                        "data": (vol.device_distance_map(0), False), "version": 3}})(), device=dev).fill_(77)
+        torch.cuda.synchronize()
+        dist.barrier()
+        n_grp = vol.update_transfer_function_sharded(opt, skip, count=want_count, stream=stream)
+        torch.cuda.synchronize()
+        if want_count and n_grp != n_single:
+            failures.append(f"skip {skip}: group count {n_grp} != {n_single} (rep {rep})")
+        for i in range(n_maps):
+            if not np.array_equal(vol.download_distance_map(i), single[i]):
+                failures.append(f"skip {skip}: group-sharded map {i} differs from the single-GPU map (rep {rep})")
+    vol.group_close()
+    dist.barrier()
     # tile-sharded frame with peer stores into rank 0
     it = scene.image_transform((0.004,) * 3, (W, H, D))
     cu, ru = vol.make_uniforms(scene.look_at_camera((95, 60, 130), aspect=FW / FH), it, 5.0)
@@ -123,14 +142,16 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def test_two_gpu_tiles_and_slabs_match_single_gpu(tmp_path):
+@pytest.mark.parametrize("world", [2, 4])
+def test_multi_gpu_tiles_and_slabs_match_single_gpu(tmp_path, world):
+    """world = 4: 30 block slices in slabs of 8, 8, 8, 6 (ragged last slab); 40 block rows in shares of 10."""
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     worker = tmp_path / "worker.py"
     worker.write_text(WORKER)
     env = dict(os.environ, VKV_ROOT=str(ROOT))
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), str(worker)]
     proc = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0 and "MULTIGPU_OK" in proc.stdout, proc.stdout[-3000:] + proc.stderr[-3000:]

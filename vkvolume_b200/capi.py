@@ -18,6 +18,7 @@ SKIP_NONE, SKIP_BLOCK, SKIP_DISTANCE, SKIP_ANISOTROPIC_DISTANCE = 0, 1, 2, 3
 TEST_NONE, TEST_RAY_ENTRY, TEST_RAY_EXIT, TEST_NUM_TEXTURE_SAMPLES = 0, 1, 2, 3
 FILTER_HARDWARE, FILTER_EXACT = 0, 1
 IPC_HANDLE_BYTES = 72
+GROUP_HANDLE_BYTES = 3 * IPC_HANDLE_BYTES
 
 
 class VkvError(RuntimeError):
@@ -151,6 +152,10 @@ _SIGNATURES = {
     "vkv_compute_occupancy_slab": (C.c_int, [_P, C.POINTER(TransferFunctionUniform), C.c_int, C.c_uint32, C.c_uint32, _P, _P]),
     "vkv_compute_distance_from_occupancy": (C.c_int, [_P, C.c_int, _P]),
     "vkv_volume_mark_occupancy_present": (C.c_int, [_P, C.c_int]),
+    "vkv_volume_group_export": (C.c_int, [_P, _P]),
+    "vkv_volume_group_open": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "vkv_volume_group_close": (C.c_int, [_P]),
+    "vkv_update_transfer_function_sharded": (C.c_int, [_P, C.POINTER(VolumeOptions), C.c_int, C.POINTER(C.c_uint64), _P]),
     "vkv_ipc_export": (C.c_int, [_P, _P]),
     "vkv_ipc_open": (C.c_int, [_P, C.POINTER(_P)]),
     "vkv_ipc_close": (C.c_int, [_P]),
@@ -303,6 +308,29 @@ class Volume:
         out = C.c_uint64(0)
         check(lib().vkv_update_transfer_function(self.handle, C.byref(options), skipping_type,
                                                  C.byref(out) if count else None, _P(stream)))
+        return out.value if count else None
+
+    # -- multi-GPU group (one process per GPU) ---------------------------------------------
+    def group_export(self) -> bytes:
+        buf = (C.c_uint8 * GROUP_HANDLE_BYTES)()
+        check(lib().vkv_volume_group_export(self.handle, buf))
+        return bytes(buf)
+
+    def group_open(self, rank: int, world: int, all_handles: list):
+        """all_handles: every rank's group_export() blob, in rank order."""
+        blob = b"".join(all_handles)
+        assert len(blob) == world * GROUP_HANDLE_BYTES
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        check(lib().vkv_volume_group_open(self.handle, rank, world, buf))
+
+    def group_close(self):
+        check(lib().vkv_volume_group_close(self.handle))
+
+    def update_transfer_function_sharded(self, options: VolumeOptions, skipping_type: int, count: bool = False, stream: int = 0):
+        """Collective over the volume's group: every rank calls it with the same arguments."""
+        out = C.c_uint64(0)
+        check(lib().vkv_update_transfer_function_sharded(self.handle, C.byref(options), skipping_type,
+                                                         C.byref(out) if count else None, _P(stream)))
         return out.value if count else None
 
     # -- ray caster ------------------------------------------------------------------------

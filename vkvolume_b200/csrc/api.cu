@@ -189,6 +189,8 @@ int vkv_volume_create(vkv_context *ctx, uint32_t width, uint32_t height, uint32_
 
 void vkv_volume_destroy(vkv_volume *vol)
 {
+	if (vol && vol->grp_world) vkv_volume_group_close(vol);
+	if (vol) cudaFree(vol->d_grp);
 	if (!vol) return;
 	DeviceGuard guard(vol->ctx->device);
 	if (vol->t_V) cudaDestroyTextureObject(vol->t_V);

@@ -83,6 +83,14 @@ struct PerDeviceOnce {
 	}
 };
 
+// multi-GPU group (group.cu): one block per rank, written by the peers through their IPC mappings of it
+constexpr int kGroupMax = 8;
+struct GroupSignals {
+	unsigned           arrived[kGroupMax];        // arrived[p]: last barrier sequence number rank p has signalled to this rank
+	unsigned           pad[8];
+	unsigned long long count[kGroupMax];          // count[p]: rank p's partial voxel count of the current rebuild
+};
+
 struct vkv_volume {
 	vkv_context *ctx = nullptr;
 	uint32_t     dim[3]{};         // W H D voxels
@@ -145,6 +153,12 @@ struct vkv_volume {
 	bool                tile_hist_valid = false;
 	int                *h_tile_promote = nullptr;        // pinned + mapped: the last ordering pass's decision (1 = long tiles promoted)
 	int                 tile_order_holdoff = 0;          // frames to go before the ordering pass is tried again
+	// multi-GPU group (group.cu): peers' map 0 / xy-intermediate / signal block, mapped through CUDA IPC
+	int                 grp_rank = -1, grp_world = 0;
+	uint8_t            *grp_map[8]{}, *grp_swap[8]{};
+	GroupSignals       *d_grp = nullptr, *grp_sig[8]{};        // this rank's block and the peers' (grp_sig[rank] == d_grp)
+	GroupSignals      **d_grp_sig = nullptr;                   // the same pointers, on the device
+	unsigned            grp_seq = 0;
 	void               *d_lq = nullptr, *d_lrays = nullptr;        // ray caster: long-ray queue header + records (raycast.cu)
 	int                 long_cap = 0;
 	int                *h_long_hint = nullptr;        // pinned + mapped: long rays of the last frame that used the hand-over
@@ -164,6 +178,9 @@ int launch_gradient(vkv_volume *vol, bool use_gradient, float modifier, cudaStre
 int launch_occupancy(vkv_volume *vol, const vkv_transfer_function_uniform *tfu, bool count, uint8_t *O, uint32_t zb_first, uint32_t zb_count,
                      unsigned long long *count_dev, cudaStream_t s);
 int launch_distance(vkv_volume *vol, int skipping_type, cudaStream_t s);
+bool distance_shardable(const vkv_volume *vol);
+int launch_distance_xy_slab(vkv_volume *vol, uint32_t zb_first, uint32_t zb_count, cudaStream_t s);
+int launch_distance_z_rows(vkv_volume *vol, uint32_t yb_first, uint32_t yb_count, cudaStream_t s);
 int launch_normalise(const void *raw_dev, size_t n, int kind, bool big_endian, float lo, float hi, uint8_t *out,
                      cudaStream_t s);
 int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_cast_uniform *ray,

@@ -614,11 +614,15 @@ __global__ void __launch_bounds__(1024) zwalk_kernel(const uint8_t *__restrict__
 	}
 }
 
+// zb_first / zb_count: the block slices to transform (the whole map by default; a rank's z-slab in the sharded build)
 template <int DIR>
-static int run_xpass(const vkv_volume *vol, const uint8_t *O, uint8_t *out, cudaStream_t s)
+static int run_xpass(const vkv_volume *vol, const uint8_t *O, uint8_t *out, cudaStream_t s, uint32_t zb_first = 0, uint32_t zb_count = 0xffffffffu)
 {
 	const uint32_t Wb    = vol->dim_b[0];
-	const uint64_t nrows = (uint64_t) vol->dim_b[1] * vol->dim_b[2];
+	if (zb_count == 0xffffffffu) zb_count = vol->dim_b[2];
+	const uint64_t nrows = (uint64_t) vol->dim_b[1] * zb_count;
+	O += (size_t) zb_first * vol->dim_b[1] * Wb;
+	out += (size_t) zb_first * vol->dim_b[1] * Wb;
 	if (Wb <= kRowWordsMax * 32) {
 		const int grid = (int) std::min<uint64_t>((nrows + 7) / 8, (uint64_t) vol->ctx->sm_count * 8);
 		if (Wb % 4 == 0) xpass_vec4_kernel<DIR><<<grid, 256, 0, s>>>(O, out, Wb, nrows);
@@ -664,10 +668,18 @@ static int run_minmax(const vkv_volume *vol, int axis, const uint8_t *src, uint8
 }
 
 template <int XDIR>
-static int run_ysweep(const vkv_volume *vol, const uint8_t *g, uint8_t *dst0, uint8_t *dst1, cudaStream_t s, bool *done)
+static int run_ysweep(const vkv_volume *vol, const uint8_t *g, uint8_t *dst0, uint8_t *dst1, cudaStream_t s, bool *done, uint32_t zb_first = 0,
+                      uint32_t zb_count = 0xffffffffu)
 {
-	const uint32_t Wb = vol->dim_b[0], Hb = vol->dim_b[1], Db = vol->dim_b[2];
+	const uint32_t Wb = vol->dim_b[0], Hb = vol->dim_b[1];
+	const uint32_t Db = zb_count == 0xffffffffu ? vol->dim_b[2] : zb_count;
 	*done = false;
+	if (Db == 0) { *done = true; return VKV_OK; }
+	{
+		const size_t off = (size_t) zb_first * Wb * Hb;        // slices are independent: a slab is a smaller map
+		g += off; dst0 += off;
+		if (dst1) dst1 += off;
+	}
 	// four cells per thread; bulk copies need 16-byte aligned row blocks (slice size, hence every block start and length)
 	if (Wb > 1024u || Wb % 4 != 0 || ((size_t) Wb * Hb) % 16 != 0 || ((size_t) kSweepRows * Wb) % 16 != 0 || (reinterpret_cast<uintptr_t>(g) % 16) != 0 ||
 	    (reinterpret_cast<uintptr_t>(dst0) % 16) != 0 || (dst1 && (reinterpret_cast<uintptr_t>(dst1) % 16) != 0))
@@ -685,11 +697,20 @@ static int run_ysweep(const vkv_volume *vol, const uint8_t *g, uint8_t *dst0, ui
 }
 
 // z lines (axis 2); MODE 0 two-sided -> dst0, MODE 3 both one-sided results
+// yb_first / yb_count: the block rows whose z lines are transformed (all by default; a rank's share in the sharded build)
 template <int MODE>
-static int run_zwalk(const vkv_volume *vol, const uint8_t *src, uint8_t *dst0, uint8_t *dst1, cudaStream_t s, bool *done)
+static int run_zwalk(const vkv_volume *vol, const uint8_t *src, uint8_t *dst0, uint8_t *dst1, cudaStream_t s, bool *done, uint32_t yb_first = 0,
+                     uint32_t yb_count = 0xffffffffu)
 {
 	const uint32_t Wb = vol->dim_b[0], Hb = vol->dim_b[1], L = vol->dim_b[2];
+	const uint32_t rows = yb_count == 0xffffffffu ? Hb : yb_count;
 	*done = false;
+	if (rows == 0) { *done = true; return VKV_OK; }
+	{
+		const size_t off = (size_t) yb_first * Wb;
+		src += off; dst0 += off;
+		if (dst1) dst1 += off;
+	}
 	if (Wb % 4 != 0 || Hb > 65535u) return VKV_OK;        // 32-bit column groups; otherwise the search kernel
 	const uint32_t max_window = std::min<uint32_t>(255u, L);
 	int            nlev       = 1;
@@ -708,7 +729,7 @@ static int run_zwalk(const vkv_volume *vol, const uint8_t *src, uint8_t *dst0, u
 	}
 	const int  nseg    = (int) ((L + kWalkSeg - 1) / kWalkSeg);
 	const int  threads = std::min(1024, std::max(64, (2 * nseg * TW + 31) / 32 * 32));
-	const dim3 grid((Wb + TW - 1) / TW, Hb);
+	const dim3 grid((Wb + TW - 1) / TW, rows);
 	zwalk_kernel<MODE><<<grid, threads, smem, s>>>(src, dst0, dst1, Wb, L, (size_t) Wb * Hb, (size_t) Wb, TW, nlev);
 	VKV_LAUNCHED();
 	*done = true;
@@ -771,6 +792,43 @@ int launch_distance(vkv_volume *vol, int skipping_type, cudaStream_t s)
 		}
 	}
 	// NONE / BLOCK: the occupancy map itself is what the ray caster reads (compute_distance_map.cpp:96-99)
+	return VKV_OK;
+}
+
+// ---- the isotropic transform cut in two for the multi-GPU build (group.cu) ------------------------------------------------------
+// The x and y passes only ever look inside one z slice, the z pass only inside one column: a rank runs x + y on its own z-slab
+// (occupancy in map 0 -> xy-intermediate in d_swap), the slabs are exchanged, and the z pass runs on the rank's share of the
+// block rows (d_swap -> map 0) before the second exchange.  Only for shapes the sweep / walk kernels cover.
+bool distance_shardable(const vkv_volume *vol)
+{
+	const uint32_t Wb = vol->dim_b[0], Hb = vol->dim_b[1];
+	return Wb <= 1024u && Wb % 4 == 0 && ((size_t) Wb * Hb) % 16 == 0 && ((size_t) kSweepRows * Wb) % 16 == 0 && Hb <= 65535u && Wb <= kRowWordsMax * 32u &&
+	       !getenv("VKV_DIST_SEARCH");
+}
+
+int launch_distance_xy_slab(vkv_volume *vol, uint32_t zb_first, uint32_t zb_count, cudaStream_t s)
+{
+	int  rc;
+	bool done = false;
+	if (zb_count == 0) return VKV_OK;
+	if ((rc = run_xpass<0>(vol, vol->d_maps[0], vol->d_tmp, s, zb_first, zb_count))) return rc;
+	if ((rc = run_ysweep<0>(vol, vol->d_tmp, vol->d_swap, nullptr, s, &done, zb_first, zb_count))) return rc;
+	if (!done) {
+		set_error("launch_distance_xy_slab: shape not covered by the sweep kernel");
+		return VKV_ERR_STATE;
+	}
+	return VKV_OK;
+}
+
+int launch_distance_z_rows(vkv_volume *vol, uint32_t yb_first, uint32_t yb_count, cudaStream_t s)
+{
+	int  rc;
+	bool done = false;
+	if ((rc = run_zwalk<0>(vol, vol->d_swap, vol->d_maps[0], nullptr, s, &done, yb_first, yb_count))) return rc;
+	if (!done) {
+		set_error("launch_distance_z_rows: shape not covered by the walk kernel");
+		return VKV_ERR_STATE;
+	}
 	return VKV_OK;
 }
 
