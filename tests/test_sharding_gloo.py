@@ -116,16 +116,65 @@ print("rank", rank, "ok")
 '''
 
 
+K3_WORKER = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, os.environ["VKV_ROOT"]); sys.path.insert(0, os.path.join(os.environ["VKV_ROOT"], "tests"))
+import oracle_api as orc
+from vkvolume_b200 import sharding
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+# The sharded isotropic distance-map build of csrc/group.cu, with numpy standing in for the three 1-D passes:
+# x and y passes on the rank's z-slab, all-gather of the xy-intermediate slabs, z pass on the rank's block rows, all-gather of
+# the rows — must equal the oracle's transform of the whole map (shaders/distance_map.comp:44-109).
+def line_pass(h, axis):
+    """D(t) = min(255, min_j max(|j - t|, h(j))) along `axis` (the operator of every pass; on 0/255 input it is the x sweep)."""
+    h = np.moveaxis(h.astype(np.int32), axis, -1)
+    L = h.shape[-1]
+    out = h.copy()
+    for n in range(1, min(L, 255)):
+        lo = np.full_like(h, 255); hi = np.full_like(h, 255)
+        lo[..., n:] = h[..., :-n]; hi[..., :-n] = h[..., n:]
+        out = np.minimum(out, np.maximum(n, np.minimum(lo, hi)))
+    return np.moveaxis(np.minimum(out, 255), -1, axis).astype(np.uint8)
+Db, Hb, Wb = 13, 10, 12        # 13 slices over 2 ranks: slabs of 7 and 6; 10 rows: 5 and 5
+rng = np.random.default_rng(17)
+O = np.where(rng.random((Db, Hb, Wb)) < 0.01, 0, 255).astype(np.uint8)
+want = orc.distance_map(O.copy())
+z0, zc = sharding.slab_range(rank, world, Db)
+xy = line_pass(line_pass(O[z0:z0 + zc], 2), 1)                     # x then y, slice-local
+s = sharding.slab_size(Db, world)
+mine = torch.full((s * Hb * Wb,), 255, dtype=torch.uint8)
+mine[: zc * Hb * Wb] = torch.from_numpy(xy.reshape(-1).copy())
+parts = [torch.empty_like(mine) for _ in range(world)]
+dist.all_gather(parts, mine)
+full_xy = np.concatenate([parts[r].numpy()[: sharding.slab_range(r, world, Db)[1] * Hb * Wb].reshape(-1, Hb, Wb) for r in range(world)])
+assert full_xy.shape == (Db, Hb, Wb)
+y0, yc = sharding.row_range(rank, world, Hb)
+rows = line_pass(full_xy[:, y0:y0 + yc, :], 0)                      # z pass on this rank's block rows
+r_s = sharding.slab_size(Hb, world)
+mine = torch.full((Db * r_s * Wb,), 255, dtype=torch.uint8)
+mine[: Db * yc * Wb] = torch.from_numpy(rows.reshape(-1).copy())
+parts = [torch.empty_like(mine) for _ in range(world)]
+dist.all_gather(parts, mine)
+got = np.concatenate([parts[r].numpy()[: Db * sharding.row_range(r, world, Hb)[1] * Wb].reshape(Db, -1, Wb) for r in range(world)], axis=1)
+assert np.array_equal(got, want), "sharded x/y-on-slabs + z-on-rows build differs from the whole-map transform"
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("worker", ["zslab", "frames"])
+@pytest.mark.parametrize("worker", ["zslab", "frames", "sharded_k3"])
 def test_exchange_world_size_2_gloo(tmp_path, worker):
     script = tmp_path / "worker.py"
-    script.write_text(WORKER if worker == "zslab" else FRAMES_WORKER)
+    script.write_text({"zslab": WORKER, "frames": FRAMES_WORKER, "sharded_k3": K3_WORKER}[worker])
     port = _free_port()
     procs = []
     for rank in range(2):

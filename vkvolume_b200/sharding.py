@@ -8,8 +8,11 @@ and on CUDA tensors with NCCL (how bench.py runs it) — there is no compute her
 * Frame sequences (an orbit, an animation) shard by frames instead: step s of an N-rank job renders views s*N .. s*N + N - 1, view
   s*N + r on rank r, which stores it into slot r of a ring of N frames in rank 0's HBM (or delivers it to its own pinned host
   buffer); again no collective.
-* The TF-change rebuild shards the O(N) occupancy pass by z-slabs of blocks; the slab rows of the occupancy map are
-  all-gathered, the voxel count is all-reduced, and every rank then runs the distance transform on the full map.
+* The TF-change rebuild shards the O(N) occupancy pass by z-slabs of blocks.  In the library's own group
+  (vkv_update_transfer_function_sharded, csrc/group.cu) the isotropic distance map is sharded too: x and y passes on the rank's slab,
+  exchange of the xy-intermediate slabs, z pass on the rank's share of the block rows (row_range), exchange of the result rows — peer
+  copies over NVLink and barriers in peer memory.  The torch.distributed helpers below (all-gather of occupancy slabs, all-reduce
+  of the count) are the same decomposition with a collective library doing the exchange; the gloo tests use them on CPU.
 """
 from __future__ import annotations
 
@@ -24,6 +27,12 @@ def slab_range(rank: int, world: int, depth_blocks: int) -> tuple[int, int]:
     s = slab_size(depth_blocks, world)
     z0 = min(rank * s, depth_blocks)
     return z0, max(0, min(s, depth_blocks - z0))
+
+
+def row_range(rank: int, world: int, height_blocks: int) -> tuple[int, int]:
+    """(first block row, number of block rows) whose z lines `rank` transforms in the sharded distance-map build
+    (vkv_update_transfer_function_sharded: x and y passes on the z-slab, exchange, z pass on these rows, exchange)."""
+    return slab_range(rank, world, height_blocks)
 
 
 def tiles_of_rank(rank: int, world: int, n_tiles: int) -> range:
