@@ -240,7 +240,10 @@ template <bool FAST> __device__ __forceinline__ float sdt_inv_(const RayParams &
 	const float sdt = step_k * P.dimf[k] / P.block_size[k];
 	return 1.0f / sdt;
 }
-constexpr int kLongWindow = 64;
+#ifndef VKV_RC_LONG_PER
+#define VKV_RC_LONG_PER 2
+#endif
+constexpr int kLongPer = VKV_RC_LONG_PER, kLongWindow = 32 * kLongPer;        // lattice steps per lane and per window
 struct LongConsts {
 	int      back, dim_b1[3];
 	TFRange  tb;
@@ -286,10 +289,10 @@ __device__ __forceinline__ void rc_long_ray(const RayParams &P, const LongConsts
 	while (i < n_steps && !done) {
 		// the window starts where a step back (volume_render.frag:253-261) from the current step could land
 		const int base = max(i - back, i_min);
-		unsigned  my_idx[2];
-		bool      my_vis[2];
+		unsigned  my_idx[kLongPer];
+		unsigned  vis_w[kLongPer];        // ballots: bit l of word h speaks for step base + 32 h + l
 #pragma unroll
-		for (int h = 0; h < 2; ++h) {
+		for (int h = 0; h < kLongPer; ++h) {
 			const int   slot   = 32 * h + lane;
 			const float fi     = (float) (base + slot);
 			const float pos[3] = {__fmaf_rn(fi, step[0], entry[0]), __fmaf_rn(fi, step[1], entry[1]), __fmaf_rn(fi, step[2], entry[2])};
@@ -322,15 +325,22 @@ __device__ __forceinline__ void rc_long_ray(const RayParams &P, const LongConsts
 			s_idx[slot] = idx;
 			s_hop[slot] = hop;
 			s_c[slot]   = c;
-			my_idx[h]         = idx;
-			my_vis[h]         = c.w >= 0.0f;
+			my_idx[h]   = idx;
+			vis_w[h]    = __ballot_sync(0xffffffffu, c.w >= 0.0f);
 		}
-		// bit k of a mask speaks for step base + k
-		const unsigned long long m_vis = (unsigned long long) __ballot_sync(0xffffffffu, my_vis[0]) | ((unsigned long long) __ballot_sync(0xffffffffu, my_vis[1]) << 32);
+		unsigned same_w[kLongPer];
 		auto same_mask = [&](unsigned ref) {
-			return (unsigned long long) __ballot_sync(0xffffffffu, my_idx[0] == ref) | ((unsigned long long) __ballot_sync(0xffffffffu, my_idx[1] == ref) << 32);
+#pragma unroll
+			for (int h = 0; h < kLongPer; ++h) same_w[h] = __ballot_sync(0xffffffffu, my_idx[h] == ref);
 		};
-		unsigned long long m_same = same_mask(idx_last);
+		// word h of a per-lane array without dynamic indexing (kLongPer is 2 or 4)
+		auto word = [&](const unsigned (&m)[kLongPer], int h) {
+			unsigned v = m[0];
+#pragma unroll
+			for (int q = 1; q < kLongPer; ++q) v = h == q ? m[q] : v;
+			return v;
+		};
+		same_mask(idx_last);
 		__syncwarp();
 		// Replay of the fragment shader's loop body (volume_render.frag:215-312) over the window; every lane carries the same state.
 		// One trip of this loop is one EVENT of the march: a skip-map consultation, a visible sample, or a whole run of empty
@@ -338,7 +348,9 @@ __device__ __forceinline__ void rc_long_ray(const RayParams &P, const LongConsts
 		while (i < n_steps) {
 			const int k = i - base;
 			if (k >= kLongWindow) break;
-			if (!voxel_occupied && !((m_same >> k) & 1ull)) {
+			const int      kw = k >> 5, kb = k & 31;
+			const unsigned sw = word(same_w, kw), vw = word(vis_w, kw);
+			if (!voxel_occupied && !((sw >> kb) & 1u)) {
 				++n_dist;
 				const int hop = s_hop[k];
 				if (hop > 0) {
@@ -346,17 +358,17 @@ __device__ __forceinline__ void rc_long_ray(const RayParams &P, const LongConsts
 				} else {
 					voxel_occupied = true;
 					idx_last       = s_idx[k];
-					m_same         = same_mask(idx_last);
-					i              = max(i - back, i_min);
+					same_mask(idx_last);
+					i = max(i - back, i_min);
 				}
-			} else if ((m_vis >> k) & 1ull) {
+			} else if ((vw >> kb) & 1u) {
 				++n_vol;
 				const float4   c   = s_c[k];
 				const unsigned idx = s_idx[k];
 				voxel_occupied = true;
 				if (idx != idx_last) {
 					idx_last = idx;
-					m_same   = same_mask(idx_last);
+					same_mask(idx_last);
 				}
 				const float w = 1.0f - out[3];
 				out[0] = __fmaf_rn(w, c.x, out[0]); out[1] = __fmaf_rn(w, c.y, out[1]); out[2] = __fmaf_rn(w, c.z, out[2]); out[3] = __fmaf_rn(w, c.w, out[3]);
@@ -370,11 +382,18 @@ __device__ __forceinline__ void rc_long_ray(const RayParams &P, const LongConsts
 				i_min = i;
 			} else {
 				// step k is sampled and empty; the steps after it are sampled too for as long as they stay in block idx_last
-				// (voxel_occupied is false from here on) and are empty themselves
-				const unsigned long long run = ~m_vis & (m_same | (1ull << k));
-				const unsigned long long t   = ~(run >> k);
-				int                      L   = t ? __ffsll((long long) t) - 1 : kLongWindow - k;
-				L                            = min(L, n_steps - i);
+				// (voxel_occupied is false from here on) and are empty themselves: count them word by word
+				int L = 0;
+				{
+					const unsigned run = ~vw & (sw | (1u << kb));
+					const unsigned t   = ~(run >> kb);        // the zeros shifted in at the top end the count at the word's end
+					L                  = t ? __ffs((int) t) - 1 : 32;
+				}
+				for (int h = kw + 1; L == 32 * (h - kw) - kb && h < kLongPer; ++h) {
+					const unsigned t = ~(~word(vis_w, h) & word(same_w, h));
+					L += t ? __ffs((int) t) - 1 : 32;
+				}
+				L = min(L, n_steps - i);
 				n_vol += (unsigned) L;
 				n_empty += (unsigned) L;
 				i += L;
@@ -869,9 +888,12 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 	}
 }
 
-constexpr int kLongWarps = 8;
+#ifndef VKV_RC_LONG_CTAS
+#define VKV_RC_LONG_CTAS 4
+#endif
+constexpr int kLongWarps = 8, kLongCtasPerSm = VKV_RC_LONG_CTAS;
 template <int SKIP>
-__global__ void __launch_bounds__(32 * kLongWarps) raycast_long_kernel(const __grid_constant__ RayParams P)
+__global__ void __launch_bounds__(32 * kLongWarps, kLongCtasPerSm) raycast_long_kernel(const __grid_constant__ RayParams P)
 {
 	__shared__ float4   s_c[kLongWarps][kLongWindow];
 	__shared__ unsigned s_idx[kLongWarps][kLongWindow];
@@ -973,7 +995,7 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(unsigned *__restrict__
 	const unsigned long long excl = s_warp[warp] + incl - mine, total = s_total;
 	const unsigned n0 = (unsigned) (total & 0xfffffu), n1 = (unsigned) ((total >> 20) & 0xfffffu);
 	const bool     promote = (n0 + n1) * 3u <= (unsigned) n;
-	if (threadIdx.x == 0) *decision = promote ? 1 : 0;        // host-visible hint (read a frame or more later, without synchronising)
+	if (threadIdx.x == 0) *decision = promote ? (int) (n0 + n1) : 0;        // host-visible hint (read a frame or more later, without synchronising): 0 = keep centre-out, else the number of promoted tiles
 	unsigned       pos[3] = {(unsigned) (excl & 0xfffffu), n0 + (unsigned) ((excl >> 20) & 0xfffffu), n0 + n1 + (unsigned) ((excl >> 40) & 0xfffffu)};
 	for (int q = s0; q < s1; ++q) {
 		const int t = centre_out(q, n);
@@ -1235,22 +1257,22 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 		}
 		vol->tile_hist_valid = use_hist;
 	}
-	for (int base = 0; base < my_tiles; base += 65535) {
-		P.seq_base = base;
-		const dim3 grid((unsigned) (tile_w / 16), (unsigned) (tile_h / kRcRows), (unsigned) std::min(65535, my_tiles - base));
+	// one launch of the march over `count` tiles of the launch's list starting at `base`, on stream `st`
+	auto launch_march = [&](const RayParams &Q, int count, cudaStream_t st) -> int {
+		const dim3 grid((unsigned) (tile_w / 16), (unsigned) (tile_h / kRcRows), (unsigned) count);
 #define VKV_RC(SK)                                                                      \
 	do {                                                                                \
-		if (load && otf && exact) raycast_kernel<SK, true, true, true, false, true><<<grid, kRcThreads, 0, s>>>(P);  \
-		else if (load && otf) raycast_kernel<SK, false, true, true, false, true><<<grid, kRcThreads, 0, s>>>(P);     \
-		else if (load && exact) raycast_kernel<SK, true, true, false, false, true><<<grid, kRcThreads, 0, s>>>(P);   \
-		else if (load) raycast_kernel<SK, false, true, false, false, true><<<grid, kRcThreads, 0, s>>>(P);           \
-		else if (d_trace && !otf && !exact) raycast_kernel<SK, false, false, false, true><<<grid, kRcThreads, 0, s>>>(P); \
-		else if (otf && exact) raycast_kernel<SK, true, true, true><<<grid, kRcThreads, 0, s>>>(P);   \
-		else if (otf) raycast_kernel<SK, false, true, true><<<grid, kRcThreads, 0, s>>>(P);      \
-		else if (exact && counts) raycast_kernel<SK, true, true><<<grid, kRcThreads, 0, s>>>(P);      \
-		else if (exact) raycast_kernel<SK, true, false><<<grid, kRcThreads, 0, s>>>(P);          \
-		else if (counts) raycast_kernel<SK, false, true><<<grid, kRcThreads, 0, s>>>(P);         \
-		else raycast_kernel<SK, false, false><<<grid, kRcThreads, 0, s>>>(P);                    \
+		if (load && otf && exact) raycast_kernel<SK, true, true, true, false, true><<<grid, kRcThreads, 0, st>>>(Q);  \
+		else if (load && otf) raycast_kernel<SK, false, true, true, false, true><<<grid, kRcThreads, 0, st>>>(Q);     \
+		else if (load && exact) raycast_kernel<SK, true, true, false, false, true><<<grid, kRcThreads, 0, st>>>(Q);   \
+		else if (load) raycast_kernel<SK, false, true, false, false, true><<<grid, kRcThreads, 0, st>>>(Q);           \
+		else if (d_trace && !otf && !exact) raycast_kernel<SK, false, false, false, true><<<grid, kRcThreads, 0, st>>>(Q); \
+		else if (otf && exact) raycast_kernel<SK, true, true, true><<<grid, kRcThreads, 0, st>>>(Q);   \
+		else if (otf) raycast_kernel<SK, false, true, true><<<grid, kRcThreads, 0, st>>>(Q);      \
+		else if (exact && counts) raycast_kernel<SK, true, true><<<grid, kRcThreads, 0, st>>>(Q);      \
+		else if (exact) raycast_kernel<SK, true, false><<<grid, kRcThreads, 0, st>>>(Q);          \
+		else if (Q.counts) raycast_kernel<SK, false, true><<<grid, kRcThreads, 0, st>>>(Q);         \
+		else raycast_kernel<SK, false, false><<<grid, kRcThreads, 0, st>>>(Q);                    \
 	} while (0)
 		switch (opt->skipping_type) {
 			case VKV_SKIP_NONE: VKV_RC(VKV_SKIP_NONE); break;
@@ -1260,13 +1282,24 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 		}
 #undef VKV_RC
 		VKV_LAUNCHED();
-	}
-	if (long_now) {
-		const unsigned grid2 = (unsigned) vol->ctx->sm_count * 4u;
-		if (opt->skipping_type == VKV_SKIP_DISTANCE) raycast_long_kernel<VKV_SKIP_DISTANCE><<<grid2, 32 * kLongWarps, 0, s>>>(P);
-		else raycast_long_kernel<VKV_SKIP_ANISOTROPIC_DISTANCE><<<grid2, 32 * kLongWarps, 0, s>>>(P);
+		return VKV_OK;
+	};
+	auto launch_long = [&](cudaStream_t st) -> int {
+		const unsigned grid2 = (unsigned) vol->ctx->sm_count * (unsigned) kLongCtasPerSm;
+		if (opt->skipping_type == VKV_SKIP_DISTANCE) raycast_long_kernel<VKV_SKIP_DISTANCE><<<grid2, 32 * kLongWarps, 0, st>>>(P);
+		else raycast_long_kernel<VKV_SKIP_ANISOTROPIC_DISTANCE><<<grid2, 32 * kLongWarps, 0, st>>>(P);
 		VKV_LAUNCHED();
+		return VKV_OK;
+	};
+	// (Measured and dropped: issuing the promoted tiles and the rest as two concurrent launches so that the second pass overlaps the
+	// bulk — the promoted tiles' launch itself lasts ~60 us, its rays hand over only after long_T trips: 2 % — and serving the queue
+	// from inside the march, by warps about to exit or by a persistent grid: slower, profiles/r2_trace.md.)
+	int rc2;
+	for (int base = 0; base < my_tiles; base += 65535) {
+		P.seq_base = base;
+		if ((rc2 = launch_march(P, std::min(65535, my_tiles - base), s))) return rc2;
 	}
+	if (long_now && (rc2 = launch_long(s))) return rc2;
 	if (d_trace) {
 		std::vector<unsigned long long> h(trace_n);
 		VKV_CUDA_CHECK(cudaStreamSynchronize(s));
