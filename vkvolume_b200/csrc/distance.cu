@@ -117,7 +117,7 @@ struct RowBits {
 	}
 };
 
-template <int DIR>
+template <int DIR, int SEGS>        // SEGS: compile-time bound on the row's 128-cell segments (2, 4, 8 or 16)
 __global__ void __launch_bounds__(256) xpass_vec4_kernel(const uint8_t *__restrict__ O, uint8_t *__restrict__ out, uint32_t Wb, uint64_t nrows)
 {
 	__shared__ unsigned s_words[8][kRowWordsMax];
@@ -129,14 +129,14 @@ __global__ void __launch_bounds__(256) xpass_vec4_kernel(const uint8_t *__restri
 	for (uint64_t row = (uint64_t) blockIdx.x * 8 + warp; row < nrows; row += (uint64_t) gridDim.x * 8) {
 		const uint8_t *src = O + row * Wb;
 		// the whole row is requested before any of it is looked at: one DRAM round trip per row, not one per 128 cells
-		unsigned cw[kRowWordsMax / 4];
+		unsigned cw[SEGS];
 #pragma unroll
-		for (uint32_t sgm = 0; sgm < (uint32_t) (kRowWordsMax / 4); ++sgm) {
+		for (uint32_t sgm = 0; sgm < (uint32_t) SEGS; ++sgm) {
 			const uint32_t x = sgm * 128 + lane * 4;
 			cw[sgm]          = (sgm < nseg && x < Wb) ? __ldg(reinterpret_cast<const unsigned *>(src + x)) : 0xffffffffu;
 		}
 #pragma unroll
-		for (uint32_t sgm = 0; sgm < (uint32_t) (kRowWordsMax / 4); ++sgm) {
+		for (uint32_t sgm = 0; sgm < (uint32_t) SEGS; ++sgm) {
 			if (sgm >= nseg) break;
 			const unsigned c = cw[sgm];
 			unsigned       t = (c & 0x7f7f7f7fu) + 0x7f7f7f7fu;        // exact zero-byte detector -> 0x80 per zero byte
@@ -397,16 +397,19 @@ __device__ __forceinline__ unsigned d_prmt(unsigned a, unsigned b, unsigned sel)
 	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
 	return r;
 }
+// `split` (isotropic, small maps): the two sweeps of a slice are independent when both start from g — the result is then
+// min(up, down), which the z pass takes while it stages — so they run as two CTAs (blockIdx.x = 2 slice + sweep) and the serial
+// chain of a slice is Hb row steps instead of 2 Hb; costs one more map of traffic, so only where the maps live in the L2.
 template <int XDIR>        // XDIR 0: isotropic (two-sided x, 3 neighbours, in-place second sweep); +-1: one-sided
 __global__ void __launch_bounds__(256) ysweep_kernel(const uint8_t *__restrict__ g, uint8_t *__restrict__ dst0, uint8_t *__restrict__ dst1,
-                                                     uint32_t Wb, uint32_t Hb)
+                                                     uint32_t Wb, uint32_t Hb, int split)
 {
 	extern __shared__ __align__(128) uint8_t s_dyn[];        // kSweepSlots chunks of kSweepRows x Wb | 2 row buffers of Wb/4 + 2 uint2
 	__shared__ __align__(8) uint64_t s_bar[kSweepSlots];
 	const uint32_t t      = threadIdx.x;                     // group of 4 cells of the row
 	const uint32_t W4     = Wb >> 2;
 	const bool     active = t < W4;
-	const size_t   slice  = (size_t) blockIdx.x * Wb * Hb;
+	const size_t   slice  = (size_t) (split ? blockIdx.x >> 1 : blockIdx.x) * Wb * Hb;
 	const uint32_t chunk_bytes = kSweepRows * Wb;
 	uint8_t       *ring = s_dyn;
 	uint2         *buf0 = reinterpret_cast<uint2 *>(s_dyn + (size_t) kSweepSlots * chunk_bytes) + 1, *buf1 = buf0 + (W4 + 2);
@@ -418,10 +421,10 @@ __global__ void __launch_bounds__(256) ysweep_kernel(const uint8_t *__restrict__
 	}
 	__syncthreads();
 	unsigned issued = 0;        // copies issued so far (thread 0): copy n lands in ring slot n % kSweepSlots, phase (n / kSweepSlots) & 1
-	for (int sweep = 0; sweep < 2; ++sweep) {
+	for (int sweep = split ? (int) (blockIdx.x & 1u) : 0; sweep < 2; ++sweep) {
 		// sweep 0 walks y upwards (sources at y' <= y), sweep 1 downwards (sources at y' >= y)
-		const uint8_t  *src  = (XDIR == 0 && sweep == 1) ? dst0 : g;
-		uint8_t        *dst  = XDIR == 0 ? dst0 : (sweep == 0 ? dst1 : dst0);
+		const uint8_t  *src  = (XDIR == 0 && sweep == 1 && !split) ? dst0 : g;
+		uint8_t        *dst  = (XDIR == 0 && !split) ? dst0 : (sweep == 0 ? dst1 : dst0);
 		const ptrdiff_t step = sweep == 0 ? (ptrdiff_t) W4 : -(ptrdiff_t) W4;        // in words
 		unsigned       *dp   = reinterpret_cast<unsigned *>(dst + slice + (sweep == 0 ? 0 : (size_t) (Hb - 1) * Wb)) + t;
 		// chunk c of this sweep = rows [lo, lo + n) of the slice, consumed upwards (sweep 0) or downwards (sweep 1)
@@ -433,7 +436,7 @@ __global__ void __launch_bounds__(256) ysweep_kernel(const uint8_t *__restrict__
 			d_tma_load_1d(ring + (size_t) slot * chunk_bytes, src + slice + (size_t) lo * Wb, n * Wb, &s_bar[slot]);
 			++issued;
 		};
-		if (XDIR == 0 && sweep == 1) {
+		if (XDIR == 0 && sweep == 1 && !split) {
 			// the second sweep re-reads what this CTA just wrote with ordinary stores: order them before the async-proxy reads
 			__threadfence();
 			asm volatile("fence.proxy.async;" ::: "memory");
@@ -490,6 +493,7 @@ __global__ void __launch_bounds__(256) ysweep_kernel(const uint8_t *__restrict__
 			if (t == 0 && c + kSweepSlots < nchunks) issue(c + kSweepSlots);
 		}
 		issued = consumed + nchunks;        // keep every thread's view of the sequence number in step with thread 0's
+		if (split) break;                   // one sweep per CTA
 	}
 }
 
@@ -526,9 +530,11 @@ __device__ __forceinline__ unsigned walk_head(const uint8_t *__restrict__ T, int
 	return lo;
 }
 
+// src2 (or null): a second input, the cell-wise minimum of the two is what gets transformed (the split y sweeps' outputs)
 template <int MODE>
-__global__ void __launch_bounds__(1024) zwalk_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst0, uint8_t *__restrict__ dst1,
-                                                     uint32_t Wb, uint32_t L, size_t line_stride, size_t outer_stride, int TW, int nlev)
+__global__ void __launch_bounds__(1024) zwalk_kernel(const uint8_t *__restrict__ src, const uint8_t *__restrict__ src2, uint8_t *__restrict__ dst0,
+                                                     uint8_t *__restrict__ dst1, uint32_t Wb, uint32_t L, size_t line_stride, size_t outer_stride, int TW,
+                                                     int nlev)
 {
 	extern __shared__ __align__(16) uint8_t T[];        // nlev levels of L x TW bytes, then the F and B lines (2 x L x TW)
 	const int      nthreads = blockDim.x;
@@ -542,7 +548,10 @@ __global__ void __launch_bounds__(1024) zwalk_kernel(const uint8_t *__restrict__
 	for (int i = threadIdx.x; i < nwords; i += nthreads) {
 		const int p = i / TW4, w = i - p * TW4;
 		unsigned  v = 0xffffffffu;
-		if (x0 + 4u * w < Wb) v = __ldg(reinterpret_cast<const unsigned *>(src + base + (size_t) p * line_stride) + w);
+		if (x0 + 4u * w < Wb) {
+			v = __ldg(reinterpret_cast<const unsigned *>(src + base + (size_t) p * line_stride) + w);
+			if (src2) v = __vminu4(v, __ldg(reinterpret_cast<const unsigned *>(src2 + base + (size_t) p * line_stride) + w));
+		}
 		reinterpret_cast<unsigned *>(T)[i] = v;
 	}
 	__syncthreads();
@@ -625,7 +634,13 @@ static int run_xpass(const vkv_volume *vol, const uint8_t *O, uint8_t *out, cuda
 	out += (size_t) zb_first * vol->dim_b[1] * Wb;
 	if (Wb <= kRowWordsMax * 32) {
 		const int grid = (int) std::min<uint64_t>((nrows + 7) / 8, (uint64_t) vol->ctx->sm_count * 8);
-		if (Wb % 4 == 0) xpass_vec4_kernel<DIR><<<grid, 256, 0, s>>>(O, out, Wb, nrows);
+		if (Wb % 4 == 0) {
+			const uint32_t nseg = (Wb + 127) / 128;
+			if (nseg <= 2) xpass_vec4_kernel<DIR, 2><<<grid, 256, 0, s>>>(O, out, Wb, nrows);
+			else if (nseg <= 4) xpass_vec4_kernel<DIR, 4><<<grid, 256, 0, s>>>(O, out, Wb, nrows);
+			else if (nseg <= 8) xpass_vec4_kernel<DIR, 8><<<grid, 256, 0, s>>>(O, out, Wb, nrows);
+			else xpass_vec4_kernel<DIR, 16><<<grid, 256, 0, s>>>(O, out, Wb, nrows);
+		}
 		else xpass_ballot_kernel<DIR><<<grid, 256, 0, s>>>(O, out, Wb, nrows);
 	} else {
 		xpass_serial_kernel<DIR><<<(unsigned) ((nrows + 127) / 128), 128, 0, s>>>(O, out, Wb, nrows);
@@ -669,7 +684,7 @@ static int run_minmax(const vkv_volume *vol, int axis, const uint8_t *src, uint8
 
 template <int XDIR>
 static int run_ysweep(const vkv_volume *vol, const uint8_t *g, uint8_t *dst0, uint8_t *dst1, cudaStream_t s, bool *done, uint32_t zb_first = 0,
-                      uint32_t zb_count = 0xffffffffu)
+                      uint32_t zb_count = 0xffffffffu, bool split = false)
 {
 	const uint32_t Wb = vol->dim_b[0], Hb = vol->dim_b[1];
 	const uint32_t Db = zb_count == 0xffffffffu ? vol->dim_b[2] : zb_count;
@@ -690,7 +705,7 @@ static int run_ysweep(const vkv_volume *vol, const uint8_t *g, uint8_t *dst0, ui
 	if (configured.first(vol->ctx->device)) {
 		VKV_CUDA_CHECK(cudaFuncSetAttribute(ysweep_kernel<XDIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
 	}
-	ysweep_kernel<XDIR><<<Db, threads, smem, s>>>(g, dst0, dst1, Wb, Hb);
+	ysweep_kernel<XDIR><<<split ? 2 * Db : Db, threads, smem, s>>>(g, dst0, dst1, Wb, Hb, split ? 1 : 0);
 	VKV_LAUNCHED();
 	*done = true;
 	return VKV_OK;
@@ -700,7 +715,7 @@ static int run_ysweep(const vkv_volume *vol, const uint8_t *g, uint8_t *dst0, ui
 // yb_first / yb_count: the block rows whose z lines are transformed (all by default; a rank's share in the sharded build)
 template <int MODE>
 static int run_zwalk(const vkv_volume *vol, const uint8_t *src, uint8_t *dst0, uint8_t *dst1, cudaStream_t s, bool *done, uint32_t yb_first = 0,
-                     uint32_t yb_count = 0xffffffffu)
+                     uint32_t yb_count = 0xffffffffu, const uint8_t *src2 = nullptr)
 {
 	const uint32_t Wb = vol->dim_b[0], Hb = vol->dim_b[1], L = vol->dim_b[2];
 	const uint32_t rows = yb_count == 0xffffffffu ? Hb : yb_count;
@@ -710,6 +725,7 @@ static int run_zwalk(const vkv_volume *vol, const uint8_t *src, uint8_t *dst0, u
 		const size_t off = (size_t) yb_first * Wb;
 		src += off; dst0 += off;
 		if (dst1) dst1 += off;
+		if (src2) src2 += off;
 	}
 	if (Wb % 4 != 0 || Hb > 65535u) return VKV_OK;        // 32-bit column groups; otherwise the search kernel
 	const uint32_t max_window = std::min<uint32_t>(255u, L);
@@ -730,7 +746,7 @@ static int run_zwalk(const vkv_volume *vol, const uint8_t *src, uint8_t *dst0, u
 	const int  nseg    = (int) ((L + kWalkSeg - 1) / kWalkSeg);
 	const int  threads = std::min(1024, std::max(64, (2 * nseg * TW + 31) / 32 * 32));
 	const dim3 grid((Wb + TW - 1) / TW, rows);
-	zwalk_kernel<MODE><<<grid, threads, smem, s>>>(src, dst0, dst1, Wb, L, (size_t) Wb * Hb, (size_t) Wb, TW, nlev);
+	zwalk_kernel<MODE><<<grid, threads, smem, s>>>(src, src2, dst0, dst1, Wb, L, (size_t) Wb * Hb, (size_t) Wb, TW, nlev);
 	VKV_LAUNCHED();
 	*done = true;
 	return VKV_OK;
@@ -744,10 +760,23 @@ int launch_distance(vkv_volume *vol, int skipping_type, cudaStream_t s)
 		const bool legacy = getenv("VKV_DIST_SEARCH") != nullptr;        // A/B switch: the binary-search kernels for every pass
 		bool       done   = false;
 		if ((rc = run_xpass<0>(vol, map, vol->d_tmp, s))) return rc;
-		if (!legacy && (rc = run_ysweep<0>(vol, vol->d_tmp, vol->d_swap, nullptr, s, &done))) return rc;
+		// small maps (L2-resident): the two y sweeps of a slice as two CTAs, their outputs (d_swap: sources above, the map itself —
+		// its occupancy was consumed by the x pass — : sources below) minimised by the z walk while it stages.  The z walk reads a
+		// column completely before it writes it, so using the map as the second input is safe.
+		const bool split_ok = !legacy && !getenv("VKV_DIST_NOSPLIT") && vol->M <= (size_t) 48 << 20 && vol->dim_b[0] % 4 == 0 && vol->dim_b[1] <= 65535u && vol->dim_b[2] <= 1024u;
+		bool       split    = false;
+		if (split_ok) {
+			if ((rc = run_ysweep<0>(vol, vol->d_tmp, vol->d_swap, map, s, &done, 0, 0xffffffffu, true))) return rc;
+			split = done;
+		}
+		if (!split && !legacy && (rc = run_ysweep<0>(vol, vol->d_tmp, vol->d_swap, nullptr, s, &done))) return rc;
 		if (!done && (rc = run_minmax<0, 1>(vol, 1, vol->d_tmp, vol->d_swap, nullptr, s))) return rc;
 		done = false;
-		if (!legacy && (rc = run_zwalk<0>(vol, vol->d_swap, map, nullptr, s, &done))) return rc;
+		if (!legacy && (rc = run_zwalk<0>(vol, vol->d_swap, map, nullptr, s, &done, 0, 0xffffffffu, split ? map : nullptr))) return rc;
+		if (split && !done) {
+			set_error("launch_distance: split y sweeps need the z walk kernel");
+			return VKV_ERR_STATE;
+		}
 		if (!done && (rc = run_minmax<0, 1>(vol, 2, vol->d_swap, map, nullptr, s))) return rc;
 	} else if (skipping_type == VKV_SKIP_ANISOTROPIC_DISTANCE) {
 		// map index i = 4[x-] + 2[y-] + [z-]  (compute_distance_map.cpp:228-252); occupancy lives in map 7
