@@ -158,6 +158,7 @@ struct vkv_volume {
 	uint8_t            *grp_map[8]{}, *grp_swap[8]{};
 	GroupSignals       *d_grp = nullptr, *grp_sig[8]{};        // this rank's block and the peers' (grp_sig[rank] == d_grp)
 	GroupSignals      **d_grp_sig = nullptr;                   // the same pointers, on the device
+	uint8_t           **d_grp_ptrs = nullptr;                  // device copy of grp_map[8] followed by grp_swap[8]
 	unsigned            grp_seq = 0;
 	void               *d_lq = nullptr, *d_lrays = nullptr;        // ray caster: long-ray queue header + records (raycast.cu)
 	int                 long_cap = 0;

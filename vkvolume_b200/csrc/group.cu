@@ -61,6 +61,39 @@ __global__ void __launch_bounds__(32) group_sum_count_kernel(const GroupSignals 
 	}
 }
 
+// The exchange itself: this rank's piece of a buffer — n_chunks chunks of chunk_bytes at chunk_stride (one chunk: a z-slab; Db chunks:
+// a range of block rows in every slice) — read once and stored into the same place of every peer's copy of the buffer through the
+// peer mappings (remote stores over NVLink, like the ray caster's framebuffer epilogue).
+template <typename T>
+__global__ void __launch_bounds__(256) group_push_kernel(uint8_t *const *__restrict__ dsts, const uint8_t *__restrict__ src, size_t first, size_t chunk_bytes,
+                                                        size_t n_chunks, size_t chunk_stride, int rank, int world)
+{
+	const size_t per   = chunk_bytes / sizeof(T);
+	const size_t total = per * n_chunks;
+	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+		const size_t c = i / per, e = i - c * per;
+		const size_t off = first + c * chunk_stride + e * sizeof(T);
+		const T      v   = *reinterpret_cast<const T *>(src + off);
+		for (int p = 0; p < world; ++p)
+			if (p != rank) *reinterpret_cast<T *>(dsts[p] + off) = v;
+	}
+}
+
+static int group_push(vkv_volume *vol, uint8_t *const *dsts_dev, const uint8_t *src, size_t first, size_t chunk_bytes, size_t n_chunks, size_t chunk_stride,
+                      cudaStream_t s)
+{
+	if (chunk_bytes == 0 || n_chunks == 0 || vol->grp_world < 2) return VKV_OK;
+	const size_t total = chunk_bytes * n_chunks;
+	const int    grid  = (int) std::min<size_t>((size_t) vol->ctx->sm_count * 8, (total / 16 + 255) / 256 + 1);
+	const bool   a16   = first % 16 == 0 && chunk_bytes % 16 == 0 && chunk_stride % 16 == 0 && reinterpret_cast<uintptr_t>(src) % 16 == 0;
+	const bool   a4    = first % 4 == 0 && chunk_bytes % 4 == 0 && chunk_stride % 4 == 0 && reinterpret_cast<uintptr_t>(src) % 4 == 0;
+	if (a16) group_push_kernel<uint4><<<grid, 256, 0, s>>>(dsts_dev, src, first, chunk_bytes, n_chunks, chunk_stride, vol->grp_rank, vol->grp_world);
+	else if (a4) group_push_kernel<uint32_t><<<grid, 256, 0, s>>>(dsts_dev, src, first, chunk_bytes, n_chunks, chunk_stride, vol->grp_rank, vol->grp_world);
+	else group_push_kernel<uint8_t><<<grid, 256, 0, s>>>(dsts_dev, src, first, chunk_bytes, n_chunks, chunk_stride, vol->grp_rank, vol->grp_world);
+	VKV_LAUNCHED();
+	return VKV_OK;
+}
+
 static int group_barrier(vkv_volume *vol, const unsigned long long *count_dev, cudaStream_t s)
 {
 	++vol->grp_seq;
@@ -119,6 +152,9 @@ int vkv_volume_group_open(vkv_volume *vol, int rank, int world, const uint8_t *a
 	}
 	VKV_CUDA_CHECK(cudaMalloc(&vol->d_grp_sig, kGroupMax * sizeof(GroupSignals *)));
 	VKV_CUDA_CHECK(cudaMemcpy(vol->d_grp_sig, vol->grp_sig, kGroupMax * sizeof(GroupSignals *), cudaMemcpyHostToDevice));
+	VKV_CUDA_CHECK(cudaMalloc(&vol->d_grp_ptrs, 2 * kGroupMax * sizeof(uint8_t *)));        // [0..8): peers' map 0, [8..16): peers' d_swap
+	VKV_CUDA_CHECK(cudaMemcpy(vol->d_grp_ptrs, vol->grp_map, kGroupMax * sizeof(uint8_t *), cudaMemcpyHostToDevice));
+	VKV_CUDA_CHECK(cudaMemcpy(vol->d_grp_ptrs + kGroupMax, vol->grp_swap, kGroupMax * sizeof(uint8_t *), cudaMemcpyHostToDevice));
 	vol->grp_rank = rank; vol->grp_world = world;
 	return VKV_OK;
 }
@@ -135,7 +171,9 @@ int vkv_volume_group_close(vkv_volume *vol)
 		if (vol->grp_sig[p]) vkv_ipc_close(vol->grp_sig[p]);
 	}
 	cudaFree(vol->d_grp_sig);
-	vol->d_grp_sig = nullptr;
+	cudaFree(vol->d_grp_ptrs);
+	vol->d_grp_sig  = nullptr;
+	vol->d_grp_ptrs = nullptr;
 	memset(vol->grp_map, 0, sizeof vol->grp_map); memset(vol->grp_swap, 0, sizeof vol->grp_swap); memset(vol->grp_sig, 0, sizeof vol->grp_sig);
 	vol->grp_world = 0; vol->grp_rank = -1;
 	return VKV_OK;
@@ -169,18 +207,11 @@ int vkv_update_transfer_function_sharded(vkv_volume *vol, const vkv_volume_optio
 	if (sharded) {
 		// 2. x + y passes on the slab, xy-intermediate slab to every peer
 		if ((rc = launch_distance_xy_slab(vol, z0, zc, s))) return rc;
-		if (zc)
-			for (int p = 0; p < world; ++p)
-				if (p != rank)
-					VKV_CUDA_CHECK(cudaMemcpyAsync(vol->grp_swap[p] + z0 * plane, vol->d_swap + z0 * plane, zc * plane, cudaMemcpyDeviceToDevice, s));
+		if ((rc = group_push(vol, vol->d_grp_ptrs + kGroupMax, vol->d_swap, z0 * plane, zc * plane, 1, 0, s))) return rc;
 		if ((rc = group_barrier(vol, count_out ? vol->d_count : nullptr, s))) return rc;
 		// 4. z pass on the own block rows, result rows to every peer
 		if ((rc = launch_distance_z_rows(vol, y0, yc, s))) return rc;
-		if (yc)
-			for (int p = 0; p < world; ++p)
-				if (p != rank)
-					VKV_CUDA_CHECK(cudaMemcpy2DAsync(vol->grp_map[p] + (size_t) y0 * Wb, plane, vol->d_maps[0] + (size_t) y0 * Wb, plane, (size_t) yc * Wb, Db,
-					                                 cudaMemcpyDeviceToDevice, s));
+		if ((rc = group_push(vol, vol->d_grp_ptrs, vol->d_maps[0], (size_t) y0 * Wb, (size_t) yc * Wb, Db, plane, s))) return rc;
 		if ((rc = group_barrier(vol, nullptr, s))) return rc;
 		vol->occupancy_in_map = -1;
 		vol->maps_valid_for   = skipping_type;
@@ -188,11 +219,14 @@ int vkv_update_transfer_function_sharded(vkv_volume *vol, const vkv_volume_optio
 		// occupancy slabs to every peer, then the whole transform on every rank.  (The octant maps keep the occupancy in map 7,
 		// which is not exported: it travels through the peers' d_swap and is copied into place after the barrier.)
 		uint8_t *const stage = n_maps == 1 ? nullptr : vol->d_swap;
-		if (zc)
-			for (int p = 0; p < world; ++p)
-				if (p != rank)
-					VKV_CUDA_CHECK(cudaMemcpyAsync((n_maps == 1 ? vol->grp_map[p] : vol->grp_swap[p]) + z0 * plane, occ_map + z0 * plane, zc * plane,
-					                               cudaMemcpyDeviceToDevice, s));
+		// (source and destination offsets coincide: the slab sits at z0 * plane in this rank's occupancy map and in the peers' staging map)
+		if (n_maps == 1) {
+			if ((rc = group_push(vol, vol->d_grp_ptrs, occ_map, z0 * plane, zc * plane, 1, 0, s))) return rc;
+		} else {
+			// the peers' d_swap is the destination, the own map 7 the source: stage the slab in the own d_swap first (same offset)
+			if (zc) VKV_CUDA_CHECK(cudaMemcpyAsync(vol->d_swap + z0 * plane, occ_map + z0 * plane, zc * plane, cudaMemcpyDeviceToDevice, s));
+			if ((rc = group_push(vol, vol->d_grp_ptrs + kGroupMax, vol->d_swap, z0 * plane, zc * plane, 1, 0, s))) return rc;
+		}
 		if ((rc = group_barrier(vol, count_out ? vol->d_count : nullptr, s))) return rc;
 		if (stage) {
 			if (z0) VKV_CUDA_CHECK(cudaMemcpyAsync(occ_map, stage, z0 * plane, cudaMemcpyDeviceToDevice, s));
