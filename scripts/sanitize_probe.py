@@ -35,9 +35,10 @@ for tfo in (dict(intensity_min=0.5, intensity_max=1.0, gradient_min=0.1, gradien
     check("count == oracle", n == orc.occupied_voxel_count(V, G, tfu))
 vol.close()
 
-# (2) distance maps: y sweep over more than six 8-row chunks (its bulk-copy ring wraps), z walk with several segments, all 8 octant maps
-O = np.where(np.random.default_rng(2).random((72, 100, 64)) < 0.002, 0, 255).astype(np.uint8)
-vol = capi.Volume(ctx, 64, 100, 72, block_size=1)
+# (2) distance maps: y sweep over rows of three strips (edge exchange through shared memory every 16 rows), z walk with its two
+# walker warps meeting in the middle (named barrier), all 8 octant maps
+O = np.where(np.random.default_rng(2).random((72, 100, 544)) < 0.0005, 0, 255).astype(np.uint8)
+vol = capi.Volume(ctx, 544, 100, 72, block_size=1)
 vol.upload(np.where(O == 0, 255, 0).astype(np.uint8))
 opt = VolumeOptions(intensity_min=0.5, intensity_max=1.0, gradient_min=0.0, gradient_max=0.0)
 tfu = capi.transfer_function_uniform(opt)

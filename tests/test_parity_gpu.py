@@ -217,10 +217,14 @@ def _volume_with_occupancy(ctx, O):
 @pytest.mark.parametrize("shape,p", [((8, 9, 10), 0.05), ((16, 12, 20), 0.01), ((5, 24, 7), 0.1), ((1, 1, 30), 0.1), ((3, 1, 1), 0.5),
                                      ((20, 40, 70), 0.002), ((33, 65, 129), 0.0005), ((4, 4, 300), 0.003), ((300, 3, 5), 0.003),
                                      ((2, 1100, 3), 0.002), ((6, 6, 6), 0.0),
-                                     # long lines through the fast paths (Wb % 4 == 0): segment-parallel z walk with saturation
-                                     # beyond 255, chamfer y sweep over several TMA chunks, 64-word x rows, sparse sources
+                                     # long lines through the fast paths (Wb % 4 == 0): z walk with saturation beyond 255 and its value
+                                     # table wrapping (lines > 256 cells), chamfer y sweep, 64-word x rows, sparse sources
                                      ((300, 8, 16), 0.002), ((40, 300, 32), 0.001), ((70, 36, 128), 0.0005), ((520, 4, 8), 0.001),
-                                     ((4, 8, 2048), 0.0005), ((2, 4, 2052), 0.0008), ((130, 50, 64), 0.00005), ((33, 17, 1024), 0.0002)])
+                                     ((4, 8, 2048), 0.0005), ((2, 4, 2052), 0.0008), ((130, 50, 64), 0.00005), ((33, 17, 1024), 0.0002),
+                                     # rows wider than one 256-cell strip of the y sweep: several edge exchanges (every 16 rows), a ragged
+                                     # last strip, a last strip that owns a handful of cells; 8 / 16 cells per lane in the x pass
+                                     ((6, 70, 544), 0.001), ((3, 40, 260), 0.004), ((2, 100, 1000), 0.0002), ((5, 33, 456), 0.002),
+                                     ((700, 6, 36), 0.001)])
 def test_distance_maps_bit_exact(ctx, shape, p):
     rng = np.random.default_rng(abs(hash(shape)) % 1000)
     O = np.where(rng.random(shape) < p, 0, 255).astype(np.uint8)

@@ -117,70 +117,110 @@ struct RowBits {
 	}
 };
 
-template <int DIR, int SEGS>        // SEGS: compile-time bound on the row's 128-cell segments (2, 4, 8 or 16)
-__global__ void __launch_bounds__(256) xpass_vec4_kernel(const uint8_t *__restrict__ O, uint8_t *__restrict__ out, uint32_t Wb, uint64_t nrows)
+// CPL cells per lane (4, 8 or 16: one 4-, 8- or 16-byte load and store), SEGS: compile-time bound on the row's segments of 32 CPL
+// cells.  The more cells a lane owns, the fewer nearest-bit searches a row costs (two per lane and segment); a row's words are
+// all requested before any is looked at, and the next row's before this row is worked on (one DRAM round trip per row, hidden
+// behind the previous row's arithmetic).  Rows without a single occupied cell are answered with one store per lane.
+template <int CPL> struct XWords;
+template <> struct XWords<4>  { using T = unsigned; };
+template <> struct XWords<8>  { using T = uint2; };
+template <> struct XWords<16> { using T = uint4; };
+
+template <int DIR, int CPL, int SEGS>
+__global__ void __launch_bounds__(256) xpass_lanes_kernel(const uint8_t *__restrict__ O, uint8_t *__restrict__ out, uint32_t Wb, uint64_t nrows)
 {
+	using V = typename XWords<CPL>::T;
+	constexpr int WPL = CPL / 4, LPW = 32 / CPL;        // words per lane; lanes per 32-cell mask word
 	__shared__ unsigned s_words[8][kRowWordsMax];
 	const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	unsigned      *words = s_words[warp];
-	const uint32_t nseg  = (Wb + 127) / 128;
+	const uint32_t nseg  = (Wb + 32 * CPL - 1) / (32 * CPL);
 	for (int i = lane; i < kRowWordsMax; i += 32) words[i] = 0;
 	__syncwarp();
-	for (uint64_t row = (uint64_t) blockIdx.x * 8 + warp; row < nrows; row += (uint64_t) gridDim.x * 8) {
+	union Cells { V v; unsigned w[WPL]; };
+	auto request = [&](Cells (&c)[SEGS], uint64_t row) {
 		const uint8_t *src = O + row * Wb;
-		// the whole row is requested before any of it is looked at: one DRAM round trip per row, not one per 128 cells
-		unsigned cw[SEGS];
 #pragma unroll
 		for (uint32_t sgm = 0; sgm < (uint32_t) SEGS; ++sgm) {
-			const uint32_t x = sgm * 128 + lane * 4;
-			cw[sgm]          = (sgm < nseg && x < Wb) ? __ldg(reinterpret_cast<const unsigned *>(src + x)) : 0xffffffffu;
+			const uint32_t x = (sgm * 32 + lane) * CPL;
+#pragma unroll
+			for (int w = 0; w < WPL; ++w) c[sgm].w[w] = 0xffffffffu;
+			if (sgm < nseg && x < Wb) c[sgm].v = __ldg(reinterpret_cast<const V *>(src + x));
 		}
+	};
+	const uint64_t stride = (uint64_t) gridDim.x * 8;
+	uint64_t       row    = (uint64_t) blockIdx.x * 8 + warp;
+	Cells cur[SEGS], nxt[SEGS];
+	if (row < nrows) request(cur, row);
+	for (; row < nrows; row += stride) {
+		if (row + stride < nrows) request(nxt, row + stride);
+		unsigned occ[SEGS];        // this lane's CPL occupancy bits per segment
 #pragma unroll
 		for (uint32_t sgm = 0; sgm < (uint32_t) SEGS; ++sgm) {
 			if (sgm >= nseg) break;
-			const unsigned c = cw[sgm];
-			unsigned       t = (c & 0x7f7f7f7fu) + 0x7f7f7f7fu;        // exact zero-byte detector -> 0x80 per zero byte
-			t                = ~(t | c | 0x7f7f7f7fu);
-			const unsigned y = t >> 7;
-			unsigned       v = ((y | (y >> 7) | (y >> 14) | (y >> 21)) & 0xfu) << (4 * (lane & 7));
-			v |= __shfl_xor_sync(0xffffffffu, v, 1);
-			v |= __shfl_xor_sync(0xffffffffu, v, 2);
-			v |= __shfl_xor_sync(0xffffffffu, v, 4);
-			if ((lane & 7) == 0) words[sgm * 4 + (lane >> 3)] = v;
+			unsigned bits = 0;
+#pragma unroll
+			for (int w = 0; w < WPL; ++w) {
+				const unsigned c = cur[sgm].w[w];
+				unsigned       t = (c & 0x7f7f7f7fu) + 0x7f7f7f7fu;        // exact zero-byte detector -> 0x80 per zero byte
+				t                = ~(t | c | 0x7f7f7f7fu);
+				const unsigned y = t >> 7;
+				bits |= ((y | (y >> 7) | (y >> 14) | (y >> 21)) & 0xfu) << (4 * w);
+			}
+			occ[sgm]   = bits;
+			unsigned v = bits << (CPL * (lane % LPW));
+#pragma unroll
+			for (int o = 1; o < LPW; o <<= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+			if (lane % LPW == 0) words[sgm * CPL + lane / LPW] = v;
 		}
 		__syncwarp();
 		RowBits rb;
 		rb.words = words;
 		rb.nz    = (unsigned long long) __ballot_sync(0xffffffffu, words[lane] != 0u) |
 		        ((unsigned long long) __ballot_sync(0xffffffffu, words[32 + lane] != 0u) << 32);
-		for (uint32_t sgm = 0; sgm < nseg; ++sgm) {
-			const uint32_t x = sgm * 128 + lane * 4;
+		uint8_t *dst = out + row * Wb;
+#pragma unroll
+		for (uint32_t sgm = 0; sgm < (uint32_t) SEGS; ++sgm) {
+			if (sgm >= nseg) break;
+			const uint32_t x = (sgm * 32 + lane) * CPL;
 			if (x < Wb) {
-				const int      w = (int) (x >> 5), b = (int) (x & 31);
-				const unsigned occ = (words[w] >> b) & 0xfu;
-				unsigned       d[4] = {255u, 255u, 255u, 255u};
-				if (DIR >= 0) {
-					unsigned r = rb.right(w, b + 3);
-					d[3]       = r;
+				Cells res;
+				if (rb.nz == 0ull) {        // nothing in this row: every distance saturates
 #pragma unroll
-					for (int k = 2; k >= 0; --k) {
-						r    = ((occ >> k) & 1u) ? 0u : min(r + 1u, 255u);
-						d[k] = r;
-					}
-				}
-				if (DIR <= 0) {
-					unsigned l = rb.left(w, b);
-					d[0]       = min(d[0], l);
+					for (int w = 0; w < WPL; ++w) res.w[w] = 0xffffffffu;
+				} else {
+					const int      w0 = (int) (x >> 5), b = (int) (x & 31);
+					const unsigned oc = occ[sgm];
+					unsigned       d[CPL];
 #pragma unroll
-					for (int k = 1; k < 4; ++k) {
-						l    = ((occ >> k) & 1u) ? 0u : min(l + 1u, 255u);
-						d[k] = min(d[k], l);
+					for (int k = 0; k < CPL; ++k) d[k] = 255u;
+					if (DIR >= 0) {
+						unsigned r = rb.right(w0, b + CPL - 1);
+						d[CPL - 1] = r;
+#pragma unroll
+						for (int k = CPL - 2; k >= 0; --k) {
+							r    = ((oc >> k) & 1u) ? 0u : __viaddmin_u32(r, 1u, 255u);
+							d[k] = r;
+						}
 					}
+					if (DIR <= 0) {
+						unsigned l = rb.left(w0, b);
+						d[0]       = min(d[0], l);
+#pragma unroll
+						for (int k = 1; k < CPL; ++k) {
+							l    = ((oc >> k) & 1u) ? 0u : __viaddmin_u32(l, 1u, 255u);
+							d[k] = min(d[k], l);
+						}
+					}
+#pragma unroll
+					for (int w = 0; w < WPL; ++w) res.w[w] = d[4 * w] | (d[4 * w + 1] << 8) | (d[4 * w + 2] << 16) | (d[4 * w + 3] << 24);
 				}
-				*reinterpret_cast<unsigned *>(out + row * Wb + x) = d[0] | (d[1] << 8) | (d[2] << 16) | (d[3] << 24);
+				*reinterpret_cast<V *>(dst + x) = res.v;
 			}
 		}
 		__syncwarp();
+#pragma unroll
+		for (uint32_t sgm = 0; sgm < (uint32_t) SEGS; ++sgm) cur[sgm] = nxt[sgm];
 	}
 }
 
@@ -343,157 +383,139 @@ __global__ void __launch_bounds__(256) minmax_rmq_kernel(const uint8_t *__restri
 // min over sources of max(|dx|, |dy|), saturating at 255 because g <= 255), O(1) per cell, no search at all.
 // The octant-restricted maps use the one-sided x pass and only the neighbours {0, sx} (a step may not leave the
 // quadrant), and keep the two sweep directions as two outputs (sources at y' >= y -> dst0, y' <= y -> dst1).
-// One CTA per z slice; thread t owns cells t, t + T, ...; the previous row lives in shared memory (double-buffered,
-// one __syncthreads per row); the rows of the input are prefetched eight at a time.
-__device__ __forceinline__ uint32_t d_smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
-__device__ __forceinline__ void d_mbar_init(uint64_t *bar, unsigned count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(d_smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void d_mbar_expect_tx(uint64_t *bar, unsigned bytes)
-{
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(d_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void d_mbar_wait(uint64_t *bar, unsigned parity)
-{
-	unsigned           ok, spins = 0;
-	unsigned long long t0 = 0ull;
-	do {
-		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-		             : "=r"(ok)
-		             : "r"(d_smem_u32(bar)), "r"(parity)
-		             : "memory");
-		// a lost arrival must surface as an error, never as a hung GPU — but only after 20 s of WALL time (%globaltimer), so that
-		// time-slicing, a debugger, compute-sanitizer or first-touch page migration cannot trip it (a spin count could)
-		if (!ok && (++spins & 1023u) == 0u) {
-			unsigned long long now;
-			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-			if (t0 == 0ull) t0 = now;
-			else if (now - t0 > 20000000000ull) __trap();
-		}
-	} while (!ok);
-}
-__device__ __forceinline__ void d_tma_load_1d(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar)
-{
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d_smem_u32(smem_dst)),
-	             "l"(gmem_src), "r"(bytes), "r"(d_smem_u32(bar))
-	             : "memory");
-}
-
-// The input rows arrive by 1-D bulk TMA copies, kSweepRows rows (one contiguous block of the slice) per copy, through a
-// ring of kSweepSlots buffers with one mbarrier each: the serial row recurrence never waits on a global load.
-// A thread owns FOUR adjacent cells.  The previous row lives in shared memory as 16-bit lanes (two u16x2 words per
-// thread), so the whole row step is a handful of native packed instructions with a short dependency chain — the step
-// latency, not the instruction count, is what bounds a sweep of Hb dependent rows:
-//     neighbours x +- 1 : 16-bit funnel shifts against the adjacent words
-//     min of the three  : VIMNMX3.U16x2
-//     min(g, m + 1)     : VIADDMNMX.U16x2     (m <= 255, so m + 1 needs no saturation; the result is <= g <= 255)
-// and a 1024-cell row is 8 warps instead of 32 — the per-row barrier is cheaper and several slices share an SM.
-constexpr int kSweepRows  = 8;
-constexpr int kSweepSlots = 6;
+//
+// What bounds a sweep is the latency of one row step times the rows of a slice, so the step is kept inside a WARP: a warp
+// owns a strip of 256 adjacent cells, eight per lane, the previous row lives in registers as 16-bit lanes (four u16x2 words
+// per lane), the x +- 1 neighbours across lanes come from two shuffles, and the step itself is a handful of native packed
+// instructions (funnel shifts, VIMNMX3.U16x2, VIADDMNMX.U16x2: min(g, m + 1) needs no saturation because m <= 255) —
+// no shared memory, no barrier.  Rows wider than a strip are covered by overlapping strips: a strip's outer 32 cells
+// on either side are a halo it computes but does not own; what a strip does not know about its neighbours spoils one
+// more halo cell per row, so every 32 rows the warps of a slice exchange their edge cells through shared memory (one
+// barrier per 32 rows instead of one per row).  Input rows are requested eight rows ahead, straight into registers.
+// (The kernel this replaces — one CTA per slice, previous row in shared memory, one barrier per row, rows streamed through a
+// bulk-TMA ring — spent 430 cycles per row step and 0.6 warp instructions per cell: profiles/r2v_k3_c5.)
+// `split` (isotropic, small maps): the two sweeps of a slice are independent when both start from g — the result is then
+// min(up, down), which the z pass takes while it stages — so they run as two CTAs (blockIdx.x = 2 slice + sweep) and the serial
+// chain of a slice is Hb row steps instead of 2 Hb; costs one more map of traffic, so only where the maps live in the L2.
+constexpr int kStripHalo = 16, kStripBlock = 16;        // kStripBlock <= kStripHalo
 __device__ __forceinline__ unsigned d_prmt(unsigned a, unsigned b, unsigned sel)
 {
 	unsigned r;
 	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
 	return r;
 }
-// `split` (isotropic, small maps): the two sweeps of a slice are independent when both start from g — the result is then
-// min(up, down), which the z pass takes while it stages — so they run as two CTAs (blockIdx.x = 2 slice + sweep) and the serial
-// chain of a slice is Hb row steps instead of 2 Hb; costs one more map of traffic, so only where the maps live in the L2.
-template <int XDIR>        // XDIR 0: isotropic (two-sided x, 3 neighbours, in-place second sweep); +-1: one-sided
-__global__ void __launch_bounds__(256) ysweep_kernel(const uint8_t *__restrict__ g, uint8_t *__restrict__ dst0, uint8_t *__restrict__ dst1,
-                                                     uint32_t Wb, uint32_t Hb, int split)
+
+// XDIR 0: isotropic (two-sided x, 3 neighbours, in-place second sweep); +-1: one-sided.
+// CPL: cells per lane, 8 (strips of 256 cells, 224 owned; the one launched) or 4 (128 / 96).
+template <int XDIR, int CPL>
+__global__ void __launch_bounds__(512) ysweep_kernel(const uint8_t *__restrict__ g, uint8_t *__restrict__ dst0, uint8_t *__restrict__ dst1,
+                                                     uint32_t Wb, uint32_t Hb, int split, int nstrips)
 {
-	extern __shared__ __align__(128) uint8_t s_dyn[];        // kSweepSlots chunks of kSweepRows x Wb | 2 row buffers of Wb/4 + 2 uint2
-	__shared__ __align__(8) uint64_t s_bar[kSweepSlots];
-	const uint32_t t      = threadIdx.x;                     // group of 4 cells of the row
-	const uint32_t W4     = Wb >> 2;
-	const bool     active = t < W4;
-	const size_t   slice  = (size_t) (split ? blockIdx.x >> 1 : blockIdx.x) * Wb * Hb;
-	const uint32_t chunk_bytes = kSweepRows * Wb;
-	uint8_t       *ring = s_dyn;
-	uint2         *buf0 = reinterpret_cast<uint2 *>(s_dyn + (size_t) kSweepSlots * chunk_bytes) + 1, *buf1 = buf0 + (W4 + 2);
-	const uint32_t nchunks = (Hb + kSweepRows - 1) / kSweepRows;
-	constexpr unsigned kFar = 0x00ff00ffu;        // 255 in both lanes
-	if (t == 0) {
-		for (int i = 0; i < kSweepSlots; ++i) d_mbar_init(&s_bar[i], 1);
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	constexpr int NW = CPL / 2, NL = CPL / 4;                  // u16x2 words of state, 32-bit words of cells per lane
+	extern __shared__ __align__(16) unsigned s_edge[];        // 2 x (Wb / 2 + 8) u16x2 words: a row of F at a block boundary (double-buffered)
+	constexpr unsigned kFar = 0x00ff00ffu;                     // 255 in both lanes
+	const int      lane = threadIdx.x & 31, strip = threadIdx.x >> 5;
+	const int      halo = nstrips > 1 ? kStripHalo : 0, own = 32 * CPL - 2 * halo;
+	const int      x    = strip * own - halo + CPL * lane;        // the first of this lane's cells (may lie outside the row)
+	const bool     owned = CPL * lane >= halo && CPL * lane < halo + own;
+	// words outside the row read as "far": load some word of the row instead and force the bits on  (Wb % 4 == 0)
+	bool     in[NL], st[NL];
+	unsigned force[NL];
+	int      xl[NL];
+#pragma unroll
+	for (int w = 0; w < NL; ++w) {
+		in[w]    = x + 4 * w >= 0 && x + 4 * w < (int) Wb;
+		force[w] = in[w] ? 0u : 0xffffffffu;
+		xl[w]    = in[w] ? x + 4 * w : 0;
+		st[w]    = owned && in[w];
 	}
-	__syncthreads();
-	unsigned issued = 0;        // copies issued so far (thread 0): copy n lands in ring slot n % kSweepSlots, phase (n / kSweepSlots) & 1
+	const size_t   slice = (size_t) (split ? blockIdx.x >> 1 : blockIdx.x) * Wb * Hb;
+	const int      edge_words = (int) (Wb >> 1) + 8;
+	int            parity = 0;
 	for (int sweep = split ? (int) (blockIdx.x & 1u) : 0; sweep < 2; ++sweep) {
 		// sweep 0 walks y upwards (sources at y' <= y), sweep 1 downwards (sources at y' >= y)
-		const uint8_t  *src  = (XDIR == 0 && sweep == 1 && !split) ? dst0 : g;
-		uint8_t        *dst  = (XDIR == 0 && !split) ? dst0 : (sweep == 0 ? dst1 : dst0);
-		const ptrdiff_t step = sweep == 0 ? (ptrdiff_t) W4 : -(ptrdiff_t) W4;        // in words
-		unsigned       *dp   = reinterpret_cast<unsigned *>(dst + slice + (sweep == 0 ? 0 : (size_t) (Hb - 1) * Wb)) + t;
-		// chunk c of this sweep = rows [lo, lo + n) of the slice, consumed upwards (sweep 0) or downwards (sweep 1)
-		auto issue = [&](uint32_t c) {
-			const uint32_t i0 = c * kSweepRows, n = min((uint32_t) kSweepRows, Hb - i0);
-			const uint32_t lo = sweep == 0 ? i0 : Hb - i0 - n;
-			const unsigned slot = issued % kSweepSlots;
-			d_mbar_expect_tx(&s_bar[slot], n * Wb);
-			d_tma_load_1d(ring + (size_t) slot * chunk_bytes, src + slice + (size_t) lo * Wb, n * Wb, &s_bar[slot]);
-			++issued;
-		};
-		if (XDIR == 0 && sweep == 1 && !split) {
-			// the second sweep re-reads what this CTA just wrote with ordinary stores: order them before the async-proxy reads
-			__threadfence();
-			asm volatile("fence.proxy.async;" ::: "memory");
-		}
-		if (t == 0) {
-			buf0[-1] = make_uint2(kFar, kFar); buf1[-1] = make_uint2(kFar, kFar);
-			buf0[W4] = make_uint2(kFar, kFar); buf1[W4] = make_uint2(kFar, kFar);
-		}
-		if (active) buf0[t] = make_uint2(kFar, kFar);        // "row -1": nothing behind the first row
-		__syncthreads();
-		const unsigned consumed = issued;       // uniform bookkeeping of the copy sequence number (every thread tracks it)
-		if (t == 0)
-			for (uint32_t c = 0; c < (uint32_t) kSweepSlots && c < nchunks; ++c) issue(c);
-		for (uint32_t c = 0; c < nchunks; ++c) {
-			const unsigned seq = consumed + c, slot = seq % kSweepSlots;
-			d_mbar_wait(&s_bar[slot], (seq / kSweepSlots) & 1u);
-			const uint32_t  n  = min((uint32_t) kSweepRows, Hb - c * kSweepRows);
-			const unsigned *cb = reinterpret_cast<const unsigned *>(ring + (size_t) slot * chunk_bytes);
-			// rows alternate between the two row buffers; a chunk has an even number of rows unless it is the last one, so the
-			// buffer roles are compile-time constants of the 2-row unrolled loop
-			const unsigned *cp = cb + (sweep == 0 ? 0 : (size_t) (n - 1) * W4) + t;        // this thread's word in the chunk's first row
-			auto row_step = [&](const uint2 *prev, uint2 *now) {
-				if (active) {
-					const unsigned gw = *cp;
-					const uint2    p  = prev[t];                       // cells 0,1 | 2,3 of this thread in the previous row
-					const unsigned mid = __funnelshift_r(p.x, p.y, 16);        // cells 1,2
-					unsigned       ma = p.x, mb = p.y;
-					if (XDIR == 0) {
-						ma = __vimin3_u16x2(p.x, __funnelshift_l(prev[(int) t - 1].y, p.x, 16), mid);        // cells -1,0 and 1,2
-						mb = __vimin3_u16x2(p.y, mid, __funnelshift_r(p.y, prev[t + 1].x, 16));              // cells 1,2 and 3,4
-					} else if (XDIR > 0) {
-						ma = __vminu2(p.x, mid);
-						mb = __vminu2(p.y, __funnelshift_r(p.y, prev[t + 1].x, 16));
-					} else {
-						ma = __vminu2(p.x, __funnelshift_l(prev[(int) t - 1].y, p.x, 16));
-						mb = __vminu2(p.y, mid);
-					}
-					const unsigned va = __viaddmin_u16x2(ma, 0x00010001u, d_prmt(gw, 0u, 0x4140u));
-					const unsigned vb = __viaddmin_u16x2(mb, 0x00010001u, d_prmt(gw, 0u, 0x4342u));
-					now[t] = make_uint2(va, vb);
-					*dp    = d_prmt(va, vb, 0x6420u);
-					dp += step;
-					cp += step;
-				}
-				__syncthreads();
-			};
-			uint32_t k = 0;
-			for (; k + 2 <= n; k += 2) {
-				row_step(buf0, buf1);
-				row_step(buf1, buf0);
+		const bool      inplace = XDIR == 0 && sweep == 1 && !split;
+		const uint8_t  *src = (inplace ? dst0 : g) + slice;
+		uint8_t        *dst = ((XDIR == 0 && !split) ? dst0 : (sweep == 0 ? dst1 : dst0)) + slice;
+		// The second sweep of the in-place variant reads what the first one wrote: its own cells, and — in the halo — cells of the
+		// neighbouring warps, which may by then hold either sweep's value.  Both are right: the final value is min(first, 1 + ...),
+		// so taking it as the base term reproduces it.
+		if (inplace) __syncthreads();
+		unsigned prev[NW];        // "row -1": nothing behind the first row
+#pragma unroll
+		for (int w = 0; w < NW; ++w) prev[w] = kFar;
+		const ptrdiff_t rs = sweep == 0 ? (ptrdiff_t) Wb : -(ptrdiff_t) Wb;        // from one row of the sweep to the next
+		const size_t    first = sweep == 0 ? 0 : (size_t) (Hb - 1) * Wb;
+		const uint8_t  *lp = src + first;        // the next row to request
+		uint8_t        *sp = dst + first;        // the next row to store
+		uint32_t        requested = 0;
+		// eight rows into registers (rows past the slice repeat its last row: requested, never used)
+		auto load8 = [&](unsigned (&buf)[8][NL]) {
+#pragma unroll
+			for (int k = 0; k < 8; ++k) {
+#pragma unroll
+				for (int w = 0; w < NL; ++w)
+					buf[k][w] = (inplace ? __ldcg(reinterpret_cast<const unsigned *>(lp + xl[w])) : __ldg(reinterpret_cast<const unsigned *>(lp + xl[w]))) | force[w];
+				if (++requested < Hb) lp += rs;
 			}
-			if (k < n) row_step(buf0, buf1);        // odd tail: only ever in the last chunk of a sweep
-			// every thread is past the chunk: its ring slot may be refilled
-			if (t == 0 && c + kSweepSlots < nchunks) issue(c + kSweepSlots);
+		};
+		auto step8 = [&](const unsigned (&buf)[8][NL], const uint32_t rows) {        // rows: how many of the eight exist (8 except in the last group)
+#pragma unroll
+			for (int k = 0; k < 8; ++k) {
+				if ((uint32_t) k >= rows) break;
+				// the cells next to the lane's own live in the neighbouring lanes; beyond the strip: far (true at the row's ends,
+				// repaired by the halo inside)
+				unsigned left  = __shfl_up_sync(0xffffffffu, prev[NW - 1], 1);
+				unsigned right = __shfl_down_sync(0xffffffffu, prev[0], 1);
+				if (lane == 0) left = kFar;
+				if (lane == 31) right = kFar;
+				unsigned m[NW + 1];        // m[w]: cells 2w - 1, 2w
+				m[0] = __funnelshift_l(left, prev[0], 16);
+#pragma unroll
+				for (int w = 1; w < NW; ++w) m[w] = __funnelshift_r(prev[w - 1], prev[w], 16);
+				m[NW] = __funnelshift_r(prev[NW - 1], right, 16);
+#pragma unroll
+				for (int w = 0; w < NW; ++w) {
+					unsigned n;
+					if (XDIR == 0) n = __vimin3_u16x2(m[w], prev[w], m[w + 1]);
+					else if (XDIR > 0) n = __vminu2(prev[w], m[w + 1]);
+					else n = __vminu2(prev[w], m[w]);
+					prev[w] = __viaddmin_u16x2(n, 0x00010001u, d_prmt(buf[k][w >> 1], 0u, (w & 1) ? 0x4342u : 0x4140u));
+				}
+#pragma unroll
+				for (int w = 0; w < NL; ++w)
+					if (st[w]) reinterpret_cast<unsigned *>(sp + x)[w] = d_prmt(prev[2 * w], prev[2 * w + 1], 0x6420u);
+				sp += rs;
+			}
+		};
+		// every kStripBlock rows the strips of the slice swap edges: owners publish the row they hold, halo lanes take it over
+		auto exchange = [&]() {
+			unsigned *e = s_edge + parity * edge_words + (x >> 1);
+			if (owned) {
+#pragma unroll
+				for (int w = 0; w < NL; ++w)
+					if (in[w]) *reinterpret_cast<uint2 *>(e + 2 * w) = make_uint2(prev[2 * w], prev[2 * w + 1]);
+			}
+			__syncthreads();
+			if (!owned) {
+#pragma unroll
+				for (int w = 0; w < NL; ++w) {
+					uint2 v = make_uint2(kFar, kFar);
+					if (in[w]) v = *reinterpret_cast<const uint2 *>(e + 2 * w);
+					prev[2 * w] = v.x; prev[2 * w + 1] = v.y;
+				}
+			}
+			parity ^= 1;
+		};
+		unsigned ga[8][NL], gb[8][NL];
+		load8(ga);
+		for (uint32_t i0 = 0; i0 < Hb; i0 += 16) {
+			load8(gb);
+			step8(ga, min(8u, Hb - i0));
+			load8(ga);
+			if (i0 + 8 < Hb) step8(gb, min(8u, Hb - i0 - 8));
+			if (nstrips > 1 && i0 + 16 < Hb) exchange();
 		}
-		issued = consumed + nchunks;        // keep every thread's view of the sequence number in step with thread 0's
-		if (split) break;                   // one sweep per CTA
 	}
 }
 
@@ -501,125 +523,143 @@ __global__ void __launch_bounds__(256) ysweep_kernel(const uint8_t *__restrict__
 // One-sided result towards +z: F(z) = min_{j >= z} max(j - z, h(j)).  Stepping from z + 1 to z every candidate's cost
 // grows by at most one, so with r = F(z + 1):   F(z) = min( h(z), r      if some j in [z+1, z+r] has h(j) <= r
 //                                                                 r + 1  otherwise ),
-// i.e. ONE range-minimum query per cell instead of an 8-step binary search; the two-sided value is min(F, B) with B the
-// mirror image.  A CTA owns TW adjacent columns: it stages them and builds the sparse range-minimum table four columns
-// per thread (32-bit shared-memory accesses, packed byte minimum).  The walk itself is cut into segments of kWalkSeg
-// cells: a walker (one thread per column, direction and segment) finds the value at the head of its segment with the
-// 8-step binary search and walks from there, so a line of L cells is 2 L / kWalkSeg independent dependency chains of
-// ~kWalkSeg + 8 queries instead of two chains of L — the CTA's shared-memory tables are shared by up to 1024 walkers
-// (with one walker per column and direction a long line left most of the SM idle).  Result rows leave as 32-bit words.
-// MODE 0: dst0 = min(F, B) | 3: dst0 = F (towards +z), dst1 = B (towards -z).   Needs Wb % 4 == 0 and TW % 4 == 0.
-constexpr int kWalkSeg = 32;
+// and the two-sided value is min(F, B) with B the mirror image.  No cell of [z+1, z+r] can have h < r (it would have made
+// F(z + 1) smaller), so the window test asks one thing only: is the NEAREST cell behind the walker whose value is exactly r
+// at most r steps away?  A walker therefore keeps, per value v, the step at which it last passed a cell with h == v (256 bytes of
+// shared memory, step numbers mod 256) and a step is: one load of h(z), one load of last[r], one load of the cell that entry
+// names to validate it (stale or never-written entries name some other cell: the test then fails on its value or its distance,
+// and an entry that happens to name a cell with h == r within reach is a witness in its own right — so the table needs no
+// initialisation), one store of last[h(z)], ~25 instructions in all, no search, no range-minimum tables, whatever the
+// distances are.  (The table-based walk this replaces spent 5 warp instructions per cell — 2.65 G on the 1024x1024x512 map,
+// 3.1 ms, profiles/r2v_k3_c5 — and 10 L bytes of shared memory per column; a variant tracking the window minimum with rescans
+// was measured slower still: on a sparse map every step of a warp has some lane rescanning.)
+// A CTA owns 32 adjacent columns, staged as 32-bit words by all its threads; warp 0 then walks them towards -z (F), warp 1 towards
+// +z (B), a lane per column, each cell's result going straight to global memory (one 32-byte sector per warp and step).
+// MODE 0: dst0 = min(F, B) (folded on the way, see walk_line) | 3: dst0 = F (towards +z), dst1 = B (towards -z).   Needs Wb % 4 == 0.
+constexpr int kWalkTW = 32;
 
-// F(z) towards +z (SIDE > 0) or -z (SIDE < 0) from scratch: smallest r with min h over the r + 1 cells from z on <= r.
-// Only radii <= 254 are ever tested (hi <= 255), so windows have at most 255 cells: table levels 0..7.
-template <int SIDE>
-__device__ __forceinline__ unsigned walk_head(const uint8_t *__restrict__ T, int L, int TW, size_t lst, int z, int col, unsigned h0)
+// SIDE > 0: F (sources at or after a cell: the walk starts at the line's last cell); SIDE < 0: B, the mirror image.
+// `tcol` = the column's cell 0 in the staged tile (rows kWalkTW bytes apart), `last` = this walker's byte of the value table's
+// row 0 (rows kWalkTW bytes apart), `res` = the column's cell 0 in the result map.
+// FOLD: the two walkers of a column meet in the middle.  Up to there a walker is the first to reach its cells and stores its own
+// value; past it (after a barrier of the two walker warps) the other walker's value is already in the result map, and what is
+// stored is the minimum of the two — the two-sided result, without a second result map or a pass to combine them.  The other
+// walker's values are requested a group of eight steps ahead (L2), off the walker's dependency chain.
+template <int SIDE, bool FOLD>
+__device__ __forceinline__ void walk_line(const uint8_t *__restrict__ tcol, uint8_t *__restrict__ last, uint8_t *res, size_t res_stride, int L, bool live)
 {
-	unsigned lo = 0, hi = min(h0, 255u);
-	while (lo < hi) {
-		const int r = (int) ((lo + hi) >> 1);
-		const int a = SIDE > 0 ? z : max(z - r, 0);
-		const int b = SIDE > 0 ? min(z + r, L - 1) : z;
-		const int k = 31 - __clz(b - a + 1);
-		const uint8_t *Tk = T + (size_t) k * lst;
-		const unsigned w  = min((unsigned) Tk[a * TW + col], (unsigned) Tk[(b - (1 << k) + 1) * TW + col]);
-		if (w <= (unsigned) r) hi = (unsigned) r;
-		else lo = (unsigned) r + 1;
+	constexpr int   st = SIDE > 0 ? kWalkTW : -kWalkTW;        // one cell towards the walker's sources
+	const int       z0 = SIDE > 0 ? L - 1 : 0;
+	const uint8_t  *p  = tcol + z0 * kWalkTW;
+	uint8_t        *o  = res + (size_t) z0 * res_stride;
+	const ptrdiff_t os = SIDE > 0 ? -(ptrdiff_t) res_stride : (ptrdiff_t) res_stride;
+	int             r  = *p;                                   // the line's end: nothing behind it
+	last[r * kWalkTW] = 0;
+	unsigned        e  = 0;                                    // last[r]: the step at which the nearest cell with h == r was passed
+	// The dependency chain of a step is  e -> distance -> address -> validating load -> witness -> r.  The table entry of the NEXT
+	// step is taken off it: r can only become min(h, r) or min(h, r + 1), both known before the witness is, so both entries are
+	// requested up front and the witness selects one.
+	auto step = [&](int k) {        // k: steps walked = cells behind the current one
+		p -= st;
+		const int      hz   = *p;
+		const unsigned dist = ((unsigned) k - e) & 255u;             // how far back the table says the nearest cell with h == r lies
+		const int      dc   = min((int) dist, k);                    // (never past the line's end: the cell there is as good a witness)
+		const int      v    = p[dc * st];
+		last[hz * kWalkTW]  = (uint8_t) k;
+		const int      ra = min(hz, r), rb = min(hz, r + 1);         // (r == 255 always has a witness one step back: no overflow)
+		const unsigned ea = last[ra * kWalkTW], eb = last[rb * kWalkTW];
+		const bool     wit = ((int) dist <= r) & (v == r);
+		r = wit ? ra : rb;
+		e = wit ? ea : eb;
+	};
+	// cells z >= L / 2 are reached by F first, the others by B
+	const int mine = FOLD ? (SIDE > 0 ? L - L / 2 : L / 2) : L;
+	if (mine > 0 && live) *o = (uint8_t) r;
+	int k = 1;
+#pragma unroll 2
+	for (; k < mine; ++k) {
+		step(k);
+		o += os;
+		if (live) *o = (uint8_t) r;
 	}
-	return lo;
+	if (FOLD) {
+		asm volatile("bar.sync 1, 64;" ::: "memory");        // the two walker warps: everything stored so far is visible to the other
+		if (mine == 0) {        // L == 1, the B walker: its only cell was F's
+			if (live) *o = (uint8_t) min(r, (int) __ldcg(o));
+			return;
+		}
+		// the other walker's values of the next eight cells, requested a group ahead
+		constexpr int G = 8;
+		auto request = [&](unsigned (&q)[G], int k0) {
+#pragma unroll
+			for (int j = 0; j < G; ++j) q[j] = (live && k0 + j < L) ? (unsigned) __ldcg(o + (ptrdiff_t) (k0 + j - (k - 1)) * os) : 255u;
+		};
+		unsigned cur[G], nxt[G];
+		request(cur, k);
+		while (k < L) {
+			request(nxt, k + G);
+#pragma unroll
+			for (int j = 0; j < G; ++j) {
+				if (k < L) {
+					step(k);
+					o += os;
+					if (live) *o = (uint8_t) min((unsigned) r, cur[j]);
+					++k;
+				}
+			}
+#pragma unroll
+			for (int j = 0; j < G; ++j) cur[j] = nxt[j];
+		}
+	}
 }
 
 // src2 (or null): a second input, the cell-wise minimum of the two is what gets transformed (the split y sweeps' outputs)
-template <int MODE>
-__global__ void __launch_bounds__(1024) zwalk_kernel(const uint8_t *__restrict__ src, const uint8_t *__restrict__ src2, uint8_t *__restrict__ dst0,
-                                                     uint8_t *__restrict__ dst1, uint32_t Wb, uint32_t L, size_t line_stride, size_t outer_stride, int TW,
-                                                     int nlev)
+template <int MODE, int THREADS>        // THREADS: 64 (short lines: CTAs per SM are bound by their number) or 256 (long lines: by shared memory; more threads stage)
+__global__ void __launch_bounds__(THREADS) zwalk_kernel(const uint8_t *__restrict__ src, const uint8_t *__restrict__ src2, uint8_t *dst0, uint8_t *dst1,
+                                                             uint32_t Wb, uint32_t L, size_t line_stride, size_t outer_stride)
 {
-	extern __shared__ __align__(16) uint8_t T[];        // nlev levels of L x TW bytes, then the F and B lines (2 x L x TW)
-	const int      nthreads = blockDim.x;
-	const int      TW4 = TW >> 2;                       // words per row
-	const uint32_t x0  = blockIdx.x * TW;
+	extern __shared__ __align__(16) uint8_t T[];        // the staged tile (L x 32), then the two walkers' value tables (2 x 256 x 32)
+	constexpr int  TW = kWalkTW, TW4 = TW >> 2;         // words per row
+	const uint32_t x0   = blockIdx.x * TW;
 	const size_t   base = (size_t) blockIdx.y * outer_stride + x0;
-	const size_t   lst  = (size_t) L * TW;
-	uint8_t       *Fl = T + (size_t) nlev * lst, *Bl = Fl + lst;
-	// stage: word w of row p = columns 4w .. 4w+3
-	const int nwords = (int) L * TW4;
-	for (int i = threadIdx.x; i < nwords; i += nthreads) {
-		const int p = i / TW4, w = i - p * TW4;
-		unsigned  v = 0xffffffffu;
-		if (x0 + 4u * w < Wb) {
-			v = __ldg(reinterpret_cast<const unsigned *>(src + base + (size_t) p * line_stride) + w);
-			if (src2) v = __vminu4(v, __ldg(reinterpret_cast<const unsigned *>(src2 + base + (size_t) p * line_stride) + w));
-		}
-		reinterpret_cast<unsigned *>(T)[i] = v;
-	}
-	__syncthreads();
-	for (int k = 1; k < nlev; ++k) {
-		const unsigned *prev = reinterpret_cast<const unsigned *>(T + (size_t) (k - 1) * lst);
-		unsigned       *cur  = reinterpret_cast<unsigned *>(T + (size_t) k * lst);
-		const int       half = (1 << (k - 1)) * TW4;        // in words
-		for (int i = threadIdx.x; i < nwords; i += nthreads) {
-			const unsigned a = prev[i];
-			const unsigned b = i + half < nwords ? prev[i + half] : 0xffffffffu;
-			cur[i] = __vminu4(a, b);
-		}
-		__syncthreads();
-	}
+	const int      nwords = (int) L * TW4;
+	uint8_t       *tables = T + (((size_t) L * TW + 15) & ~(size_t) 15);
+	// stage: word w of row p = columns 4w .. 4w+3; four requests in flight per thread
 	{
-		const int Li = (int) L, nseg = (Li + kWalkSeg - 1) / kWalkSeg;
-		const int nwalk = 2 * nseg * TW;        // walker id = (direction * nseg + segment) * TW + column
-		for (int wk = threadIdx.x; wk < nwalk; wk += nthreads) {
-			const int col = wk % TW, sd = wk / TW, seg = sd % nseg;
-			const int z_lo = seg * kWalkSeg, z_hi = min(z_lo + kWalkSeg, Li) - 1;        // inclusive
-			if (sd < nseg) {        // F: towards +z, walking down from the segment's last cell
-				unsigned r = T[z_hi * TW + col];
-				if (z_hi != Li - 1) r = walk_head<1>(T, Li, TW, lst, z_hi, col, r);
-				Fl[z_hi * TW + col] = (uint8_t) r;
-				for (int z = z_hi - 1; z >= z_lo; --z) {
-					const unsigned hz = T[z * TW + col];
-					unsigned cand = min(r + 1u, 255u);
-					if (r > 0u && hz > r) {        // h(z) <= r decides F(z) = h(z) whatever the window holds
-						const int a = z + 1, b = min(z + (int) r, Li - 1);
-						const int k = 31 - __clz(b - a + 1);
-						const uint8_t *Tk = T + (size_t) k * lst;
-						const unsigned w  = min((unsigned) Tk[a * TW + col], (unsigned) Tk[(b - (1 << k) + 1) * TW + col]);
-						if (w <= r) cand = r;
-					}
-					r = min(hz, cand);
-					Fl[z * TW + col] = (uint8_t) r;
+		const int  w  = threadIdx.x % TW4;
+		const bool in = x0 + 4u * w < Wb;
+		for (int p0 = threadIdx.x / TW4; p0 < (int) L; p0 += 4 * (THREADS / TW4)) {
+			unsigned v[4];
+#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				const int p = p0 + j * (THREADS / TW4);
+				v[j]        = 0xffffffffu;
+				if (in && p < (int) L) v[j] = __ldg(reinterpret_cast<const unsigned *>(src + base + (size_t) p * line_stride) + w);
+			}
+			if (src2) {
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					const int p = p0 + j * (THREADS / TW4);
+					if (in && p < (int) L) v[j] = __vminu4(v[j], __ldg(reinterpret_cast<const unsigned *>(src2 + base + (size_t) p * line_stride) + w));
 				}
-			} else {                // B: towards -z, walking up from the segment's first cell
-				unsigned r = T[z_lo * TW + col];
-				if (z_lo != 0) r = walk_head<-1>(T, Li, TW, lst, z_lo, col, r);
-				Bl[z_lo * TW + col] = (uint8_t) r;
-				for (int z = z_lo + 1; z <= z_hi; ++z) {
-					const unsigned hz = T[z * TW + col];
-					unsigned cand = min(r + 1u, 255u);
-					if (r > 0u && hz > r) {
-						const int b = z - 1, a = max(z - (int) r, 0);
-						const int k = 31 - __clz(b - a + 1);
-						const uint8_t *Tk = T + (size_t) k * lst;
-						const unsigned w  = min((unsigned) Tk[a * TW + col], (unsigned) Tk[(b - (1 << k) + 1) * TW + col]);
-						if (w <= r) cand = r;
-					}
-					r = min(hz, cand);
-					Bl[z * TW + col] = (uint8_t) r;
-				}
+			}
+#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				const int p = p0 + j * (THREADS / TW4);
+				if (p < (int) L) reinterpret_cast<unsigned *>(T)[p * TW4 + w] = v[j];
 			}
 		}
 	}
 	__syncthreads();
-	for (int i = threadIdx.x; i < nwords; i += nthreads) {
-		const int p = i / TW4, w = i - p * TW4;
-		if (x0 + 4u * w >= Wb) continue;
-		const unsigned f = reinterpret_cast<const unsigned *>(Fl)[i], b = reinterpret_cast<const unsigned *>(Bl)[i];
-		const size_t   o = base + (size_t) p * line_stride;
-		if (MODE == 0) reinterpret_cast<unsigned *>(dst0 + o)[w] = __vminu4(f, b);
-		else {
-			reinterpret_cast<unsigned *>(dst0 + o)[w] = f;
-			reinterpret_cast<unsigned *>(dst1 + o)[w] = b;
-		}
+	const int  lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const bool live = x0 + lane < Wb;
+	if (MODE == 0) {
+		// both walkers store into dst0 and fold as they go
+		if (warp == 0) walk_line<1, true>(T + lane, tables + lane, dst0 + base + lane, line_stride, (int) L, live);
+		else if (warp == 1) walk_line<-1, true>(T + lane, tables + 256 * TW + lane, dst0 + base + lane, line_stride, (int) L, live);
+	} else {
+		if (warp == 0) walk_line<1, false>(T + lane, tables + lane, dst0 + base + lane, line_stride, (int) L, live);
+		else if (warp == 1) walk_line<-1, false>(T + lane, tables + 256 * TW + lane, dst1 + base + lane, line_stride, (int) L, live);
 	}
 }
 
@@ -635,11 +675,24 @@ static int run_xpass(const vkv_volume *vol, const uint8_t *O, uint8_t *out, cuda
 	if (Wb <= kRowWordsMax * 32) {
 		const int grid = (int) std::min<uint64_t>((nrows + 7) / 8, (uint64_t) vol->ctx->sm_count * 8);
 		if (Wb % 4 == 0) {
-			const uint32_t nseg = (Wb + 127) / 128;
-			if (nseg <= 2) xpass_vec4_kernel<DIR, 2><<<grid, 256, 0, s>>>(O, out, Wb, nrows);
-			else if (nseg <= 4) xpass_vec4_kernel<DIR, 4><<<grid, 256, 0, s>>>(O, out, Wb, nrows);
-			else if (nseg <= 8) xpass_vec4_kernel<DIR, 8><<<grid, 256, 0, s>>>(O, out, Wb, nrows);
-			else xpass_vec4_kernel<DIR, 16><<<grid, 256, 0, s>>>(O, out, Wb, nrows);
+			// cells per lane: as many as keep most of a warp busy on one row
+#define VKV_XP(CPL, SEGS) xpass_lanes_kernel<DIR, CPL, SEGS><<<grid, 256, 0, s>>>(O, out, Wb, nrows)
+			if (Wb % 16 == 0 && Wb >= 384) {
+				const uint32_t nseg = (Wb + 511) / 512;
+				if (nseg <= 1) VKV_XP(16, 1);
+				else if (nseg <= 2) VKV_XP(16, 2);
+				else VKV_XP(16, 4);
+			} else if (Wb % 8 == 0 && Wb >= 160) {
+				const uint32_t nseg = (Wb + 255) / 256;
+				if (nseg <= 1) VKV_XP(8, 1);
+				else if (nseg <= 2) VKV_XP(8, 2);
+				else VKV_XP(8, 8);
+			} else {
+				const uint32_t nseg = (Wb + 127) / 128;
+				if (nseg <= 2) VKV_XP(4, 2);
+				else VKV_XP(4, 16);
+			}
+#undef VKV_XP
 		}
 		else xpass_ballot_kernel<DIR><<<grid, 256, 0, s>>>(O, out, Wb, nrows);
 	} else {
@@ -695,17 +748,15 @@ static int run_ysweep(const vkv_volume *vol, const uint8_t *g, uint8_t *dst0, ui
 		g += off; dst0 += off;
 		if (dst1) dst1 += off;
 	}
-	// four cells per thread; bulk copies need 16-byte aligned row blocks (slice size, hence every block start and length)
-	if (Wb > 1024u || Wb % 4 != 0 || ((size_t) Wb * Hb) % 16 != 0 || ((size_t) kSweepRows * Wb) % 16 != 0 || (reinterpret_cast<uintptr_t>(g) % 16) != 0 ||
-	    (reinterpret_cast<uintptr_t>(dst0) % 16) != 0 || (dst1 && (reinterpret_cast<uintptr_t>(dst1) % 16) != 0))
-		return VKV_OK;        // otherwise the search kernel
-	const int    threads = (int) ((Wb / 4 + 31u) / 32u * 32u);
-	const size_t smem    = (size_t) kSweepSlots * kSweepRows * Wb + 2 * ((size_t) Wb / 4 + 2) * sizeof(uint2) + 16;
-	static PerDeviceOnce configured;
-	if (configured.first(vol->ctx->device)) {
-		VKV_CUDA_CHECK(cudaFuncSetAttribute(ysweep_kernel<XDIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-	}
-	ysweep_kernel<XDIR><<<split ? 2 * Db : Db, threads, smem, s>>>(g, dst0, dst1, Wb, Hb, split ? 1 : 0);
+	// 32-bit words of four cells; up to 16 strips (512 threads) per slice.  (Four cells per lane — twice the warps, half the work per
+	// warp and row — was measured on the 208x208x124 map, where a slice is one strip and most SMs hold a single warp: no gain,
+	// 37.2 vs 38.9 us; the row step is a latency chain either way.)
+	if (Wb % 4 != 0) return VKV_OK;        // otherwise the search kernel
+	const uint32_t ctas    = split ? 2 * Db : Db;
+	const int      nstrips = Wb <= 256u ? 1 : (int) ((Wb + (256 - 2 * kStripHalo) - 1) / (256 - 2 * kStripHalo));
+	if (nstrips > 16) return VKV_OK;
+	const size_t smem = 2 * ((size_t) Wb / 2 + 8) * sizeof(unsigned);
+	ysweep_kernel<XDIR, 8><<<ctas, 32 * nstrips, smem, s>>>(g, dst0, dst1, Wb, Hb, split ? 1 : 0, nstrips);
 	VKV_LAUNCHED();
 	*done = true;
 	return VKV_OK;
@@ -728,25 +779,16 @@ static int run_zwalk(const vkv_volume *vol, const uint8_t *src, uint8_t *dst0, u
 		if (src2) src2 += off;
 	}
 	if (Wb % 4 != 0 || Hb > 65535u) return VKV_OK;        // 32-bit column groups; otherwise the search kernel
-	const uint32_t max_window = std::min<uint32_t>(255u, L);
-	int            nlev       = 1;
-	while ((2u << (nlev - 1)) <= max_window) ++nlev;
-	// 32 columns per CTA (a warp of walkers reads 32 consecutive bytes of a table row) unless the tables then exceed what
-	// lets a few CTAs share an SM; narrower tiles for long lines
-	const size_t per_col = (size_t) (nlev + 2) * L;
-	int          TW      = 32;
-	while (TW > 8 && per_col * TW > (size_t) 100 * 1024) TW >>= 1;
-	if (per_col * TW <= (size_t) 50 * 1024 && Wb >= 64 && L >= 4u * kWalkSeg) TW = 64;
-	const size_t smem = per_col * TW;
+	const size_t smem = (((size_t) L * kWalkTW + 15) & ~(size_t) 15) + 2 * 256 * kWalkTW;
 	if (smem > (size_t) 200 * 1024) return VKV_OK;
 	static PerDeviceOnce configured;
 	if (configured.first(vol->ctx->device)) {
-		VKV_CUDA_CHECK(cudaFuncSetAttribute(zwalk_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+		VKV_CUDA_CHECK(cudaFuncSetAttribute(zwalk_kernel<MODE, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+		VKV_CUDA_CHECK(cudaFuncSetAttribute(zwalk_kernel<MODE, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 	}
-	const int  nseg    = (int) ((L + kWalkSeg - 1) / kWalkSeg);
-	const int  threads = std::min(1024, std::max(64, (2 * nseg * TW + 31) / 32 * 32));
-	const dim3 grid((Wb + TW - 1) / TW, rows);
-	zwalk_kernel<MODE><<<grid, threads, smem, s>>>(src, src2, dst0, dst1, Wb, L, (size_t) Wb * Hb, (size_t) Wb, TW, nlev);
+	const dim3 grid((Wb + kWalkTW - 1) / kWalkTW, rows);
+	if (smem * 8 > (size_t) 220 * 1024) zwalk_kernel<MODE, 256><<<grid, 256, smem, s>>>(src, src2, dst0, dst1, Wb, L, (size_t) Wb * Hb, (size_t) Wb);
+	else zwalk_kernel<MODE, 64><<<grid, 64, smem, s>>>(src, src2, dst0, dst1, Wb, L, (size_t) Wb * Hb, (size_t) Wb);
 	VKV_LAUNCHED();
 	*done = true;
 	return VKV_OK;
@@ -831,7 +873,7 @@ int launch_distance(vkv_volume *vol, int skipping_type, cudaStream_t s)
 bool distance_shardable(const vkv_volume *vol)
 {
 	const uint32_t Wb = vol->dim_b[0], Hb = vol->dim_b[1];
-	return Wb <= 1024u && Wb % 4 == 0 && ((size_t) Wb * Hb) % 16 == 0 && ((size_t) kSweepRows * Wb) % 16 == 0 && Hb <= 65535u && Wb <= kRowWordsMax * 32u &&
+	return Wb % 4 == 0 && Wb <= (uint32_t) (256 - 2 * kStripHalo) * 16u && Hb <= 65535u && Wb <= kRowWordsMax * 32u && (size_t) vol->dim_b[2] * kWalkTW + 2 * 256 * kWalkTW + 16 <= (size_t) 200 * 1024 &&
 	       !getenv("VKV_DIST_SEARCH");
 }
 
