@@ -706,7 +706,9 @@ def run_native(args):
             "distance_samples_per_frame": n_dist / K / slots, "covered_pixels_per_frame": n_cov / K / slots,
             "mpixels_per_s": slots * FW * FH / (ms_per_step * 1e-3) / 1e6,
             "ess_rebuild_ms": {"median": float(np.median(rebuild_ms)), "mean": float(np.mean(rebuild_ms)), "p95": float(np.percentile(rebuild_ms, 95)),
-                               "changes": n_changes, "stages": stage_ms, "sharded_z_slabs": world > 1},
+                               "changes": n_changes, "stages": stage_ms,
+                               # the library shards volumes of 512 Mi voxels and more; smaller ones are rebuilt on every replica, with no communication
+                               "sharded_z_slabs": world > 1 and int(np.prod(wl["dim"])) >= (512 << 20)},
             "occupied_voxels": occupied, "occupied_percent": 100.0 * occupied / N_vox,
             "modes": modes, "tiles_match_single_gpu_frame": tiles_match, "sharded_rebuild_matches": sharded_rebuild_matches,
             "tiles_8k": tiles_8k, "tf_sweep": tf_sweep, "e2e": e2e, "gpu_launches": int(launches), "wall_s_timed_region": wall,

@@ -366,7 +366,9 @@ VKV_API int vkv_volume_mark_occupancy_present(vkv_volume *vol, int skipping_type
  * trip, no collective library on the data path.  Set-up: every rank calls vkv_volume_group_export, the application hands
  * all ranks' handle blobs to every rank (any transport: MPI, torch.distributed, a file), every rank calls
  * vkv_volume_group_open with the blobs in rank order.  All ranks must then make the same sequence of sharded calls
- * (it is a collective).  At most 8 ranks. */
+ * (it is a collective).  At most 8 ranks.  Volumes below 512 Mi voxels are rebuilt by every rank on its own replica instead
+ * (same results, no communication: the barriers and exchanges would cost more than a second GPU saves; VKV_GROUP_ALWAYS=1
+ * in the environment forces the sharded path). */
 #define VKV_GROUP_HANDLE_BYTES (3 * 72)
 VKV_API int vkv_volume_group_export(vkv_volume *vol, uint8_t handles_out[VKV_GROUP_HANDLE_BYTES]);
 VKV_API int vkv_volume_group_open(vkv_volume *vol, int rank, int world, const uint8_t *all_handles);

@@ -26,6 +26,7 @@ from vkvolume_b200 import capi, scene, sharding
 from vkvolume_b200.capi import RenderOptions, VolumeOptions
 
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+os.environ["VKV_GROUP_ALWAYS"] = "1"        # the library rebuilds volumes this small on every replica; the sharded path is what is under test
 torch.cuda.set_device(lr)
 dev = torch.device("cuda", lr)
 dist.init_process_group("nccl", device_id=dev)

@@ -180,8 +180,8 @@ int launch_occupancy(vkv_volume *vol, const vkv_transfer_function_uniform *tfu, 
                      unsigned long long *count_dev, cudaStream_t s);
 int launch_distance(vkv_volume *vol, int skipping_type, cudaStream_t s);
 bool distance_shardable(const vkv_volume *vol);
-int launch_distance_xy_slab(vkv_volume *vol, uint32_t zb_first, uint32_t zb_count, cudaStream_t s);
-int launch_distance_z_rows(vkv_volume *vol, uint32_t yb_first, uint32_t yb_count, cudaStream_t s);
+int launch_distance_xy_slab(vkv_volume *vol, uint32_t zb_first, uint32_t zb_count, bool split, cudaStream_t s);
+int launch_distance_z_rows(vkv_volume *vol, uint32_t yb_first, uint32_t yb_count, bool split, cudaStream_t s);
 int launch_normalise(const void *raw_dev, size_t n, int kind, bool big_endian, float lo, float hi, uint8_t *out,
                      cudaStream_t s);
 int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_cast_uniform *ray,

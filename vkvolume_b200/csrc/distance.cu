@@ -877,13 +877,16 @@ bool distance_shardable(const vkv_volume *vol)
 	       !getenv("VKV_DIST_SEARCH");
 }
 
-int launch_distance_xy_slab(vkv_volume *vol, uint32_t zb_first, uint32_t zb_count, cudaStream_t s)
+// `split`: the two y sweeps of a slice as two CTAs (half the serial chain — with a slab's few slices the sweep is nothing but that
+// chain): sources above -> d_swap, sources below -> map 0 (its occupancy was consumed by the x pass); the z pass then takes the
+// minimum of the two while it stages, and both slabs are exchanged.
+int launch_distance_xy_slab(vkv_volume *vol, uint32_t zb_first, uint32_t zb_count, bool split, cudaStream_t s)
 {
 	int  rc;
 	bool done = false;
 	if (zb_count == 0) return VKV_OK;
 	if ((rc = run_xpass<0>(vol, vol->d_maps[0], vol->d_tmp, s, zb_first, zb_count))) return rc;
-	if ((rc = run_ysweep<0>(vol, vol->d_tmp, vol->d_swap, nullptr, s, &done, zb_first, zb_count))) return rc;
+	if ((rc = run_ysweep<0>(vol, vol->d_tmp, vol->d_swap, split ? vol->d_maps[0] : nullptr, s, &done, zb_first, zb_count, split))) return rc;
 	if (!done) {
 		set_error("launch_distance_xy_slab: shape not covered by the sweep kernel");
 		return VKV_ERR_STATE;
@@ -891,11 +894,11 @@ int launch_distance_xy_slab(vkv_volume *vol, uint32_t zb_first, uint32_t zb_coun
 	return VKV_OK;
 }
 
-int launch_distance_z_rows(vkv_volume *vol, uint32_t yb_first, uint32_t yb_count, cudaStream_t s)
+int launch_distance_z_rows(vkv_volume *vol, uint32_t yb_first, uint32_t yb_count, bool split, cudaStream_t s)
 {
 	int  rc;
 	bool done = false;
-	if ((rc = run_zwalk<0>(vol, vol->d_swap, vol->d_maps[0], nullptr, s, &done, yb_first, yb_count))) return rc;
+	if ((rc = run_zwalk<0>(vol, vol->d_swap, vol->d_maps[0], nullptr, s, &done, yb_first, yb_count, split ? vol->d_maps[0] : nullptr))) return rc;
 	if (!done) {
 		set_error("launch_distance_z_rows: shape not covered by the walk kernel");
 		return VKV_ERR_STATE;

@@ -6,7 +6,8 @@
 //   1. K2a (+K2b) on its z-slab of blocks                                     -> rows of map 0, partial voxel count;
 //   2. isotropic distance map: K3 x and y passes on that slab (they never look outside a z slice)
 //                                                                             -> xy-intermediate slab in d_swap;
-//      slab pushed into every peer's d_swap (peer copies over NVLink), partial count into every peer's signal block;
+//      each block row of the slab pushed into the d_swap of the peer whose z pass needs it (remote stores over NVLink: 1/n of the
+//      slab per peer), partial count into every peer's signal block;
 //   3. barrier — all slabs have landed;
 //   4. K3 z pass on its share of the block ROWS (a z line needs every slab, nothing else)   -> rows of map 0;
 //      rows pushed into every peer's map 0;
@@ -92,6 +93,25 @@ static int group_push(vkv_volume *vol, uint8_t *const *dsts_dev, const uint8_t *
 	else group_push_kernel<uint8_t><<<grid, 256, 0, s>>>(dsts_dev, src, first, chunk_bytes, n_chunks, chunk_stride, vol->grp_rank, vol->grp_world);
 	VKV_LAUNCHED();
 	return VKV_OK;
+}
+
+// The first exchange of the sharded distance build only has to feed the z pass: the peer that transforms block rows [y0, y0 + yc)
+// needs those rows of this rank's slab and nothing else — 1/world of what a broadcast of the slab moves.  One warp per (slice, row):
+// the row goes to the one peer that owns it (rows are dealt out `rows_per` at a time, like split()).
+__global__ void __launch_bounds__(256) group_scatter_rows_kernel(uint8_t *const *__restrict__ dsts, const uint8_t *__restrict__ src, uint32_t z0, uint32_t zc,
+                                                                uint32_t Wb, uint32_t Hb, uint32_t rows_per, int rank)
+{
+	const int      lane = threadIdx.x & 31;
+	const uint64_t nrow = (uint64_t) zc * Hb;
+	for (uint64_t r = (uint64_t) blockIdx.x * 8 + (threadIdx.x >> 5); r < nrow; r += (uint64_t) gridDim.x * 8) {
+		const uint32_t z = z0 + (uint32_t) (r / Hb), y = (uint32_t) (r % Hb);
+		const int      p = (int) (y / rows_per);
+		if (p == rank) continue;
+		const size_t off = ((size_t) z * Hb + y) * Wb;
+		const uint4 *sp  = reinterpret_cast<const uint4 *>(src + off);
+		uint4       *dp  = reinterpret_cast<uint4 *>(dsts[p] + off);
+		for (uint32_t i = lane; i < Wb / 16; i += 32) dp[i] = sp[i];
+	}
 }
 
 static int group_barrier(vkv_volume *vol, const unsigned long long *count_dev, cudaStream_t s)
@@ -195,6 +215,10 @@ int vkv_update_transfer_function_sharded(vkv_volume *vol, const vkv_volume_optio
 	split(Hb, rank, world, &y0, &yc);
 	const int  n_maps  = skipping_type == VKV_SKIP_ANISOTROPIC_DISTANCE ? 8 : 1;
 	const bool sharded = skipping_type == VKV_SKIP_DISTANCE && distance_shardable(vol);
+	// Small volumes are not worth the three barriers and two exchanges (~60 us against the ~40 us of occupancy pass a second GPU
+	// saves on 342 M voxels): every rank then rebuilds its replica on its own, with no communication at all.
+	const uint64_t n_voxels = (uint64_t) vol->dim[0] * vol->dim[1] * vol->dim[2];
+	if (world == 1 || (n_voxels < (512ull << 20) && !getenv("VKV_GROUP_ALWAYS"))) return vkv_update_transfer_function(vol, opt, skipping_type, count_out, stream);
 	// 0. nobody is still reading the old maps
 	if ((rc = group_barrier(vol, nullptr, s))) return rc;
 	// 1. TF texture + masks (replicated, a few microseconds), occupancy (+ count) of the own slab into map n-1
@@ -205,12 +229,28 @@ int vkv_update_transfer_function_sharded(vkv_volume *vol, const vkv_volume_optio
 	if ((rc = vkv_compute_occupancy_slab(vol, &u, skipping_type, z0, zc, count_out ? (uint64_t *) vol->d_count : nullptr, stream))) return rc;
 	uint8_t *const occ_map = vol->d_maps[n_maps - 1];
 	if (sharded) {
-		// 2. x + y passes on the slab, xy-intermediate slab to every peer
-		if ((rc = launch_distance_xy_slab(vol, z0, zc, s))) return rc;
-		if ((rc = group_push(vol, vol->d_grp_ptrs + kGroupMax, vol->d_swap, z0 * plane, zc * plane, 1, 0, s))) return rc;
+		// 2. x + y passes on the slab; its block rows to the peers whose z pass needs them.  Few slices per rank make the y sweep a
+		// pure latency chain: its two directions then run side by side into two maps (d_swap and map 0), both exchanged.
+		const bool ysplit = world > 1 && (size_t) zc * plane <= ((size_t) 12 << 20) && !getenv("VKV_DIST_NOSPLIT");        // (33 MB slabs: measured slower)
+		if ((rc = launch_distance_xy_slab(vol, z0, zc, ysplit, s))) return rc;
+		if (Wb % 16 == 0 && reinterpret_cast<uintptr_t>(vol->d_swap) % 16 == 0 && reinterpret_cast<uintptr_t>(vol->d_maps[0]) % 16 == 0 && !getenv("VKV_GROUP_BROADCAST")) {
+			if (zc) {
+				const uint32_t rows_per = (Hb + (uint32_t) world - 1u) / (uint32_t) world;        // as split()
+				const int      grid     = (int) std::min<uint64_t>(((uint64_t) zc * Hb + 7) / 8, (uint64_t) vol->ctx->sm_count * 8);
+				group_scatter_rows_kernel<<<grid, 256, 0, s>>>(vol->d_grp_ptrs + kGroupMax, vol->d_swap, z0, zc, Wb, Hb, rows_per, rank);
+				VKV_LAUNCHED();
+				if (ysplit) {
+					group_scatter_rows_kernel<<<grid, 256, 0, s>>>(vol->d_grp_ptrs, vol->d_maps[0], z0, zc, Wb, Hb, rows_per, rank);
+					VKV_LAUNCHED();
+				}
+			}
+		} else {
+			if ((rc = group_push(vol, vol->d_grp_ptrs + kGroupMax, vol->d_swap, z0 * plane, zc * plane, 1, 0, s))) return rc;
+			if (ysplit && (rc = group_push(vol, vol->d_grp_ptrs, vol->d_maps[0], z0 * plane, zc * plane, 1, 0, s))) return rc;
+		}
 		if ((rc = group_barrier(vol, count_out ? vol->d_count : nullptr, s))) return rc;
 		// 4. z pass on the own block rows, result rows to every peer
-		if ((rc = launch_distance_z_rows(vol, y0, yc, s))) return rc;
+		if ((rc = launch_distance_z_rows(vol, y0, yc, ysplit, s))) return rc;
 		if ((rc = group_push(vol, vol->d_grp_ptrs, vol->d_maps[0], (size_t) y0 * Wb, (size_t) yc * Wb, Db, plane, s))) return rc;
 		if ((rc = group_barrier(vol, nullptr, s))) return rc;
 		vol->occupancy_in_map = -1;
