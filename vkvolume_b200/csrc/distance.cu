@@ -519,6 +519,157 @@ __global__ void __launch_bounds__(512) ysweep_kernel(const uint8_t *__restrict__
 	}
 }
 
+// ---- y sweep, one CTA per slice (narrow maps) ------------------------------------------------------------------------------
+// Round 1's formulation of the same recurrence, kept for maps a single strip wide with too few slices to fill the machine (the
+// 208x208x124 map of config 2: 248 sweeps): there a sweep is a pure latency chain, and a lone warp walking a 256-cell strip issues
+// ~95 ALU-pipe instructions per row at one per ~4 cycles (385 cycles per row measured, with or without its loads, stores and
+// shuffles), while a CTA with four cells per thread, the previous row in shared memory and one barrier per row takes ~220.
+__device__ __forceinline__ uint32_t d_smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void d_mbar_init(uint64_t *bar, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(d_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void d_mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(d_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void d_mbar_wait(uint64_t *bar, unsigned parity)
+{
+	unsigned           ok, spins = 0;
+	unsigned long long t0 = 0ull;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(ok)
+		             : "r"(d_smem_u32(bar)), "r"(parity)
+		             : "memory");
+		// a lost arrival must surface as an error, never as a hung GPU — but only after 20 s of WALL time (%globaltimer), so that
+		// time-slicing, a debugger, compute-sanitizer or first-touch page migration cannot trip it (a spin count could)
+		if (!ok && (++spins & 1023u) == 0u) {
+			unsigned long long now;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+			if (t0 == 0ull) t0 = now;
+			else if (now - t0 > 20000000000ull) __trap();
+		}
+	} while (!ok);
+}
+__device__ __forceinline__ void d_tma_load_1d(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d_smem_u32(smem_dst)),
+	             "l"(gmem_src), "r"(bytes), "r"(d_smem_u32(bar))
+	             : "memory");
+}
+
+// The input rows arrive by 1-D bulk TMA copies, kSweepRows rows (one contiguous block of the slice) per copy, through a
+// ring of kSweepSlots buffers with one mbarrier each: the serial row recurrence never waits on a global load.
+// A thread owns FOUR adjacent cells.  The previous row lives in shared memory as 16-bit lanes (two u16x2 words per
+// thread), so the whole row step is a handful of native packed instructions with a short dependency chain — the step
+// latency, not the instruction count, is what bounds a sweep of Hb dependent rows:
+//     neighbours x +- 1 : 16-bit funnel shifts against the adjacent words
+//     min of the three  : VIMNMX3.U16x2
+//     min(g, m + 1)     : VIADDMNMX.U16x2     (m <= 255, so m + 1 needs no saturation; the result is <= g <= 255)
+// and a 1024-cell row is 8 warps instead of 32 — the per-row barrier is cheaper and several slices share an SM.
+constexpr int kSweepRows  = 8;
+constexpr int kSweepSlots = 6;
+// `split` (isotropic, small maps): the two sweeps of a slice are independent when both start from g — the result is then
+// min(up, down), which the z pass takes while it stages — so they run as two CTAs (blockIdx.x = 2 slice + sweep) and the serial
+// chain of a slice is Hb row steps instead of 2 Hb; costs one more map of traffic, so only where the maps live in the L2.
+template <int XDIR>        // XDIR 0: isotropic (two-sided x, 3 neighbours, in-place second sweep); +-1: one-sided
+__global__ void __launch_bounds__(256) ysweep_ring_kernel(const uint8_t *__restrict__ g, uint8_t *__restrict__ dst0, uint8_t *__restrict__ dst1,
+                                                     uint32_t Wb, uint32_t Hb, int split)
+{
+	extern __shared__ __align__(128) uint8_t s_dyn[];        // kSweepSlots chunks of kSweepRows x Wb | 2 row buffers of Wb/4 + 2 uint2
+	__shared__ __align__(8) uint64_t s_bar[kSweepSlots];
+	const uint32_t t      = threadIdx.x;                     // group of 4 cells of the row
+	const uint32_t W4     = Wb >> 2;
+	const bool     active = t < W4;
+	const size_t   slice  = (size_t) (split ? blockIdx.x >> 1 : blockIdx.x) * Wb * Hb;
+	const uint32_t chunk_bytes = kSweepRows * Wb;
+	uint8_t       *ring = s_dyn;
+	uint2         *buf0 = reinterpret_cast<uint2 *>(s_dyn + (size_t) kSweepSlots * chunk_bytes) + 1, *buf1 = buf0 + (W4 + 2);
+	const uint32_t nchunks = (Hb + kSweepRows - 1) / kSweepRows;
+	constexpr unsigned kFar = 0x00ff00ffu;        // 255 in both lanes
+	if (t == 0) {
+		for (int i = 0; i < kSweepSlots; ++i) d_mbar_init(&s_bar[i], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	unsigned issued = 0;        // copies issued so far (thread 0): copy n lands in ring slot n % kSweepSlots, phase (n / kSweepSlots) & 1
+	for (int sweep = split ? (int) (blockIdx.x & 1u) : 0; sweep < 2; ++sweep) {
+		// sweep 0 walks y upwards (sources at y' <= y), sweep 1 downwards (sources at y' >= y)
+		const uint8_t  *src  = (XDIR == 0 && sweep == 1 && !split) ? dst0 : g;
+		uint8_t        *dst  = (XDIR == 0 && !split) ? dst0 : (sweep == 0 ? dst1 : dst0);
+		const ptrdiff_t step = sweep == 0 ? (ptrdiff_t) W4 : -(ptrdiff_t) W4;        // in words
+		unsigned       *dp   = reinterpret_cast<unsigned *>(dst + slice + (sweep == 0 ? 0 : (size_t) (Hb - 1) * Wb)) + t;
+		// chunk c of this sweep = rows [lo, lo + n) of the slice, consumed upwards (sweep 0) or downwards (sweep 1)
+		auto issue = [&](uint32_t c) {
+			const uint32_t i0 = c * kSweepRows, n = min((uint32_t) kSweepRows, Hb - i0);
+			const uint32_t lo = sweep == 0 ? i0 : Hb - i0 - n;
+			const unsigned slot = issued % kSweepSlots;
+			d_mbar_expect_tx(&s_bar[slot], n * Wb);
+			d_tma_load_1d(ring + (size_t) slot * chunk_bytes, src + slice + (size_t) lo * Wb, n * Wb, &s_bar[slot]);
+			++issued;
+		};
+		if (XDIR == 0 && sweep == 1 && !split) {
+			// the second sweep re-reads what this CTA just wrote with ordinary stores: order them before the async-proxy reads
+			__threadfence();
+			asm volatile("fence.proxy.async;" ::: "memory");
+		}
+		if (t == 0) {
+			buf0[-1] = make_uint2(kFar, kFar); buf1[-1] = make_uint2(kFar, kFar);
+			buf0[W4] = make_uint2(kFar, kFar); buf1[W4] = make_uint2(kFar, kFar);
+		}
+		if (active) buf0[t] = make_uint2(kFar, kFar);        // "row -1": nothing behind the first row
+		__syncthreads();
+		const unsigned consumed = issued;       // uniform bookkeeping of the copy sequence number (every thread tracks it)
+		if (t == 0)
+			for (uint32_t c = 0; c < (uint32_t) kSweepSlots && c < nchunks; ++c) issue(c);
+		for (uint32_t c = 0; c < nchunks; ++c) {
+			const unsigned seq = consumed + c, slot = seq % kSweepSlots;
+			d_mbar_wait(&s_bar[slot], (seq / kSweepSlots) & 1u);
+			const uint32_t  n  = min((uint32_t) kSweepRows, Hb - c * kSweepRows);
+			const unsigned *cb = reinterpret_cast<const unsigned *>(ring + (size_t) slot * chunk_bytes);
+			// rows alternate between the two row buffers; a chunk has an even number of rows unless it is the last one, so the
+			// buffer roles are compile-time constants of the 2-row unrolled loop
+			const unsigned *cp = cb + (sweep == 0 ? 0 : (size_t) (n - 1) * W4) + t;        // this thread's word in the chunk's first row
+			auto row_step = [&](const uint2 *prev, uint2 *now) {
+				if (active) {
+					const unsigned gw = *cp;
+					const uint2    p  = prev[t];                       // cells 0,1 | 2,3 of this thread in the previous row
+					const unsigned mid = __funnelshift_r(p.x, p.y, 16);        // cells 1,2
+					unsigned       ma = p.x, mb = p.y;
+					if (XDIR == 0) {
+						ma = __vimin3_u16x2(p.x, __funnelshift_l(prev[(int) t - 1].y, p.x, 16), mid);        // cells -1,0 and 1,2
+						mb = __vimin3_u16x2(p.y, mid, __funnelshift_r(p.y, prev[t + 1].x, 16));              // cells 1,2 and 3,4
+					} else if (XDIR > 0) {
+						ma = __vminu2(p.x, mid);
+						mb = __vminu2(p.y, __funnelshift_r(p.y, prev[t + 1].x, 16));
+					} else {
+						ma = __vminu2(p.x, __funnelshift_l(prev[(int) t - 1].y, p.x, 16));
+						mb = __vminu2(p.y, mid);
+					}
+					const unsigned va = __viaddmin_u16x2(ma, 0x00010001u, d_prmt(gw, 0u, 0x4140u));
+					const unsigned vb = __viaddmin_u16x2(mb, 0x00010001u, d_prmt(gw, 0u, 0x4342u));
+					now[t] = make_uint2(va, vb);
+					*dp    = d_prmt(va, vb, 0x6420u);
+					dp += step;
+					cp += step;
+				}
+				__syncthreads();
+			};
+			uint32_t k = 0;
+			for (; k + 2 <= n; k += 2) {
+				row_step(buf0, buf1);
+				row_step(buf1, buf0);
+			}
+			if (k < n) row_step(buf0, buf1);        // odd tail: only ever in the last chunk of a sweep
+			// every thread is past the chunk: its ring slot may be refilled
+			if (t == 0 && c + kSweepSlots < nchunks) issue(c + kSweepSlots);
+		}
+		issued = consumed + nchunks;        // keep every thread's view of the sequence number in step with thread 0's
+		if (split) break;                   // one sweep per CTA
+	}
+}
+
 // ---- z pass as a walk along the line --------------------------------------------------------------------------
 // One-sided result towards +z: F(z) = min_{j >= z} max(j - z, h(j)).  Stepping from z + 1 to z every candidate's cost
 // grows by at most one, so with r = F(z + 1):   F(z) = min( h(z), r      if some j in [z+1, z+r] has h(j) <= r
@@ -753,6 +904,25 @@ static int run_ysweep(const vkv_volume *vol, const uint8_t *g, uint8_t *dst0, ui
 	// 37.2 vs 38.9 us; the row step is a latency chain either way.)
 	if (Wb % 4 != 0) return VKV_OK;        // otherwise the search kernel
 	const uint32_t ctas    = split ? 2 * Db : Db;
+	// narrow maps with few slices: the CTA-per-slice sweep (bulk copies need 16-byte aligned row blocks)
+	const bool ring_ok = Wb <= 256u && ((size_t) Wb * Hb) % 16 == 0 && ((size_t) kSweepRows * Wb) % 16 == 0 && (reinterpret_cast<uintptr_t>(g) % 16) == 0 &&
+	                     (reinterpret_cast<uintptr_t>(dst0) % 16) == 0 && (!dst1 || (reinterpret_cast<uintptr_t>(dst1) % 16) == 0);
+	const char *force = getenv("VKV_YSWEEP");        // A/B: "ring" / "strip"
+	// (measured, sweep kernel alone: isotropic 208x208x124 / 256x256x199 maps 22 / 28 us against 35 / 43 us with strips; the one-sided
+	// sweeps of the octant maps the other way round, 39 / 44 against 27 / 34 us)
+	const bool  ring  = ring_ok && (force ? force[0] == 'r' : (XDIR == 0 && ctas < (uint32_t) vol->ctx->sm_count * 4u));
+	if (ring) {
+		const int    threads = (int) ((Wb / 4 + 31u) / 32u * 32u);
+		const size_t smem_r  = (size_t) kSweepSlots * kSweepRows * Wb + 2 * ((size_t) Wb / 4 + 2) * sizeof(uint2) + 16;
+		static PerDeviceOnce configured;
+		if (configured.first(vol->ctx->device)) {
+			VKV_CUDA_CHECK(cudaFuncSetAttribute(ysweep_ring_kernel<XDIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+		}
+		ysweep_ring_kernel<XDIR><<<ctas, threads, smem_r, s>>>(g, dst0, dst1, Wb, Hb, split ? 1 : 0);
+		VKV_LAUNCHED();
+		*done = true;
+		return VKV_OK;
+	}
 	const int      nstrips = Wb <= 256u ? 1 : (int) ((Wb + (256 - 2 * kStripHalo) - 1) / (256 - 2 * kStripHalo));
 	if (nstrips > 16) return VKV_OK;
 	const size_t smem = 2 * ((size_t) Wb / 2 + 8) * sizeof(unsigned);
