@@ -217,6 +217,9 @@ void vkv_volume_destroy(vkv_volume *vol)
 		for (int i = 0; i < vkv_volume::kAsyncSlots; ++i) { cudaEventDestroy(vol->async_rendered[i]); cudaEventDestroy(vol->async_copied[i]); }
 	if (vol->h_count) cudaFreeHost(vol->h_count);
 	if (vol->order_event) cudaEventDestroy(vol->order_event);
+	if (vol->side_stream) { cudaStreamSynchronize(vol->side_stream); cudaStreamDestroy(vol->side_stream); }
+	if (vol->ev_march) cudaEventDestroy(vol->ev_march);
+	if (vol->ev_order) cudaEventDestroy(vol->ev_order);
 	cudaFree(vol->d_lq); cudaFree(vol->d_lrays);
 	if (vol->h_long_hint) cudaFreeHost(vol->h_long_hint);
 	delete vol;

@@ -153,6 +153,9 @@ struct vkv_volume {
 	bool                tile_hist_valid = false;
 	int                *h_tile_promote = nullptr;        // pinned + mapped: the last ordering pass's decision (1 = long tiles promoted)
 	int                 tile_order_holdoff = 0;          // frames to go before the ordering pass is tried again
+	bool                tile_order_prepared = false;     // d_tile_order holds (or will hold, once ev_order fires) the order for the next frame of this key
+	cudaStream_t        side_stream = nullptr;           // the ordering pass runs here, beside the frame's long-ray pass
+	cudaEvent_t         ev_march = nullptr, ev_order = nullptr;
 	// multi-GPU group (group.cu): peers' map 0 / xy-intermediate / signal block, mapped through CUDA IPC
 	int                 grp_rank = -1, grp_world = 0;
 	uint8_t            *grp_map[8]{}, *grp_swap[8]{};

@@ -1213,15 +1213,21 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 		VKV_CUDA_CHECK(cudaMemsetAsync(d_trace, 0, trace_n * sizeof(unsigned long long), s));
 		P.trace = d_trace;
 	}
-	// tile scheduling history (see tile_order_kernel); VKV_RC_NO_HISTORY=1 keeps the centre-out order
+	// tile scheduling history (see tile_order_kernel); VKV_RC_NO_HISTORY=1 keeps the centre-out order.  The ordering pass for frame
+	// k + 1 needs nothing but frame k's march: it is launched on a side stream as soon as that march is, and runs beside frame k's
+	// long-ray pass instead of in front of frame k + 1 (one CTA, ~5 us: 5 % of the headline frame when it sat on the critical path).
+	bool use_hist = false;
+	int  tiles_y_hist = tiles_y;
 	{
 		const char *no_hist  = getenv("VKV_RC_NO_HISTORY");
 		// distance-map modes only: block skipping and ESS off are throughput-bound at every size measured (promotion costs them 2 %)
-		const bool  use_hist = !(no_hist && atoi(no_hist) != 0) && my_tiles >= 64 && my_tiles <= 6000 &&
-		                       (opt->skipping_type == VKV_SKIP_DISTANCE || opt->skipping_type == VKV_SKIP_ANISOTROPIC_DISTANCE) && !otf && !exact && !load;
+		use_hist = !(no_hist && atoi(no_hist) != 0) && my_tiles >= 64 && my_tiles <= 6000 &&
+		           (opt->skipping_type == VKV_SKIP_DISTANCE || opt->skipping_type == VKV_SKIP_ANISOTROPIC_DISTANCE) && !otf && !exact && !load;
 		const int   key[8]   = {width, height, tile_w, tile_h, tile_first, tile_stride, my_tiles, opt->skipping_type};
 		if (use_hist) {
 			if (vol->tile_hist_capacity < my_tiles) {
+				if (vol->tile_order_prepared) VKV_CUDA_CHECK(cudaStreamSynchronize(vol->side_stream));
+				vol->tile_order_prepared = false;
 				cudaFree(vol->d_tile_cost);
 				cudaFree(vol->d_tile_order);
 				vol->d_tile_cost = vol->d_tile_order = nullptr;
@@ -1231,32 +1237,51 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 				VKV_CUDA_CHECK(cudaMalloc(&vol->d_tile_order, (size_t) my_tiles * sizeof(unsigned)));
 				vol->tile_hist_capacity = my_tiles;
 			}
+			if (!vol->side_stream) {
+				VKV_CUDA_CHECK(cudaStreamCreateWithFlags(&vol->side_stream, cudaStreamNonBlocking));
+				VKV_CUDA_CHECK(cudaEventCreateWithFlags(&vol->ev_march, cudaEventDisableTiming));
+				VKV_CUDA_CHECK(cudaEventCreateWithFlags(&vol->ev_order, cudaEventDisableTiming));
+			}
 			const bool same = vol->tile_hist_valid && std::equal(key, key + 8, vol->tile_hist_key);
 			if (!vol->h_tile_promote) {
 				VKV_CUDA_CHECK(cudaHostAlloc(&vol->h_tile_promote, sizeof(int), cudaHostAllocMapped));
 				*vol->h_tile_promote = 1;
 			}
-			// a frame that did not qualify (throughput-bound) is not asked again for a while: the pass costs ~4 us
-			if (same && vol->tile_order_holdoff == 0 && *static_cast<volatile int *>(vol->h_tile_promote) == 0) {
-				vol->tile_order_holdoff  = 32;
-				*vol->h_tile_promote     = 1;
-			}
-			if (!same) vol->tile_order_holdoff = 0;
-			if (same && vol->tile_order_holdoff > 0) {
-				--vol->tile_order_holdoff;        // centre-out order; the cost keeps accumulating (maximum over the frames in between)
-			} else if (same) {
-				const int full = (tile_first == 0 && tile_stride == 1 && my_tiles == n_tiles) ? 1 : 0;
-				tile_order_kernel<<<1, 1024, 2 * (size_t) my_tiles * sizeof(unsigned), s>>>(vol->d_tile_cost, vol->d_tile_order, my_tiles, P.tiles_x, tiles_y, full, vol->h_tile_promote);
-				VKV_LAUNCHED();
-				P.tile_order = vol->d_tile_order;
-			} else {
+			// whatever the side stream was given has to be through before this frame touches the cost and order arrays
+			if (vol->tile_order_prepared) VKV_CUDA_CHECK(cudaStreamWaitEvent(s, vol->ev_order, 0));
+			if (same && vol->tile_order_prepared) {
+				P.tile_order = vol->d_tile_order;        // computed from the previous frame's cost, beside its long-ray pass
+			} else if (!same) {
 				VKV_CUDA_CHECK(cudaMemsetAsync(vol->d_tile_cost, 0, (size_t) my_tiles * sizeof(unsigned), s));
-			}
+				vol->tile_order_holdoff = 0;
+			}        // (same, nothing prepared: a hold-off frame — centre-out order; the cost keeps accumulating, maximum over the frames in between)
+			vol->tile_order_prepared = false;
 			P.tile_cost = vol->d_tile_cost;
 			std::copy(key, key + 8, vol->tile_hist_key);
 		}
 		vol->tile_hist_valid = use_hist;
 	}
+	// after the march of this frame has been launched: the ordering pass for the next frame of the same key
+	auto prepare_next_order = [&]() -> int {
+		if (!use_hist) return VKV_OK;
+		// a frame that did not qualify (throughput-bound) is not asked again for a while: the pass costs ~5 us
+		if (vol->tile_order_holdoff == 0 && *static_cast<volatile int *>(vol->h_tile_promote) == 0) {
+			vol->tile_order_holdoff = 32;
+			*vol->h_tile_promote    = 1;
+		}
+		if (vol->tile_order_holdoff > 0) {
+			--vol->tile_order_holdoff;
+			return VKV_OK;
+		}
+		const int full = (tile_first == 0 && tile_stride == 1 && my_tiles == n_tiles) ? 1 : 0;
+		VKV_CUDA_CHECK(cudaEventRecord(vol->ev_march, s));
+		VKV_CUDA_CHECK(cudaStreamWaitEvent(vol->side_stream, vol->ev_march, 0));
+		tile_order_kernel<<<1, 1024, 2 * (size_t) my_tiles * sizeof(unsigned), vol->side_stream>>>(vol->d_tile_cost, vol->d_tile_order, my_tiles, P.tiles_x, tiles_y_hist, full, vol->h_tile_promote);
+		VKV_LAUNCHED();
+		VKV_CUDA_CHECK(cudaEventRecord(vol->ev_order, vol->side_stream));
+		vol->tile_order_prepared = true;
+		return VKV_OK;
+	};
 	// one launch of the march over `count` tiles of the launch's list starting at `base`, on stream `st`
 	auto launch_march = [&](const RayParams &Q, int count, cudaStream_t st) -> int {
 		const dim3 grid((unsigned) (tile_w / 16), (unsigned) (tile_h / kRcRows), (unsigned) count);
@@ -1299,6 +1324,7 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 		P.seq_base = base;
 		if ((rc2 = launch_march(P, std::min(65535, my_tiles - base), s))) return rc2;
 	}
+	if ((rc2 = prepare_next_order())) return rc2;
 	if (long_now && (rc2 = launch_long(s))) return rc2;
 	if (d_trace) {
 		std::vector<unsigned long long> h(trace_n);
