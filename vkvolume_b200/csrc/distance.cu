@@ -12,18 +12,21 @@
 //   z pass : D(z)   = min_n max(|n|, s(z+n))
 // so any exact evaluation is bit-identical to the reference's passes.
 //
-// B200 design: every output cell gets its own thread.
-//   * x pass: the row is turned into a bit mask with warp ballots and each lane finds the
-//     nearest set bit with clz/ffs over at most 8 words per side (255-cell cap) — O(1), coalesced.
-//   * y / z passes: s(y) <= r iff the minimum of g over the window [y-r, y+r] is <= r — monotone in r — so
-//     each cell does an 8-step binary search on r against a sparse range-minimum table built in shared
-//     memory from the staged tile (32 adjacent columns x the whole line, coalesced 32-byte row segments).
-//     One thread per cell, no serial scan, ~25 conflict-free shared-memory operations per cell whatever
-//     the distances are.  Lines too long for shared memory use narrower tiles, then a global-memory search.
+// B200 design (round 2; every pass of round 1 turned out to be bound by instruction issue or by the latency of a short dependent
+// chain, never by bytes — profiles/r2_k3_summary.md — so each pass is built around its instruction count):
+//   * x pass: the row is turned into a bit mask and each lane finds the nearest set bit on either side of its 4, 8 or 16 adjacent
+//     cells with two O(1) searches (a 64-bit mask of the non-zero mask words names the word that holds it); cells in between by
+//     recurrence; one vector load and store per lane, the next row prefetched.  At the HBM roofline on maps past the L2.
+//   * y pass: chamfer recurrence, a whole row per step.  Wide maps: a warp owns a strip of 256 cells in registers (u16x2 lanes,
+//     neighbours by shuffle, VIMNMX3 / VIADDMNMX), strips exchange edge cells through shared memory every 16 rows.  Narrow
+//     isotropic maps with few slices: one CTA per sweep, previous row in shared memory, rows streamed through a bulk-TMA ring.
+//   * z pass: a walk along the line, F(z) = min(h(z), F(z+1) or F(z+1) + 1), decided by a per-value "last seen at step" table in
+//     shared memory (no search, no range-minimum tables); two walker warps per 32 columns, one per direction, meeting in the middle.
 //   * the anisotropic build shares the 2 x passes and 4 y passes between the 8 octant maps
 //     (same sharing as the reference's 14-dispatch schedule).
-// The maps are small (M bytes, L2-resident below ~100 MB); algorithmic bytes 6 B/block
-// (isotropic) and 28 B/block (anisotropic) as in SURVEY §8(d).
+//   * shapes the fast kernels do not cover (Wb % 4 != 0, rows over 2048 cells, ...) fall back to a binary search on the radius against
+//     a sparse range-minimum table (minmax_rmq_kernel) or the literal search (minmax_pass_kernel).
+// Algorithmic bytes 6 B/block (isotropic) and 28 B/block (anisotropic) as in SURVEY §8(d).
 #include <cstdlib>
 
 #include "common.cuh"
