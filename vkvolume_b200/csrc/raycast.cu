@@ -1220,7 +1220,8 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 	int  tiles_y_hist = tiles_y;
 	{
 		const char *no_hist  = getenv("VKV_RC_NO_HISTORY");
-		// distance-map modes only: block skipping and ESS off are throughput-bound at every size measured (promotion costs them 2 %)
+		// distance-map modes only: block skipping and ESS off are throughput-bound at every size measured (promotion costs them 2 %);
+		// up to 6000 tiles: an 8K frame (16 200 tiles) is throughput-bound too (measured with the limit lifted: 1.394 vs 1.343 ms)
 		use_hist = !(no_hist && atoi(no_hist) != 0) && my_tiles >= 64 && my_tiles <= 6000 &&
 		           (opt->skipping_type == VKV_SKIP_DISTANCE || opt->skipping_type == VKV_SKIP_ANISOTROPIC_DISTANCE) && !otf && !exact && !load;
 		const int   key[8]   = {width, height, tile_w, tile_h, tile_first, tile_stride, my_tiles, opt->skipping_type};
