@@ -458,7 +458,9 @@ __global__ void __launch_bounds__(512) ysweep_kernel(const uint8_t *__restrict__
 			for (int k = 0; k < 8; ++k) {
 #pragma unroll
 				for (int w = 0; w < NL; ++w)
-					buf[k][w] = (inplace ? __ldcg(reinterpret_cast<const unsigned *>(lp + xl[w])) : __ldg(reinterpret_cast<const unsigned *>(lp + xl[w]))) | force[w];
+					// (the isotropic variant's second sweep reads what the first wrote: L2 loads throughout — the rows are streamed once anyway,
+					// and one load flavour keeps the instruction stream free of a predicated twin of every load)
+					buf[k][w] = (XDIR == 0 ? __ldcg(reinterpret_cast<const unsigned *>(lp + xl[w])) : __ldg(reinterpret_cast<const unsigned *>(lp + xl[w]))) | force[w];
 				if (++requested < Hb) lp += rs;
 			}
 		};
