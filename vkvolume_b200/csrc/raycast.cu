@@ -435,7 +435,7 @@ struct RcTraceAcc {        // TRACE instantiation only
 // TRACE: debug instantiation (VKV_RC_TRACE) that also records the per-warp timeline.
 // LOAD: blend and depth-test over the existing contents of the target (vkv_render_options::load_framebuffer) instead of the
 // render-pass clear, and honour depth_attachment; these instantiations always count (COUNT).
-template <int SKIP, bool EXACT, bool COUNT, bool OTF, bool TRACE, bool LOAD>
+template <int SKIP, bool EXACT, bool COUNT, bool OTF, bool TRACE, bool LOAD, bool GRAD>
 __device__ __forceinline__ void rc_cast_pixel(const RayParams &P, const int px, const int py, const int lane, unsigned &n_vol, unsigned &n_dist,
                                               unsigned &n_empty, unsigned &covered_acc, unsigned &n_iter_out, RcTraceAcc &tr)
 {
@@ -445,6 +445,9 @@ __device__ __forceinline__ void rc_cast_pixel(const RayParams &P, const int px, 
 	constexpr bool kLong = kHist;
 	// hardware-filter production variants: contracted multiply-adds, 2-ulp divisions, fp32 entry point away from the silhouette
 	constexpr bool kFast = !EXACT && !OTF && !LOAD;
+	// GRAD = false: instantiations for transfer functions that ignore the gradient (the headline configuration): the gradient fetches,
+	// their batch registers and the second texel index are not compiled in at all (a predicated-off instruction still costs an issue slot)
+	const bool   use_g = GRAD && P.use_gradient;
 	const bool   in_frame = px < P.width && py < P.height;
 	const size_t p        = (size_t) py * P.width + px;
 	unsigned covered = 0u;        // this pixel
@@ -610,7 +613,7 @@ __device__ __forceinline__ void rc_cast_pixel(const RayParams &P, const int px, 
 					// inside occupied regions, and one batch of independent fetches replaces four dependent round trips
 					// conservative visible rectangle of the TF texture in (intensity texel, gradient texel): a sample outside it is
 					// empty (alpha byte 0) and needs no colour-table read — on the long grazing rays most samples are
-					const TFRange tb    = P.use_gradient ? P.bounds->tex_all : P.bounds->tex_row255;
+					const TFRange tb    = use_g ? P.bounds->tex_all : P.bounds->tex_row255;
 					const unsigned tb_vspan = tb.v_hi - tb.v_lo, tb_gspan = tb.g_hi - tb.g_lo;
 					int      pre_base = -0x40000000;
 					float pre_v0 = 0.0f, pre_v1 = 0.0f, pre_v2 = 0.0f, pre_v3 = 0.0f, pre_g0 = 1.0f, pre_g1 = 1.0f, pre_g2 = 1.0f, pre_g3 = 1.0f;
@@ -666,7 +669,7 @@ __device__ __forceinline__ void rc_cast_pixel(const RayParams &P, const int px, 
 								pre_v1 = tex3D<float>(P.tex_v, q1[0], q1[1], q1[2]);
 								pre_v2 = tex3D<float>(P.tex_v, q2[0], q2[1], q2[2]);
 								pre_v3 = tex3D<float>(P.tex_v, q3[0], q3[1], q3[2]);
-								if (P.use_gradient) {
+								if (use_g) {
 									pre_g0 = tex3D<float>(P.tex_g, pos[0], pos[1], pos[2]);
 									pre_g1 = tex3D<float>(P.tex_g, q1[0], q1[1], q1[2]);
 									pre_g2 = tex3D<float>(P.tex_g, q2[0], q2[1], q2[2]);
@@ -709,18 +712,18 @@ __device__ __forceinline__ void rc_cast_pixel(const RayParams &P, const int px, 
 							float intensity, gradient = 1.0f;
 							if (OTF) {
 								intensity = EXACT ? sample_exact(P.V, P.dim, pos[0], pos[1], pos[2]) : tex3D<float>(P.tex_v, pos[0], pos[1], pos[2]);
-								if (P.use_gradient)
+								if (use_g)
 									gradient = gradient_otf<EXACT>(P.tex_v, P.V, P.dim, dim_inv, P.grad_modifier, pos[0], pos[1], pos[2]);
 							} else if (EXACT) {
 								intensity = sample_exact(P.V, P.dim, pos[0], pos[1], pos[2]);
-								if (P.use_gradient) gradient = sample_exact(P.G, P.dim, pos[0], pos[1], pos[2]);
+								if (use_g) gradient = sample_exact(P.G, P.dim, pos[0], pos[1], pos[2]);
 							} else {
 								intensity = pick4_(k, pre_v0, pre_v1, pre_v2, pre_v3);
-								if (P.use_gradient) gradient = pick4_(k, pre_g0, pre_g1, pre_g2, pre_g3);
+								if (use_g) gradient = pick4_(k, pre_g0, pre_g1, pre_g2, pre_g3);
 							}
-							const int ti = tf_texel(intensity), tg = tf_texel(gradient);
-							float4    c  = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
-							if (!(P.flags & 1) || ((unsigned) ti - tb.v_lo <= tb_vspan && (unsigned) tg - tb.g_lo <= tb_gspan)) c = __ldg(P.ctab + tg * 256 + ti);
+							const int ti = tf_texel(intensity), tg = GRAD ? tf_texel(gradient) : 255;        // gradient = 1.0 without a gradient TF
+							float4    c;
+							c = __ldg(P.ctab + tg * 256 + ti);        // (skipping the read for texels outside the TF's visible rectangle was measured: no change here)
 							voxel_occupied = c.w >= 0.0f;
 							if (voxel_occupied) {
 								if (SKIP != VKV_SKIP_NONE) idx_last = idx;
@@ -805,7 +808,7 @@ __device__ __forceinline__ void rc_cast_pixel(const RayParams &P, const int px, 
 
 // A CTA is two warps = a 16x4 pixel tile; small CTAs keep the register file busy while long rays finish.
 // grid = (CTAs per tile in x, CTAs per tile in y, tiles of this launch).
-template <int SKIP, bool EXACT, bool COUNT, bool OTF = false, bool TRACE = false, bool LOAD = false>
+template <int SKIP, bool EXACT, bool COUNT, bool OTF = false, bool TRACE = false, bool LOAD = false, bool GRAD = true>
 __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CTAS) * 2 / kRcWarps) raycast_kernel(const __grid_constant__ RayParams P)
 {
 	__shared__ unsigned long long s_cnt[kRcWarps][4];
@@ -845,7 +848,7 @@ __global__ void __launch_bounds__(kRcThreads, ((OTF || LOAD) ? 8 : VKV_RC_MIN_CT
 	}
 
 	unsigned n_vol = 0, n_dist = 0, n_empty = 0, covered = 0;
-	rc_cast_pixel<SKIP, EXACT, COUNT, OTF, TRACE, LOAD>(P, px, py, lane, n_vol, n_dist, n_empty, covered, n_iter, tr);
+	rc_cast_pixel<SKIP, EXACT, COUNT, OTF, TRACE, LOAD, GRAD>(P, px, py, lane, n_vol, n_dist, n_empty, covered, n_iter, tr);
 
 	if (kHist && P.tile_cost) {
 		const unsigned it_warp = __reduce_max_sync(0xffffffffu, n_iter);
@@ -1286,6 +1289,7 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 	// one launch of the march over `count` tiles of the launch's list starting at `base`, on stream `st`
 	auto launch_march = [&](const RayParams &Q, int count, cudaStream_t st) -> int {
 		const dim3 grid((unsigned) (tile_w / 16), (unsigned) (tile_h / kRcRows), (unsigned) count);
+		const bool nograd = !Q.use_gradient && !getenv("VKV_RC_GRAD_GENERIC");        // (A/B: the generic instantiation)
 #define VKV_RC(SK)                                                                      \
 	do {                                                                                \
 		if (load && otf && exact) raycast_kernel<SK, true, true, true, false, true><<<grid, kRcThreads, 0, st>>>(Q);  \
@@ -1297,6 +1301,8 @@ int launch_render(vkv_volume *vol, const vkv_camera_uniform *cam, const vkv_ray_
 		else if (otf) raycast_kernel<SK, false, true, true><<<grid, kRcThreads, 0, st>>>(Q);      \
 		else if (exact && counts) raycast_kernel<SK, true, true><<<grid, kRcThreads, 0, st>>>(Q);      \
 		else if (exact) raycast_kernel<SK, true, false><<<grid, kRcThreads, 0, st>>>(Q);          \
+		else if (Q.counts && nograd) raycast_kernel<SK, false, true, false, false, false, false><<<grid, kRcThreads, 0, st>>>(Q); \
+		else if (nograd) raycast_kernel<SK, false, false, false, false, false, false><<<grid, kRcThreads, 0, st>>>(Q); \
 		else if (Q.counts) raycast_kernel<SK, false, true><<<grid, kRcThreads, 0, st>>>(Q);         \
 		else raycast_kernel<SK, false, false><<<grid, kRcThreads, 0, st>>>(Q);                    \
 	} while (0)
