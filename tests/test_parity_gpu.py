@@ -155,6 +155,39 @@ def test_gradient_persistent_walk_byte_exact(ctx, shape, kind):
     vol.close()
 
 
+@pytest.mark.parametrize("knob", ["VKV_GRAD_FLAT", "VKV_GRAD_V1", "VKV_GRAD_FP32"])
+def test_gradient_fallback_kernels_byte_exact(ctx, knob, monkeypatch):
+    """The column walk is the default since round 2; the flat walk, the row-task kernel and the pure-fp32 kernel remain as fallbacks
+    (indices that do not fit, grad_magnitude_modifier != 1) and must keep producing the oracle's bytes."""
+    monkeypatch.setenv(knob, "1")
+    D, H, W = 41, 77, 208
+    V = scene.blobs_volume((D, H, W), seed=5)
+    V[::3] = (V[::3].astype(np.int32) + np.random.default_rng(9).integers(-2, 3, size=V[::3].shape)).clip(0, 255).astype(np.uint8)
+    vol = capi.Volume(ctx, W, H, D)
+    vol.upload(V)
+    vol.compute_gradient_map(capi.transfer_function_uniform(VolumeOptions(gradient_min=0.0, gradient_max=0.2)))
+    Gref = orc.gradient_map(V)
+    assert np.array_equal(vol.download_gradient(), Gref)
+    assert np.array_equal(vol.download_gradient_texture(), Gref)
+    vol.close()
+
+
+@pytest.mark.parametrize("shape", [(3, 2, 16), (2, 1, 32), (5, 100, 16), (4, 7, 528), (66, 3, 48)])
+def test_gradient_column_walk_edge_shapes(ctx, shape):
+    """Column walk corner cases: one or two rows (both parities clamp), a single chunk per row (every lane is first and last),
+    rows longer than a warp's 256-byte run (the outer lanes read the neighbouring word from memory), more planes than rows."""
+    D, H, W = shape
+    V = np.random.default_rng(D * H + W).integers(0, 256, size=shape, dtype=np.uint8)
+    V[:, :, ::2] = 128        # many exact ties
+    vol = capi.Volume(ctx, W, H, D)
+    vol.upload(V)
+    vol.compute_gradient_map(capi.transfer_function_uniform(VolumeOptions(gradient_min=0.0, gradient_max=0.2)))
+    Gref = orc.gradient_map(V)
+    assert np.array_equal(vol.download_gradient(), Gref)
+    assert np.array_equal(vol.download_gradient_texture(), Gref)
+    vol.close()
+
+
 # ---- K2a / K2b -----------------------------------------------------------------------------------------
 @pytest.mark.parametrize("shape,bs", [((16, 16, 32), 4), ((9, 10, 13), 4), ((24, 20, 48), 4), ((12, 12, 32), 2), ((16, 24, 64), 8),
                                       ((7, 9, 10), 3), ((15, 11, 48), 5), ((10, 10, 10), 1), ((6, 6, 6), 8), ((33, 17, 80), 4),

@@ -12,6 +12,7 @@
 // identical to the CPU oracle's (the byte feeds the occupancy LUT).  UNORM decode b/255 is
 // served from a 256-entry shared-memory table built with a true division.
 // Algorithmic bytes: read N + write N = 2 B/voxel.
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -408,6 +409,211 @@ __global__ void __launch_bounds__(256) gradient_flat_kernel(const uint8_t *__res
 	while (qn) grad_drain<SURF>(q, qn, s_lut, warp, lane, qn < 32u ? qn : 32u, V, G, surf, W, H, D);
 }
 
+// ---- column walk ------------------------------------------------------------------------------------------------
+// The tap lattice (x +- 1, y +- 1, z +- 1) splits the rows of the volume by the parity of y: the voxels of row y read rows
+// y - 1 and y + 1 only.  A thread therefore owns one column — a 16-voxel chunk of x at one z — and walks every second row
+// of a y segment: the two rows (y + 1, z - 1), (y + 1, z + 1) it loads for row y serve row y + 2 again (as its y - 1 taps),
+// so a step is TWO 16-byte loads instead of four, the addresses are one multiply-add per plane (no chunk -> (x, y, z)
+// decode, no carries), and nothing but the row registers rotates (the loop is unrolled by the three row pairs in flight).
+// The x -+ 1 byte of a row comes from the neighbouring lane as one indexed shuffle of an "edge word" built per row:
+// byte 0 = the row's first voxel, byte 3 = its last, bytes 1/2 = the voxel before / after the warp's run (loaded by the outer
+// lanes of a run only).  Which lane a thread asks and which byte it takes — neighbour, own word at a clamped volume edge, or the
+// memory byte — never changes during the walk, so the clamps cost nothing in the loop.  The shift by the tap's x offset is
+// folded into the first stage of the 4x4 byte transpose (9 + 9 permutes per chunk instead of 16 shifts + 16 permutes).
+// Arithmetic and tie handling as in the flat kernel: same bytes, about 40 % fewer instructions per voxel.
+struct GradPair {        // rows (y', z - 1) and (y', z + 1) of one column
+	uint4    m, p;
+	unsigned xm, xp;        // the word beside the warp's run (lanes 0 / 31 only; undefined elsewhere)
+	unsigned em, ep;        // edge words
+};
+
+__device__ __forceinline__ void grad_pair_load(GradPair &r, const uint8_t *__restrict__ baseM, const uint8_t *__restrict__ baseP, uint32_t row, uint32_t W,
+                                               bool need_x, int xoff)
+{
+	// (volatile: the compiler otherwise sinks these loads to the end of the step to shorten their live ranges, which leaves
+	// them ~50 instructions instead of a whole step ahead of their first use)
+	const size_t o = (size_t) row * W;
+	asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.m.x), "=r"(r.m.y), "=r"(r.m.z), "=r"(r.m.w) : "l"(baseM + o));
+	asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.p.x), "=r"(r.p.y), "=r"(r.p.z), "=r"(r.p.w) : "l"(baseP + o));
+	r.xm = r.xp = 0;
+	if (need_x) {
+		asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r.xm) : "l"(baseM + o + xoff));
+		asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r.xp) : "l"(baseP + o + xoff));
+	}
+}
+
+// Tie passes of the column walk, split in two so that the tap re-reads of a pass are in flight during a whole row of the walk:
+// `start` pops the top n_take (<= 32) entries (one tie each; entries holding more ties push the rest back) and requests the
+// four taps, `finish` evaluates the shader's fp32 chain and patches the byte in the linear map and in the texture array.
+struct GradPass {
+	bool     on = false, mine = false;        // on: warp-uniform
+	unsigned ta, tb, tc, td, yz, x;
+};
+
+__device__ __forceinline__ void grad_pass_start(GradPass &ps, GradQueue &q, unsigned &n, int warp, int lane, unsigned n_take, const uint8_t *__restrict__ V,
+                                                uint32_t W, uint32_t H, uint32_t D)
+{
+	__syncwarp();
+	ps.on   = true;
+	ps.mine = (unsigned) lane < n_take;
+	unsigned t = 0, yz = 0, cx = 0;
+	if (ps.mine) {
+		const unsigned e = n - n_take + lane;
+		t = q.tie[warp][e], yz = q.yz[warp][e], cx = q.cx[warp][e];
+	}
+	n -= n_take;
+	__syncwarp();
+	const unsigned rest = t & (t - 1u);
+	grad_push(q, n, warp, lane, rest != 0u, rest, yz, cx);
+	ps.ta = ps.tb = ps.tc = ps.td = 0;
+	if (ps.mine) {
+		const unsigned pos = __ffs(t) - 1;
+		const uint32_t x = cx * 16 + 4 * (pos & 7u) + (pos >> 3), y = yz & 0xffffu, z = yz >> 16;
+		const uint32_t xm = x > 0 ? x - 1 : 0, xp = x + 1 < W ? x + 1 : W - 1;
+		const uint32_t ym = y > 0 ? y - 1 : 0, yp = y + 1 < H ? y + 1 : H - 1;
+		const uint32_t zmH = (z > 0 ? z - 1 : 0) * H, zpH = (z + 1 < D ? z + 1 : D - 1) * H;
+		const uint8_t *Vp = V + xp, *Vm = V + xm;
+		asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(ps.ta) : "l"(Vp + (size_t) (zmH + ym) * W));
+		asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(ps.tb) : "l"(Vm + (size_t) (zpH + ym) * W));
+		asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(ps.tc) : "l"(Vm + (size_t) (zmH + yp) * W));
+		asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(ps.td) : "l"(Vp + (size_t) (zpH + yp) * W));
+		ps.yz = yz, ps.x = x;
+	}
+}
+
+template <bool SURF>
+__device__ __forceinline__ void grad_pass_finish(GradPass &ps, const float *s_lut, uint8_t *__restrict__ G, cudaSurfaceObject_t surf, uint32_t W, uint32_t H, uint32_t dbg = 0)
+{
+	if (ps.mine) {
+		const uint32_t      y = ps.yz & 0xffffu, z = ps.yz >> 16;
+		const unsigned char g = gradient_byte(s_lut[ps.ta], s_lut[ps.tb], s_lut[ps.tc], s_lut[ps.td], 1.0f);
+		if (!(dbg & 16) || g == 77) G[(size_t) (z * H + y) * W + ps.x] = g;
+		if (SURF && (!(dbg & 32) || g == 77)) surf3Dwrite(g, surf, (int) ps.x, (int) y, (int) z);
+	}
+	ps.on = false;
+}
+
+__device__ __forceinline__ unsigned grad_edge_word(const uint4 &q, unsigned x)
+{
+	return prmt_(prmt_(q.x, q.w, 0x7000u), x, 0x3470u);        // (q[0], x[3], x[0], q[15])
+}
+
+// ABL: the ablation instantiation (VKV_GRAD_DBG=<bits>, timing only — the map is wrong): 1 no tie queue, 2 no row surface stores,
+// 4 no row stores to the linear map, 8 no arithmetic (rows copied through), 16 / 32 no tie patches to the linear map / the array.
+template <bool SURF, bool ABL>
+__global__ void __launch_bounds__(256, 3) gradient_walk_kernel(const uint8_t *__restrict__ V, uint8_t *__restrict__ G, cudaSurfaceObject_t surf,
+                                                              uint32_t W, uint32_t H, uint32_t D, uint32_t ncols, uint32_t ncg, uint32_t nseg, uint32_t steps, uint32_t dbg_bits)
+{
+	const uint32_t dbg = ABL ? dbg_bits : 0u;
+	__shared__ float     s_lut[256];
+	__shared__ GradQueue q;
+	s_lut[threadIdx.x] = (float) threadIdx.x / 255.0f;        // UNORM decode, exactly as imageLoad
+	__syncthreads();
+	const uint32_t nchunks = W / 16;
+	const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	unsigned       qn = 0;        // entries in this warp's queue (warp-uniform)
+	// A warp is 16 columns x the two row parities (lanes 16..31 walk the odd rows): each step it completes two adjacent rows of
+	// 256 B, which is what the block-linear texture array wants — surface stores of 512 B x 1 row per warp run at less than half
+	// the rate of 256 B x 2 (scripts/ubench/sust_patterns.cu: 0.168 vs 0.094 ms for this volume, copy + surface 0.35 vs 0.18 ms).
+	// column = (z, chunk) with the chunk fastest; warp = (segment, group of 16 columns); lanes past the last column mirror it.
+	const uint32_t gw  = blockIdx.x * 8u + (uint32_t) warp, l16 = (uint32_t) lane & 15u;
+	const uint32_t seg = gw / ncg, cg = gw - seg * ncg;
+	uint32_t       col = cg * 16u + l16;
+	const bool     valid = seg < nseg && col < ncols;
+	col                  = col < ncols ? col : ncols - 1;
+	const uint32_t z = col / nchunks, cx = col - z * nchunks;
+	uint32_t       y = seg * (2u * steps) + ((uint32_t) lane >> 4);        // first row; then every second one
+	const bool     first = cx == 0, last = cx == nchunks - 1;
+	const uint32_t zm = z > 0 ? z - 1 : 0, zp = z + 1 < D ? z + 1 : D - 1;
+	const uint8_t *baseM = V + (size_t) zm * H * W + cx * 16, *baseP = V + (size_t) zp * H * W + cx * 16;
+	uint8_t       *baseG = G + (size_t) z * H * W + cx * 16;
+	// where the x - 1 / x + 1 byte of a row comes from: the lane asked and the byte of its edge word (4 + k: operand b of prmt)
+	const bool     mem_prev = l16 == 0 && !first, mem_next = l16 == 15 && !last;
+	const int      src_prev = (first || l16 == 0) ? lane : lane - 1, src_next = (last || l16 == 15) ? lane : lane + 1;
+	const unsigned kp = first ? 0u : mem_prev ? 1u : 3u, kn = last ? 3u : mem_next ? 2u : 0u;
+	const unsigned sel_prev = 0x0100u | ((4u + kp) << 12) | ((4u + kp) << 4);        // (a0, e[kp], a1, e[kp]): voxel 0 in the high half
+	const unsigned sel_next = 0x6060u | kn | (kn << 8);                              // (e[kn], b2, e[kn], b2): voxel 15 in the low half
+	const bool     need_x = mem_prev || mem_next;
+	const int      xoff   = mem_prev ? -4 : 16;
+	const uint32_t Hm1    = H - 1;
+
+	GradPass ps;
+	GradPair r0, r1, r2;
+	grad_pair_load(r0, baseM, baseP, min(y > 0 ? y - 1 : 0u, Hm1), W, need_x, xoff);
+	grad_pair_load(r1, baseM, baseP, min(y + 1, Hm1), W, need_x, xoff);
+	r0.em = grad_edge_word(r0.m, r0.xm), r0.ep = grad_edge_word(r0.p, r0.xp);
+
+	// one row of the walk: taps A, B on the pair `lo` (row y - 1), C, E on `hi` (row y + 1); `nx` receives row y + 3
+	auto step = [&](GradPair &lo, GradPair &hi, GradPair &nx) {
+		grad_pair_load(nx, baseM, baseP, min(y + 3, Hm1), W, need_x, xoff);
+		hi.em = grad_edge_word(hi.m, hi.xm), hi.ep = grad_edge_word(hi.p, hi.xp);
+		const unsigned eA = __shfl_sync(0xffffffffu, lo.em, src_next), eB = __shfl_sync(0xffffffffu, lo.ep, src_prev);
+		const unsigned eC = __shfl_sync(0xffffffffu, hi.em, src_prev), eE = __shfl_sync(0xffffffffu, hi.ep, src_next);
+		const unsigned a[4] = {lo.m.x, lo.m.y, lo.m.z, lo.m.w}, b[4] = {lo.p.x, lo.p.y, lo.p.z, lo.p.w};        // A at x + 1, B at x - 1
+		const unsigned c[4] = {hi.m.x, hi.m.y, hi.m.z, hi.m.w}, e[4] = {hi.p.x, hi.p.y, hi.p.z, hi.p.w};        // C at x - 1, E at x + 1
+		// first transpose stage with the x shift folded in.  P[j] = voxels (4j - 1, 4j), Q[j] = voxels (4j + 1, 4j + 2);
+		// a half is (tap at x + 1, tap at x - 1) of one voxel
+		unsigned pab[5], pce[5], qab[4], qce[4];
+		pab[0] = prmt_(a[0], eB, sel_prev), pce[0] = prmt_(e[0], eC, sel_prev);
+		pab[4] = prmt_(eA, b[3], sel_next), pce[4] = prmt_(eE, c[3], sel_next);
+#pragma unroll
+		for (int j = 1; j < 4; ++j) pab[j] = prmt_(a[j], b[j - 1], 0x7160u), pce[j] = prmt_(e[j], c[j - 1], 0x7160u);
+#pragma unroll
+		for (int j = 0; j < 4; ++j) qab[j] = prmt_(a[j], b[j], 0x5342u), qce[j] = prmt_(e[j], c[j], 0x5342u);
+		unsigned out[4] = {0, 0, 0, 0}, tie[4] = {0, 0, 0, 0};
+		if (!(dbg & 8))
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			// second stage: the four taps of one voxel in one word (their order does not matter to the two dot products)
+			const unsigned wv[4] = {prmt_(pab[j], pce[j], 0x7632u), prmt_(qab[j], qce[j], 0x5410u), prmt_(qab[j], qce[j], 0x7632u),
+			                        prmt_(pab[j + 1], pce[j + 1], 0x5410u)};
+			unsigned yv[4];
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				const unsigned qq = __dp4a(wv[i], wv[i], 0x12c00000u);       // A^2 + B^2 + C^2 + D^2 + 0x4b000000 / 4
+				const unsigned sm = __dp4a(wv[i], 0x01010101u, 0u);          // A + B + C + D
+				const unsigned Sb = (qq << 2) - sm * sm;                    // bits of the float 2^23 + S   (S = 4 qq - sm^2 < 2^18)
+				const float    f  = __uint_as_float(Sb) - 8388608.0f;       // S, exactly
+				float          rt;
+				asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rt) : "f"(f));
+				yv[i] = __float_as_uint(__fmaf_rn(rt, 64.0f, 8388736.0f));   // low 16 mantissa bits = rint(64 sqrt(S)) + 128
+			}
+			const unsigned p01 = prmt_(yv[0], yv[1], 0x5410u), p23 = prmt_(yv[2], yv[3], 0x5410u);
+			out[j]             = prmt_(p01, p23, 0x7531u);                  // rint(sqrt(S) / 4) where that is safe
+			const unsigned lo8 = prmt_(p01, p23, 0x6420u);
+			tie[j]             = (lo8 - 0x01010101u) & ~lo8 & 0x80808080u;   // 0x80 in the bytes of lo8 that are zero
+		}
+		const bool  active = valid && y < H;
+		uint4 o      = make_uint4(out[0], out[1], out[2], out[3]);
+		if (dbg & 8) o = make_uint4(lo.m.x ^ eA, lo.p.y ^ eB, hi.m.z ^ eC, hi.p.w ^ eE);
+		if (active) {
+			if (!(dbg & 4)) *reinterpret_cast<uint4 *>(baseG + (size_t) y * W) = o;
+			if (SURF && !(dbg & 2)) surf3Dwrite(o, surf, (int) (cx * 16), (int) y, (int) z);        // x in bytes
+		}
+		const unsigned t = (tie[0] >> 7) | (tie[1] >> 6) | (tie[2] >> 5) | (tie[3] >> 4);
+		grad_push(q, qn, warp, lane, t != 0u && active && !(dbg & 1), t, y | (z << 16), cx);
+		y += 2;
+		// the pass started a row ago has its taps by now; then at most one new pass per row is put in flight (the __syncwarp at
+		// the top of grad_pass_start orders this row's stores before its byte patches).  Only a volume made of ties needs more.
+		if (ps.on) grad_pass_finish<SURF>(ps, s_lut, G, surf, W, H, dbg);
+		while (qn >= 64u) {
+			grad_pass_start(ps, q, qn, warp, lane, 32u, V, W, H, D);
+			grad_pass_finish<SURF>(ps, s_lut, G, surf, W, H, dbg);
+		}
+		if (qn >= 32u) grad_pass_start(ps, q, qn, warp, lane, 32u, V, W, H, D);
+	};
+	for (uint32_t k = 0; k < steps; k += 3) {
+		step(r0, r1, r2);
+		step(r1, r2, r0);
+		step(r2, r0, r1);
+	}
+	if (ps.on) grad_pass_finish<SURF>(ps, s_lut, G, surf, W, H, dbg);
+	while (qn) {
+		grad_pass_start(ps, q, qn, warp, lane, qn < 32u ? qn : 32u, V, W, H, D);
+		grad_pass_finish<SURF>(ps, s_lut, G, surf, W, H, dbg);
+	}
+}
+
 // Any extents: one thread per voxel, clamped byte loads through L1.
 __global__ void __launch_bounds__(256) gradient_scalar_kernel(const uint8_t *__restrict__ V, uint8_t *__restrict__ G, uint32_t W,
                                                              uint32_t H, uint32_t D, float modifier)
@@ -449,7 +655,34 @@ int launch_gradient(vkv_volume *vol, bool use_gradient, float modifier, cudaStre
 		// multi-gigabyte volumes the row-task kernel, whose warps sweep one row each and keep neighbouring rows together, is up
 		// to 2x faster (measured: 2048x2048x1024 5.4 vs 6.0 ms, 4096x4096x2048 44 vs 86 ms; 832x832x494 0.50 vs 0.37 ms).
 		const bool flat_ok = vol->N <= (2ull << 30) || getenv("VKV_GRAD_FLAT");
-		if (!getenv("VKV_GRAD_V1") && flat_ok && vol->dim[0] <= 65536 && vol->dim[1] <= 65536 && vol->dim[2] < 65536 && chunks < (1ull << 32)) {
+		// The column walk (round 2) replaces both wherever its packed indices fit: half the loads, no index arithmetic in the loop.
+		const uint32_t nch = vol->dim[0] / 16;
+		const uint64_t ncols = (uint64_t) nch * vol->dim[2];
+		uint32_t       steps = 24;        // rows per thread; a segment is 2 * steps rows (two parities)
+		const uint64_t ncg   = (ncols + 15) / 16;        // warps per segment: 16 columns x 2 row parities
+		auto           n_seg = [&](uint32_t st) { return (uint64_t) ((vol->dim[1] + 2 * st - 1) / (2 * st)); };
+		const uint64_t resident = (uint64_t) vol->ctx->sm_count * 3 * 8;        // warps
+		while (steps > 3 && ncg * n_seg(steps) < 8 * resident) steps /= 2;
+		if (const char *e = getenv("VKV_GRAD_STEPS")) steps = (uint32_t) std::max(1, atoi(e)) * 3;
+		const bool walk_ok = !getenv("VKV_GRAD_V1") && !getenv("VKV_GRAD_FLAT") && nch <= 65535 && vol->dim[1] <= 65535 && vol->dim[2] <= 65535 &&
+		                     ncg * n_seg(steps) < (1ull << 31) && ncols < (1ull << 31);
+		if (walk_ok) {
+			const uint64_t warps = ncg * n_seg(steps);
+			const unsigned g     = (unsigned) ((warps + 7) / 8);
+			const bool     surf  = vol->s_G && !getenv("VKV_GRAD_NOSURF");
+			const uint32_t dbg   = (surf && getenv("VKV_GRAD_DBG")) ? (uint32_t) atoi(getenv("VKV_GRAD_DBG")) : 0u;
+#define VKV_GRAD_WALK(SURF_, ABL_)                                                                                                                 \
+	gradient_walk_kernel<SURF_, ABL_><<<g, 256, 0, s>>>(vol->d_V, vol->d_G, SURF_ ? vol->s_G : 0, vol->dim[0], vol->dim[1], vol->dim[2], (uint32_t) ncols, \
+	                                                    (uint32_t) ncg, (uint32_t) n_seg(steps), steps, dbg)
+			if (dbg)
+				VKV_GRAD_WALK(true, true);
+			else if (surf)
+				VKV_GRAD_WALK(true, false);
+			else
+				VKV_GRAD_WALK(false, false);
+#undef VKV_GRAD_WALK
+			vol->G_array_synced = surf;        // the kernel wrote the array itself
+		} else if (!getenv("VKV_GRAD_V1") && flat_ok && vol->dim[0] <= 65536 && vol->dim[1] <= 65536 && vol->dim[2] < 65536 && chunks < (1ull << 32)) {
 			// persistent: every warp resident at once, each thread walks chunks gid, gid + stride, ...
 			const unsigned nchunks = vol->dim[0] / 16;
 			const char    *e_ctas      = getenv("VKV_GRAD_CTAS");
