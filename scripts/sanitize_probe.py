@@ -18,6 +18,17 @@ def check(name, cond):
     print(("ok   " if cond else "FAIL ") + name, flush=True)
     ok = ok and bool(cond)
 
+# (0) gradient column walk on a volume full of exact ties (per-warp tie queue in shared memory, passes split around a row of the walk,
+# indexed shuffles between the lanes of a 256-byte run, rows wider than a run)
+V = (128 + np.random.default_rng(3).integers(-2, 3, size=(9, 31, 528))).astype(np.uint8)
+vol = capi.Volume(ctx, 528, 31, 9)
+vol.upload(V)
+vol.compute_gradient_map(capi.transfer_function_uniform(VolumeOptions(gradient_min=0.0, gradient_max=0.2)))
+Gref = orc.gradient_map(V, True)
+check("gradient map (column walk, ties) == oracle", np.array_equal(vol.download_gradient(), Gref))
+check("gradient texture array == oracle", np.array_equal(vol.download_gradient_texture(), Gref))
+vol.close()
+
 # (1) occupancy_tma_kernel with and without the gradient map on a 1024-wide volume; fused count
 W, H, D = 1024, 24, 16
 V = np.random.default_rng(1).integers(0, 256, size=(D, H, W), dtype=np.uint8)
