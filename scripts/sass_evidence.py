@@ -44,9 +44,9 @@ def excerpt(match, pat, before=4, after=8, title=""):
                     out.extend(["", f"## {title}", "", f"`{short(n)}`", "", "```"] + [re.sub(r"\s+/\* 0x[0-9a-f]+ \*/\s*$", "", x) for x in kern[n][max(0, i - before): i + after]] + ["```"])
                     return
 excerpt("occupancy_tma_kernel<true, true>", r"UTMALDG", title="occupancy_tma_kernel: 3-D tiled TMA load (UTMALDG) armed on an mbarrier (SYNCS)")
-excerpt("ysweep_kernel<0>", r"UBLKCP", title="ysweep_kernel: 1-D bulk copy (UBLKCP) of a block of rows into the shared-memory ring")
-excerpt("raycast_kernel<2, false, false, false, false, false>", r"TEX\.", before=2, after=14, title="raycast_kernel: the four-sample texture batch (TEX) of the look-ahead")
+excerpt("ysweep_ring_kernel<0>", r"UBLKCP", title="ysweep_ring_kernel: 1-D bulk copy (UBLKCP) of a block of rows into the shared-memory ring")
+excerpt("raycast_kernel<2, false, false, false, false, false, false>", r"TEX\.", before=2, after=14, title="raycast_kernel: the four-sample texture batch (TEX) of the look-ahead")
 excerpt("raycast_long_kernel<2>", r"TEX\.", before=2, after=10, title="raycast_long_kernel: window fetches (TEX + skip-map byte load), then ballots for the replay masks")
-excerpt("gradient_flat_kernel<true>", r"IDP", before=2, after=10, title="gradient_flat_kernel: dp4a (IDP.4A) integer formulation, MUFU.SQRT, surface store (SUST)")
+excerpt("gradient_walk_kernel<true, false>", r"IDP", before=2, after=10, title="gradient_walk_kernel: dp4a (IDP.4A) integer formulation, MUFU.SQRT; indexed shuffles (SHFL.IDX) for the x -+ 1 bytes, surface store (SUST)")
 (ROOT / "profiles" / f"{tag}_sass_evidence.md").write_text("\n".join(out) + "\n")
 print("wrote", ROOT / "profiles" / f"{tag}_sass_evidence.md", len(out), "lines")
