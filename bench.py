@@ -409,11 +409,15 @@ def run_native(args):
     ropt = RenderOptions(skipping_type=skip, clip_distance=wl["clip"], early_ray_termination=1)
     fb_ptr, peer_ptr = None, None
     frame_bytes = FW * FH * 4
-    if rank == 0:
-        fb_all = torch.zeros((slots, FH, FW, 4), dtype=torch.uint8, device=dev)
+    # Frames mode (one independent view per rank per step) keeps every rank's frame in that rank's own HBM, exactly as at N = 1: the
+    # decomposition has no exchange step and none is invented.  --gather-frames restores round 1's variant (every rank stores its
+    # pixels into its slot of a frame ring in rank 0's HBM through peer stores).  Tiles mode always gathers into rank 0 (north star).
+    local_frames = frames_mode and not args.gather_frames
+    if rank == 0 or local_frames:
+        fb_all = torch.zeros((1 if local_frames else slots, FH, FW, 4), dtype=torch.uint8, device=dev)
         fb = fb_all[0]
         fb_ptr = fb_all.data_ptr()
-    if world > 1:
+    if world > 1 and not local_frames:
         import ctypes as C
         handle = [None]
         if rank == 0:
@@ -459,10 +463,15 @@ def run_native(args):
     # stores must equal rank 0's own full-frame render of the same view, byte for byte
     tiles_match = None
     if world > 1:
-        fb_all.zero_() if rank == 0 else None
+        fb_all.zero_() if (rank == 0 or local_frames) else None
         barrier()
         render_step(0, 0)
         barrier()
+        got = fb_all if rank == 0 else None
+        if local_frames:        # collect every rank's frame of step 0 on rank 0 (NCCL, untimed) for the comparison
+            parts = [torch.empty_like(fb_all) for _ in range(world)] if rank == 0 else None
+            dist.gather(fb_all, parts, dst=0)
+            got = torch.cat(parts, dim=0) if rank == 0 else None
         if rank == 0:
             full = torch.zeros_like(fb)
             tiles_match = True
@@ -470,8 +479,8 @@ def run_native(args):
                 cu0, ru0 = uniforms(r)
                 vol.render(cu0, ru0, tfu, ropt, FW, FH, full.data_ptr(), 0, 0, stream)
                 torch.cuda.synchronize()
-                tiles_match = tiles_match and bool(torch.equal(full, fb_all[r]))
-            del full
+                tiles_match = tiles_match and bool(torch.equal(full, got[r]))
+            del full, got
         barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -711,7 +720,9 @@ def run_native(args):
             "config": {"workload": wl["name"], "volume": [W, H, D], "frame": [FW, FH], "block_size": 4, "ess": ["none", "block", "distance", "anisotropic"][skip],
                        "ert": True, "tf": wl["tf"], "views": "72-view orbit, one view per step",
                        "l2": "256 MiB flush write between timed steps (untimed); volume 342 MB > 126 MB L2" if args.workload == "c2" else "256 MiB flush write between timed steps (untimed)",
-                       "parallelism": (f"frames: a step is {world} consecutive orbit views, one per rank, each stored into its slot of rank 0's frame ring through peer stores"
+                       "parallelism": ((f"frames: a step is {world} consecutive orbit views, one per rank, each into the rank's own HBM as at N = 1 (independent frames: no exchange step)"
+                                        if local_frames else
+                                        f"frames: a step is {world} consecutive orbit views, one per rank, each stored into its slot of rank 0's frame ring through peer stores")
                                        if frames_mode else f"image tiles {TILE_W}x{TILE_H} round-robin over {world} ranks, peer stores into rank 0") if world > 1 else "single GPU",
                        "frames_per_step": slots},
             "timing": ("CUDA events around every step on every rank (256 MiB L2 flush before it, untimed); " +
@@ -908,6 +919,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="skip the per-mode table")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tiles-8k", action="store_true", help="N > 1: skip the extra tile-sharded 8K series")
+    ap.add_argument("--gather-frames", action="store_true", help="N > 1, frames mode: store every rank's frame into a ring in rank 0's HBM through peer stores (round 1's variant)")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = 6 if args.steps is None else args.steps
