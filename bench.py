@@ -502,18 +502,13 @@ def run_native(args):
     step_ms = torch.tensor([a.elapsed_time(b) for a, b in zip(starts, stops)], dtype=torch.float64, device=dev)
     lockstep_ms = None
     if world > 1:
-        if frames_mode:
-            # Independent frames (one view per rank per step, no exchange between ranks, no barrier inside the timed region): the job
-            # is done when the slowest rank has rendered its K frames -> the contract's "time K steps, max over ranks".  The stricter
-            # figure — every step waiting for its slowest view, as if a barrier followed each frame — is reported beside it.
-            lock = step_ms.clone()
-            dist.all_reduce(lock, op=dist.ReduceOp.MAX)
-            lockstep_ms = float(lock.sum().item()) / K
-            tot = step_ms.sum().reshape(1)
-            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-            step_ms = torch.full_like(step_ms, float(tot.item()) / K)
-        else:
-            dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)        # tiles of one frame: a step is done when the slowest rank is
+        # Independent frames (one view per rank per step, no exchange between ranks, no barrier inside the timed region): the job is
+        # done when the slowest rank has rendered its K frames -> the contract's "time K steps, max over ranks".  The stricter figure —
+        # every step waiting for its slowest view, as if a barrier followed each frame — is reported beside it.  Tiles of one frame:
+        # a step is done when the slowest rank is.
+        tot_ms, lock_tot = sharding.reduce_step_times(step_ms, frames_mode)
+        lockstep_ms = lock_tot / K if lock_tot is not None else None
+        step_ms = torch.full_like(step_ms, tot_ms / K)
         dist.all_reduce(counts_t)
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
         dist.all_reduce(lt)

@@ -165,16 +165,35 @@ print("rank", rank, "ok")
 '''
 
 
+
+TIMES_WORKER = r'''
+import os, sys
+import torch, torch.distributed as dist
+sys.path.insert(0, os.environ["VKV_ROOT"])
+from vkvolume_b200 import sharding
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+# rank 0 is slow on even steps, rank 1 on odd ones: per-rank totals 6.0 and 7.0, per-step maxima sum to 9.0
+mine = torch.tensor([2.0, 1.0, 2.0, 1.0] if rank == 0 else [1.0, 2.5, 1.0, 2.5], dtype=torch.float64)
+tot, lock = sharding.reduce_step_times(mine, independent=True)
+assert tot == 7.0 and lock == 9.0, (tot, lock)
+tot, lock = sharding.reduce_step_times(mine, independent=False)
+assert tot == 9.0 and lock is None, (tot, lock)
+assert mine.tolist() == ([2.0, 1.0, 2.0, 1.0] if rank == 0 else [1.0, 2.5, 1.0, 2.5])        # input untouched
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("worker", ["zslab", "frames", "sharded_k3"])
+@pytest.mark.parametrize("worker", ["zslab", "frames", "sharded_k3", "step_times"])
 def test_exchange_world_size_2_gloo(tmp_path, worker):
     script = tmp_path / "worker.py"
-    script.write_text({"zslab": WORKER, "frames": FRAMES_WORKER, "sharded_k3": K3_WORKER}[worker])
+    script.write_text({"zslab": WORKER, "frames": FRAMES_WORKER, "sharded_k3": K3_WORKER, "step_times": TIMES_WORKER}[worker])
     port = _free_port()
     procs = []
     for rank in range(2):

@@ -6,8 +6,8 @@ and on CUDA tensors with NCCL (how bench.py runs it) — there is no compute her
   ESS/ERT make per-pixel cost wildly non-uniform); every rank holds a full replica and stores its tiles straight into
   rank 0's framebuffer (peer mapping), so that path has no collective at all.
 * Frame sequences (an orbit, an animation) shard by frames instead: step s of an N-rank job renders views s*N .. s*N + N - 1, view
-  s*N + r on rank r, which stores it into slot r of a ring of N frames in rank 0's HBM (or delivers it to its own pinned host
-  buffer); again no collective.
+  s*N + r on rank r, into the rank's own HBM (or delivers it to its own pinned host buffer; bench.py --gather-frames stores it into
+  slot r of a ring of N frames in rank 0's HBM instead); no collective, no exchange.  reduce_step_times says when such a job is done.
 * The TF-change rebuild shards the O(N) occupancy pass by z-slabs of blocks.  In the library's own group
   (vkv_update_transfer_function_sharded, csrc/group.cu) the isotropic distance map is sharded too: x and y passes on the rank's slab,
   exchange of the xy-intermediate slabs, z pass on the rank's share of the block rows (row_range), exchange of the result rows — peer
@@ -82,3 +82,23 @@ def all_reduce_count(count_tensor, group=None):
 
     dist.all_reduce(count_tensor, group=group)
     return count_tensor
+
+
+def reduce_step_times(step_ms, independent: bool, group=None):
+    """Job time of K timed steps from every rank's per-step device times (1-D float64 tensor, one entry per step).
+
+    independent = False (tiles of one frame): a step is done when its slowest rank is -> per-step max over ranks, summed.
+    independent = True (frames: one view per rank per step, no exchange between ranks): the job is done when the slowest rank has
+    rendered its K views -> per-rank sum, max over ranks; the per-step-max figure ("lockstep": as if a barrier followed every frame)
+    is returned beside it.  Returns (total_ms, lockstep_total_ms or None); every rank gets the same numbers."""
+    import torch.distributed as dist
+
+    if not independent:
+        t = step_ms.clone()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        return float(t.sum().item()), None
+    lock = step_ms.clone()
+    dist.all_reduce(lock, op=dist.ReduceOp.MAX, group=group)
+    tot = step_ms.sum().reshape(1)
+    dist.all_reduce(tot, op=dist.ReduceOp.MAX, group=group)
+    return float(tot.item()), float(lock.sum().item())
