@@ -442,55 +442,66 @@ __device__ __forceinline__ void grad_pair_load(GradPair &r, const uint8_t *__res
 	}
 }
 
-// Tie passes of the column walk, split in two so that the tap re-reads of a pass are in flight during a whole row of the walk:
-// `start` pops the top n_take (<= 32) entries (one tie each; entries holding more ties push the rest back) and requests the
-// four taps, `finish` evaluates the shader's fp32 chain and patches the byte in the linear map and in the texture array.
-struct GradPass {
-	bool     on = false, mine = false;        // on: warp-uniform
-	unsigned ta, tb, tc, td, yz, x;
+// Ties of the column walk.  Every row step stashes the packed taps of its 16 voxels in shared memory (four 16-byte stores per lane
+// into a ring of three steps), and a lane with ties appends ONE entry (its tie mask, its lane, the step) to the warp's FIFO.  A
+// pass takes the 32 OLDEST entries, a lane per entry: lowest tie of the mask, taps from the stash (one shared-memory load — no tap
+// addresses, no global re-reads, nothing to wait for), the shader's fp32 chain, byte patch in the linear map and in the texture
+// array.  Entries with ties left go back to the HEAD of the queue, so the queue stays sorted by age and at the benchmark volume's
+// tie rate (a pass every 1.6 steps) an entry is served while its step is still in the stash; an entry that has outlived the ring
+// (sparse ties: the queue reaches 32 entries only every so many steps) re-reads its four taps from global memory instead.
+constexpr int kWalkQ = 128, kWalkRing = 3;        // queue capacity per warp (<= 31 carried + 32 pushed, and slack); steps in the stash
+struct WalkShared {
+	uint4    stash[kWalkRing][4][8][32];        // [step % 3][word of the chunk][warp][lane]: (A, B, E, C) bytes of voxels 4j .. 4j+3
+	unsigned q_t[8][kWalkQ];                   // tie masks (bit 8 i + j <=> voxel 4 j + i)
+	unsigned q_id[8][kWalkQ];                  // lane | step << 8
+	float    lut[256];
 };
 
-__device__ __forceinline__ void grad_pass_start(GradPass &ps, GradQueue &q, unsigned &n, int warp, int lane, unsigned n_take, const uint8_t *__restrict__ V,
-                                                uint32_t W, uint32_t H, uint32_t D)
-{
-	__syncwarp();
-	ps.on   = true;
-	ps.mine = (unsigned) lane < n_take;
-	unsigned t = 0, yz = 0, cx = 0;
-	if (ps.mine) {
-		const unsigned e = n - n_take + lane;
-		t = q.tie[warp][e], yz = q.yz[warp][e], cx = q.cx[warp][e];
-	}
-	n -= n_take;
-	__syncwarp();
-	const unsigned rest = t & (t - 1u);
-	grad_push(q, n, warp, lane, rest != 0u, rest, yz, cx);
-	ps.ta = ps.tb = ps.tc = ps.td = 0;
-	if (ps.mine) {
-		const unsigned pos = __ffs(t) - 1;
-		const uint32_t x = cx * 16 + 4 * (pos & 7u) + (pos >> 3), y = yz & 0xffffu, z = yz >> 16;
-		const uint32_t xm = x > 0 ? x - 1 : 0, xp = x + 1 < W ? x + 1 : W - 1;
-		const uint32_t ym = y > 0 ? y - 1 : 0, yp = y + 1 < H ? y + 1 : H - 1;
-		const uint32_t zmH = (z > 0 ? z - 1 : 0) * H, zpH = (z + 1 < D ? z + 1 : D - 1) * H;
-		const uint8_t *Vp = V + xp, *Vm = V + xm;
-		asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(ps.ta) : "l"(Vp + (size_t) (zmH + ym) * W));
-		asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(ps.tb) : "l"(Vm + (size_t) (zpH + ym) * W));
-		asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(ps.tc) : "l"(Vm + (size_t) (zmH + yp) * W));
-		asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(ps.td) : "l"(Vp + (size_t) (zpH + yp) * W));
-		ps.yz = yz, ps.x = x;
-	}
-}
-
 template <bool SURF>
-__device__ __forceinline__ void grad_pass_finish(GradPass &ps, const float *s_lut, uint8_t *__restrict__ G, cudaSurfaceObject_t surf, uint32_t W, uint32_t H, uint32_t dbg = 0)
+__device__ __forceinline__ void walk_tie_pass(WalkShared &S, unsigned &qhead, unsigned qtail, int warp, int lane, unsigned step_now, uint32_t y_first,
+                                              uint32_t cx, uint32_t z, const uint8_t *__restrict__ V, uint8_t *__restrict__ G, cudaSurfaceObject_t surf,
+                                              uint32_t W, uint32_t H, uint32_t D, uint32_t dbg)
 {
-	if (ps.mine) {
-		const uint32_t      y = ps.yz & 0xffffu, z = ps.yz >> 16;
-		const unsigned char g = gradient_byte(s_lut[ps.ta], s_lut[ps.tb], s_lut[ps.tc], s_lut[ps.td], 1.0f);
-		if (!(dbg & 16) || g == 77) G[(size_t) (z * H + y) * W + ps.x] = g;
-		if (SURF && (!(dbg & 32) || g == 77)) surf3Dwrite(g, surf, (int) ps.x, (int) y, (int) z);
+	__syncwarp();        // this step's row stores, stash and queue entries are visible to the whole warp
+	const unsigned n_take = min(32u, qtail - qhead);
+	const bool     mine   = (unsigned) lane < n_take;
+	unsigned       t = 0, id = 0;
+	if (mine) {
+		const unsigned e = (qhead + lane) & (kWalkQ - 1);
+		t = S.q_t[warp][e], id = S.q_id[warp][e];
 	}
-	ps.on = false;
+	__syncwarp();
+	// entries with ties left return to the head, in order: the queue stays sorted by age
+	const unsigned rest = t & (t - 1u);
+	const bool     surv = mine && rest != 0u;
+	const unsigned ms   = __ballot_sync(0xffffffffu, surv), nsurv = __popc(ms);
+	if (surv) {
+		const unsigned e = (qhead + n_take - nsurv + __popc(ms & ((1u << lane) - 1u))) & (kWalkQ - 1);
+		S.q_t[warp][e] = rest, S.q_id[warp][e] = id;
+	}
+	qhead += n_take - nsurv;
+	// the column of the lane that owns the entry (constant over its walk)
+	const int      src  = (int) (id & 31u);
+	const uint32_t cx_s = __shfl_sync(0xffffffffu, cx, src), z_s = __shfl_sync(0xffffffffu, z, src);
+	if (mine) {
+		const unsigned es  = id >> 8;
+		const unsigned pos = __ffs(t) - 1, j = pos & 7u, i = pos >> 3;
+		const uint32_t x = cx_s * 16 + 4 * j + i, y = y_first + 2u * es + ((unsigned) src >> 4);
+		unsigned       wv;        // (A, B, E, C)
+		if (es + (kWalkRing - 1) >= step_now) {
+			wv = reinterpret_cast<const unsigned *>(&S.stash[es % kWalkRing][j][warp][src])[i];
+		} else {
+			const uint32_t xm = x > 0 ? x - 1 : 0, xp = x + 1 < W ? x + 1 : W - 1;
+			const uint32_t ym = y > 0 ? y - 1 : 0, yp = y + 1 < H ? y + 1 : H - 1;
+			const uint32_t zmH = (z_s > 0 ? z_s - 1 : 0) * H, zpH = (z_s + 1 < D ? z_s + 1 : D - 1) * H;
+			const uint8_t *Vp = V + xp, *Vm = V + xm;
+			wv = (unsigned) __ldg(Vp + (size_t) (zmH + ym) * W) | ((unsigned) __ldg(Vm + (size_t) (zpH + ym) * W) << 8) |
+			     ((unsigned) __ldg(Vp + (size_t) (zpH + yp) * W) << 16) | ((unsigned) __ldg(Vm + (size_t) (zmH + yp) * W) << 24);
+		}
+		const unsigned char g = gradient_byte(S.lut[wv & 0xffu], S.lut[(wv >> 8) & 0xffu], S.lut[wv >> 24], S.lut[(wv >> 16) & 0xffu], 1.0f);
+		if (!(dbg & 16) || g == 77) G[(size_t) (z_s * H + y) * W + x] = g;
+		if (SURF && (!(dbg & 32) || g == 77)) surf3Dwrite(g, surf, (int) x, (int) y, (int) z_s);
+	}
 }
 
 __device__ __forceinline__ unsigned grad_edge_word(const uint4 &q, unsigned x)
@@ -505,13 +516,13 @@ __global__ void __launch_bounds__(256, 3) gradient_walk_kernel(const uint8_t *__
                                                               uint32_t W, uint32_t H, uint32_t D, uint32_t ncols, uint32_t ncg, uint32_t nseg, uint32_t steps, uint32_t dbg_bits)
 {
 	const uint32_t dbg = ABL ? dbg_bits : 0u;
-	__shared__ float     s_lut[256];
-	__shared__ GradQueue q;
-	s_lut[threadIdx.x] = (float) threadIdx.x / 255.0f;        // UNORM decode, exactly as imageLoad
+	extern __shared__ __align__(16) unsigned char walk_smem[];
+	WalkShared &S = *reinterpret_cast<WalkShared *>(walk_smem);
+	S.lut[threadIdx.x] = (float) threadIdx.x / 255.0f;        // UNORM decode, exactly as imageLoad
 	__syncthreads();
 	const uint32_t nchunks = W / 16;
 	const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	unsigned       qn = 0;        // entries in this warp's queue (warp-uniform)
+	unsigned       qhead = 0, qtail = 0;        // this warp's FIFO (warp-uniform counters; entry = counter mod kWalkQ)
 	// A warp is 16 columns x the two row parities (lanes 16..31 walk the odd rows): each step it completes two adjacent rows of
 	// 256 B, which is what the block-linear texture array wants — surface stores of 512 B x 1 row per warp run at less than half
 	// the rate of 256 B x 2 (scripts/ubench/sust_patterns.cu: 0.168 vs 0.094 ms for this volume, copy + surface 0.35 vs 0.18 ms).
@@ -537,14 +548,15 @@ __global__ void __launch_bounds__(256, 3) gradient_walk_kernel(const uint8_t *__
 	const int      xoff   = mem_prev ? -4 : 16;
 	const uint32_t Hm1    = H - 1;
 
-	GradPass ps;
+	const uint32_t y_first = seg * (2u * steps);        // row of step 0, parity 0 (warp-uniform)
+	unsigned       sidx    = 0;                         // steps walked (warp-uniform)
 	GradPair r0, r1, r2;
 	grad_pair_load(r0, baseM, baseP, min(y > 0 ? y - 1 : 0u, Hm1), W, need_x, xoff);
 	grad_pair_load(r1, baseM, baseP, min(y + 1, Hm1), W, need_x, xoff);
 	r0.em = grad_edge_word(r0.m, r0.xm), r0.ep = grad_edge_word(r0.p, r0.xp);
 
 	// one row of the walk: taps A, B on the pair `lo` (row y - 1), C, E on `hi` (row y + 1); `nx` receives row y + 3
-	auto step = [&](GradPair &lo, GradPair &hi, GradPair &nx) {
+	auto step = [&](GradPair &lo, GradPair &hi, GradPair &nx, const int slot) {
 		grad_pair_load(nx, baseM, baseP, min(y + 3, Hm1), W, need_x, xoff);
 		hi.em = grad_edge_word(hi.m, hi.xm), hi.ep = grad_edge_word(hi.p, hi.xp);
 		const unsigned eA = __shfl_sync(0xffffffffu, lo.em, src_next), eB = __shfl_sync(0xffffffffu, lo.ep, src_prev);
@@ -567,6 +579,7 @@ __global__ void __launch_bounds__(256, 3) gradient_walk_kernel(const uint8_t *__
 			// second stage: the four taps of one voxel in one word (their order does not matter to the two dot products)
 			const unsigned wv[4] = {prmt_(pab[j], pce[j], 0x7632u), prmt_(qab[j], qce[j], 0x5410u), prmt_(qab[j], qce[j], 0x7632u),
 			                        prmt_(pab[j + 1], pce[j + 1], 0x5410u)};
+			S.stash[slot][j][warp][lane] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
 			unsigned yv[4];
 #pragma unroll
 			for (int i = 0; i < 4; ++i) {
@@ -591,27 +604,26 @@ __global__ void __launch_bounds__(256, 3) gradient_walk_kernel(const uint8_t *__
 			if (SURF && !(dbg & 2)) surf3Dwrite(o, surf, (int) (cx * 16), (int) y, (int) z);        // x in bytes
 		}
 		const unsigned t = (tie[0] >> 7) | (tie[1] >> 6) | (tie[2] >> 5) | (tie[3] >> 4);
-		grad_push(q, qn, warp, lane, t != 0u && active && !(dbg & 1), t, y | (z << 16), cx);
-		y += 2;
-		// the pass started a row ago has its taps by now; then at most one new pass per row is put in flight (the __syncwarp at
-		// the top of grad_pass_start orders this row's stores before its byte patches).  Only a volume made of ties needs more.
-		if (ps.on) grad_pass_finish<SURF>(ps, s_lut, G, surf, W, H, dbg);
-		while (qn >= 64u) {
-			grad_pass_start(ps, q, qn, warp, lane, 32u, V, W, H, D);
-			grad_pass_finish<SURF>(ps, s_lut, G, surf, W, H, dbg);
+		{
+			const bool     push = t != 0u && active && !(dbg & 1);
+			const unsigned m    = __ballot_sync(0xffffffffu, push);
+			if (push) {
+				const unsigned e = (qtail + __popc(m & ((1u << lane) - 1u))) & (kWalkQ - 1);
+				S.q_t[warp][e] = t, S.q_id[warp][e] = (unsigned) lane | (sidx << 8);
+			}
+			qtail += __popc(m);
 		}
-		if (qn >= 32u) grad_pass_start(ps, q, qn, warp, lane, 32u, V, W, H, D);
+		y += 2;
+		while (qtail - qhead >= 32u) walk_tie_pass<SURF>(S, qhead, qtail, warp, lane, sidx, y_first, cx, z, V, G, surf, W, H, D, dbg);
+		++sidx;
+		__syncwarp();        // the passes have read the stash slot that the step after next overwrites
 	};
 	for (uint32_t k = 0; k < steps; k += 3) {
-		step(r0, r1, r2);
-		step(r1, r2, r0);
-		step(r2, r0, r1);
+		step(r0, r1, r2, 0);
+		step(r1, r2, r0, 1);
+		step(r2, r0, r1, 2);
 	}
-	if (ps.on) grad_pass_finish<SURF>(ps, s_lut, G, surf, W, H, dbg);
-	while (qn) {
-		grad_pass_start(ps, q, qn, warp, lane, qn < 32u ? qn : 32u, V, W, H, D);
-		grad_pass_finish<SURF>(ps, s_lut, G, surf, W, H, dbg);
-	}
+	while (qtail != qhead) walk_tie_pass<SURF>(S, qhead, qtail, warp, lane, sidx - 1u, y_first, cx, z, V, G, surf, W, H, D, dbg);
 }
 
 // Any extents: one thread per voxel, clamped byte loads through L1.
@@ -671,8 +683,14 @@ int launch_gradient(vkv_volume *vol, bool use_gradient, float modifier, cudaStre
 			const unsigned g     = (unsigned) ((warps + 7) / 8);
 			const bool     surf  = vol->s_G && !getenv("VKV_GRAD_NOSURF");
 			const uint32_t dbg   = (surf && getenv("VKV_GRAD_DBG")) ? (uint32_t) atoi(getenv("VKV_GRAD_DBG")) : 0u;
+			static PerDeviceOnce walk_configured;
+			if (walk_configured.first(vol->ctx->device)) {
+				VKV_CUDA_CHECK(cudaFuncSetAttribute(gradient_walk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(WalkShared)));
+				VKV_CUDA_CHECK(cudaFuncSetAttribute(gradient_walk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(WalkShared)));
+				VKV_CUDA_CHECK(cudaFuncSetAttribute(gradient_walk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(WalkShared)));
+			}
 #define VKV_GRAD_WALK(SURF_, ABL_)                                                                                                                 \
-	gradient_walk_kernel<SURF_, ABL_><<<g, 256, 0, s>>>(vol->d_V, vol->d_G, SURF_ ? vol->s_G : 0, vol->dim[0], vol->dim[1], vol->dim[2], (uint32_t) ncols, \
+	gradient_walk_kernel<SURF_, ABL_><<<g, 256, sizeof(WalkShared), s>>>(vol->d_V, vol->d_G, SURF_ ? vol->s_G : 0, vol->dim[0], vol->dim[1], vol->dim[2], (uint32_t) ncols, \
 	                                                    (uint32_t) ncg, (uint32_t) n_seg(steps), steps, dbg)
 			if (dbg)
 				VKV_GRAD_WALK(true, true);
