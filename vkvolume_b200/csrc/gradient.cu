@@ -443,22 +443,34 @@ __device__ __forceinline__ void grad_pair_load(GradPair &r, const uint8_t *__res
 }
 
 // Ties of the column walk.  Every row step stashes the packed taps of its 16 voxels in shared memory (four 16-byte stores per lane
-// into a ring of three steps), and a lane with ties appends ONE entry (its tie mask, its lane, the step) to the warp's FIFO.  A
+// into a ring of kWalkRing steps), and a lane with ties appends ONE entry (its tie mask, its lane, the step) to the warp's FIFO.  A
 // pass takes the 32 OLDEST entries, a lane per entry: lowest tie of the mask, taps from the stash (one shared-memory load — no tap
-// addresses, no global re-reads, nothing to wait for), the shader's fp32 chain, byte patch in the linear map and in the texture
-// array.  Entries with ties left go back to the HEAD of the queue, so the queue stays sorted by age and at the benchmark volume's
-// tie rate (a pass every 1.6 steps) an entry is served while its step is still in the stash; an entry that has outlived the ring
-// (sparse ties: the queue reaches 32 entries only every so many steps) re-reads its four taps from global memory instead.
-constexpr int kWalkQ = 128, kWalkRing = 3;        // queue capacity per warp (<= 31 carried + 32 pushed, and slack); steps in the stash
+// addresses, no global re-reads, nothing to wait for), the shader's fp32 chain, and the byte goes into the step's RESULT ROW, which
+// is staged in shared memory as well and leaves for the linear map and the texture array a step after it was computed — whole
+// 16-byte stores only, no byte patches in memory.  Entries with ties left go back to the HEAD of the queue, so the queue stays
+// sorted by age and at the benchmark volume's tie rate (a pass every 1.6 steps) an entry is served while its step is still staged;
+// an entry that has outlived the ring (sparse ties: the queue reaches 32 entries only every so many steps) re-reads its four taps
+// from global memory and patches the stored byte in both maps instead.
+// Steps staged in shared memory.  Shared memory is taken from the L1 that serves the walk's row loads (every row is read by the
+// columns at z - 1 and z + 1): measured on B200 with 3 CTAs per SM, ring 3 (70 KB per CTA) 0.347 / 1.07 / 4.26 ms on the
+// 832x832x494 / 1024^3 / 2048x2048x1024 volumes, ring 2 (45 KB) 0.328 / 1.10 / 4.20 ms; 2 CTAs per SM lose 5-10 % either way.
+#ifndef VKV_WALK_RING
+#define VKV_WALK_RING 2
+#endif
+#ifndef VKV_WALK_CTAS
+#define VKV_WALK_CTAS 3
+#endif
+constexpr int kWalkQ = 64, kWalkRing = VKV_WALK_RING;        // queue capacity per warp (<= 31 carried + 32 pushed); steps staged in shared memory
 struct WalkShared {
-	uint4    stash[kWalkRing][4][8][32];        // [step % 3][word of the chunk][warp][lane]: (A, B, E, C) bytes of voxels 4j .. 4j+3
+	uint4    stash[kWalkRing][4][8][32];        // [step % ring][word of the chunk][warp][lane]: (A, B, E, C) bytes of voxels 4j .. 4j+3
+	uint4    rows[kWalkRing][8][32];            // [step % ring][warp][lane]: the step's 16 result bytes, stored to memory ring - 1 steps later
 	unsigned q_t[8][kWalkQ];                   // tie masks (bit 8 i + j <=> voxel 4 j + i)
 	unsigned q_id[8][kWalkQ];                  // lane | step << 8
 	float    lut[256];
 };
 
 template <bool SURF>
-__device__ __forceinline__ void walk_tie_pass(WalkShared &S, unsigned &qhead, unsigned qtail, int warp, int lane, unsigned step_now, uint32_t y_first,
+__device__ __forceinline__ void walk_tie_pass(WalkShared &S, unsigned &qhead, unsigned qtail, int warp, int lane, unsigned first_staged, uint32_t y_first,
                                               uint32_t cx, uint32_t z, const uint8_t *__restrict__ V, uint8_t *__restrict__ G, cudaSurfaceObject_t surf,
                                               uint32_t W, uint32_t H, uint32_t D, uint32_t dbg)
 {
@@ -488,7 +500,8 @@ __device__ __forceinline__ void walk_tie_pass(WalkShared &S, unsigned &qhead, un
 		const unsigned pos = __ffs(t) - 1, j = pos & 7u, i = pos >> 3;
 		const uint32_t x = cx_s * 16 + 4 * j + i, y = y_first + 2u * es + ((unsigned) src >> 4);
 		unsigned       wv;        // (A, B, E, C)
-		if (es + (kWalkRing - 1) >= step_now) {
+		const bool     staged = es >= first_staged;        // the step's taps and result row are still in shared memory
+		if (staged) {
 			wv = reinterpret_cast<const unsigned *>(&S.stash[es % kWalkRing][j][warp][src])[i];
 		} else {
 			const uint32_t xm = x > 0 ? x - 1 : 0, xp = x + 1 < W ? x + 1 : W - 1;
@@ -499,8 +512,12 @@ __device__ __forceinline__ void walk_tie_pass(WalkShared &S, unsigned &qhead, un
 			     ((unsigned) __ldg(Vp + (size_t) (zpH + yp) * W) << 16) | ((unsigned) __ldg(Vm + (size_t) (zmH + yp) * W) << 24);
 		}
 		const unsigned char g = gradient_byte(S.lut[wv & 0xffu], S.lut[(wv >> 8) & 0xffu], S.lut[wv >> 24], S.lut[(wv >> 16) & 0xffu], 1.0f);
-		if (!(dbg & 16) || g == 77) G[(size_t) (z_s * H + y) * W + x] = g;
-		if (SURF && (!(dbg & 32) || g == 77)) surf3Dwrite(g, surf, (int) x, (int) y, (int) z_s);
+		if (staged) {
+			reinterpret_cast<unsigned char *>(&S.rows[es % kWalkRing][warp][src])[4 * j + i] = g;
+		} else {
+			if (!(dbg & 16) || g == 77) G[(size_t) (z_s * H + y) * W + x] = g;
+			if (SURF && (!(dbg & 32) || g == 77)) surf3Dwrite(g, surf, (int) x, (int) y, (int) z_s);
+		}
 	}
 }
 
@@ -512,7 +529,7 @@ __device__ __forceinline__ unsigned grad_edge_word(const uint4 &q, unsigned x)
 // ABL: the ablation instantiation (VKV_GRAD_DBG=<bits>, timing only — the map is wrong): 1 no tie queue, 2 no row surface stores,
 // 4 no row stores to the linear map, 8 no arithmetic (rows copied through), 16 / 32 no tie patches to the linear map / the array.
 template <bool SURF, bool ABL>
-__global__ void __launch_bounds__(256, 3) gradient_walk_kernel(const uint8_t *__restrict__ V, uint8_t *__restrict__ G, cudaSurfaceObject_t surf,
+__global__ void __launch_bounds__(256, VKV_WALK_CTAS) gradient_walk_kernel(const uint8_t *__restrict__ V, uint8_t *__restrict__ G, cudaSurfaceObject_t surf,
                                                               uint32_t W, uint32_t H, uint32_t D, uint32_t ncols, uint32_t ncg, uint32_t nseg, uint32_t steps, uint32_t dbg_bits)
 {
 	const uint32_t dbg = ABL ? dbg_bits : 0u;
@@ -555,6 +572,15 @@ __global__ void __launch_bounds__(256, 3) gradient_walk_kernel(const uint8_t *__
 	grad_pair_load(r1, baseM, baseP, min(y + 1, Hm1), W, need_x, xoff);
 	r0.em = grad_edge_word(r0.m, r0.xm), r0.ep = grad_edge_word(r0.p, r0.xp);
 
+	// the result row of step r leaves shared memory: one 16-byte store to the linear map, one into the texture array
+	auto store_row = [&](unsigned r) {
+		const uint32_t yr = y_first + ((uint32_t) lane >> 4) + 2u * r;
+		if (valid && yr < H) {
+			const uint4 o = S.rows[r % kWalkRing][warp][lane];
+			if (!(dbg & 4)) *reinterpret_cast<uint4 *>(baseG + (size_t) yr * W) = o;
+			if (SURF && !(dbg & 2)) surf3Dwrite(o, surf, (int) (cx * 16), (int) yr, (int) z);        // x in bytes
+		}
+	};
 	// one row of the walk: taps A, B on the pair `lo` (row y - 1), C, E on `hi` (row y + 1); `nx` receives row y + 3
 	auto step = [&](GradPair &lo, GradPair &hi, GradPair &nx, const int slot) {
 		grad_pair_load(nx, baseM, baseP, min(y + 3, Hm1), W, need_x, xoff);
@@ -599,10 +625,7 @@ __global__ void __launch_bounds__(256, 3) gradient_walk_kernel(const uint8_t *__
 		const bool  active = valid && y < H;
 		uint4 o      = make_uint4(out[0], out[1], out[2], out[3]);
 		if (dbg & 8) o = make_uint4(lo.m.x ^ eA, lo.p.y ^ eB, hi.m.z ^ eC, hi.p.w ^ eE);
-		if (active) {
-			if (!(dbg & 4)) *reinterpret_cast<uint4 *>(baseG + (size_t) y * W) = o;
-			if (SURF && !(dbg & 2)) surf3Dwrite(o, surf, (int) (cx * 16), (int) y, (int) z);        // x in bytes
-		}
+		S.rows[slot][warp][lane] = o;
 		const unsigned t = (tie[0] >> 7) | (tie[1] >> 6) | (tie[2] >> 5) | (tie[3] >> 4);
 		{
 			const bool     push = t != 0u && active && !(dbg & 1);
@@ -614,16 +637,22 @@ __global__ void __launch_bounds__(256, 3) gradient_walk_kernel(const uint8_t *__
 			qtail += __popc(m);
 		}
 		y += 2;
-		while (qtail - qhead >= 32u) walk_tie_pass<SURF>(S, qhead, qtail, warp, lane, sidx, y_first, cx, z, V, G, surf, W, H, D, dbg);
+		const unsigned first_staged = sidx >= (unsigned) (kWalkRing - 1) ? sidx - (unsigned) (kWalkRing - 1) : 0u;
+		while (qtail - qhead >= 32u) walk_tie_pass<SURF>(S, qhead, qtail, warp, lane, first_staged, y_first, cx, z, V, G, surf, W, H, D, dbg);
+		__syncwarp();        // the passes' byte patches are in the staged rows; their reads of the oldest stash slot are done
+		if (sidx >= (unsigned) (kWalkRing - 1)) store_row(sidx - (unsigned) (kWalkRing - 1));        // (its slot is the one the next step overwrites)
 		++sidx;
-		__syncwarp();        // the passes have read the stash slot that the step after next overwrites
 	};
 	for (uint32_t k = 0; k < steps; k += 3) {
-		step(r0, r1, r2, 0);
-		step(r1, r2, r0, 1);
-		step(r2, r0, r1, 2);
+		step(r0, r1, r2, kWalkRing == 3 ? 0 : (int) (sidx % kWalkRing));
+		step(r1, r2, r0, kWalkRing == 3 ? 1 : (int) (sidx % kWalkRing));
+		step(r2, r0, r1, kWalkRing == 3 ? 2 : (int) (sidx % kWalkRing));
 	}
-	while (qtail != qhead) walk_tie_pass<SURF>(S, qhead, qtail, warp, lane, sidx - 1u, y_first, cx, z, V, G, surf, W, H, D, dbg);
+	// the last kWalkRing - 1 rows are still staged: the remaining ties first, then the rows
+	while (qtail != qhead) walk_tie_pass<SURF>(S, qhead, qtail, warp, lane, sidx - (unsigned) (kWalkRing - 1), y_first, cx, z, V, G, surf, W, H, D, dbg);
+	__syncwarp();
+#pragma unroll
+	for (int r = kWalkRing - 1; r >= 1; --r) store_row(sidx - (unsigned) r);
 }
 
 // Any extents: one thread per voxel, clamped byte loads through L1.
@@ -673,7 +702,7 @@ int launch_gradient(vkv_volume *vol, bool use_gradient, float modifier, cudaStre
 		uint32_t       steps = 24;        // rows per thread; a segment is 2 * steps rows (two parities)
 		const uint64_t ncg   = (ncols + 15) / 16;        // warps per segment: 16 columns x 2 row parities
 		auto           n_seg = [&](uint32_t st) { return (uint64_t) ((vol->dim[1] + 2 * st - 1) / (2 * st)); };
-		const uint64_t resident = (uint64_t) vol->ctx->sm_count * 3 * 8;        // warps
+		const uint64_t resident = (uint64_t) vol->ctx->sm_count * VKV_WALK_CTAS * 8;        // warps
 		while (steps > 3 && ncg * n_seg(steps) < 8 * resident) steps /= 2;
 		if (const char *e = getenv("VKV_GRAD_STEPS")) steps = (uint32_t) std::max(1, atoi(e)) * 3;
 		const bool walk_ok = !getenv("VKV_GRAD_V1") && !getenv("VKV_GRAD_FLAT") && nch <= 65535 && vol->dim[1] <= 65535 && vol->dim[2] <= 65535 &&
