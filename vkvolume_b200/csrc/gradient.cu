@@ -460,44 +460,40 @@ __device__ __forceinline__ void grad_pair_load(GradPair &r, const uint8_t *__res
 #ifndef VKV_WALK_CTAS
 #define VKV_WALK_CTAS 3
 #endif
-constexpr int kWalkQ = 64, kWalkRing = VKV_WALK_RING;        // queue capacity per warp (<= 31 carried + 32 pushed); steps staged in shared memory
+#ifndef VKV_WALK_Q
+#define VKV_WALK_Q 64
+#endif
+constexpr int kWalkQ = VKV_WALK_Q, kWalkRing = VKV_WALK_RING;        // queue capacity per warp (<= 31 carried + 32 pushed); steps staged in shared memory
 struct WalkShared {
 	uint4    stash[kWalkRing][4][8][32];        // [step % ring][word of the chunk][warp][lane]: (A, B, E, C) bytes of voxels 4j .. 4j+3
 	uint4    rows[kWalkRing][8][32];            // [step % ring][warp][lane]: the step's 16 result bytes, stored to memory ring - 1 steps later
-	unsigned q_t[8][kWalkQ];                   // tie masks (bit 8 i + j <=> voxel 4 j + i)
-	unsigned q_id[8][kWalkQ];                  // lane | step << 8
+	unsigned q[8][kWalkQ];                     // tie mask (bit 4 i + j <=> voxel 4 j + i) | lane << 16 | (step mod 2048) << 21
 	float    lut[256];
 };
 
 template <bool SURF>
-__device__ __forceinline__ void walk_tie_pass(WalkShared &S, unsigned &qhead, unsigned qtail, int warp, int lane, unsigned first_staged, uint32_t y_first,
+__device__ __forceinline__ void walk_tie_pass(WalkShared &S, unsigned &qhead, unsigned qtail, int warp, int lane, unsigned step_now, unsigned first_staged, uint32_t y_first,
                                               uint32_t cx, uint32_t z, const uint8_t *__restrict__ V, uint8_t *__restrict__ G, cudaSurfaceObject_t surf,
                                               uint32_t W, uint32_t H, uint32_t D, uint32_t dbg)
 {
 	__syncwarp();        // this step's row stores, stash and queue entries are visible to the whole warp
 	const unsigned n_take = min(32u, qtail - qhead);
 	const bool     mine   = (unsigned) lane < n_take;
-	unsigned       t = 0, id = 0;
-	if (mine) {
-		const unsigned e = (qhead + lane) & (kWalkQ - 1);
-		t = S.q_t[warp][e], id = S.q_id[warp][e];
-	}
+	unsigned       ent = 0;
+	if (mine) ent = S.q[warp][(qhead + lane) & (kWalkQ - 1)];
 	__syncwarp();
 	// entries with ties left return to the head, in order: the queue stays sorted by age
-	const unsigned rest = t & (t - 1u);
+	const unsigned t = ent & 0xffffu, rest = t & (t - 1u);
 	const bool     surv = mine && rest != 0u;
 	const unsigned ms   = __ballot_sync(0xffffffffu, surv), nsurv = __popc(ms);
-	if (surv) {
-		const unsigned e = (qhead + n_take - nsurv + __popc(ms & ((1u << lane) - 1u))) & (kWalkQ - 1);
-		S.q_t[warp][e] = rest, S.q_id[warp][e] = id;
-	}
+	if (surv) S.q[warp][(qhead + n_take - nsurv + __popc(ms & ((1u << lane) - 1u))) & (kWalkQ - 1)] = (ent & 0xffff0000u) | rest;
 	qhead += n_take - nsurv;
 	// the column of the lane that owns the entry (constant over its walk)
-	const int      src  = (int) (id & 31u);
+	const int      src  = (int) ((ent >> 16) & 31u);
 	const uint32_t cx_s = __shfl_sync(0xffffffffu, cx, src), z_s = __shfl_sync(0xffffffffu, z, src);
 	if (mine) {
-		const unsigned es  = id >> 8;
-		const unsigned pos = __ffs(t) - 1, j = pos & 7u, i = pos >> 3;
+		const unsigned es  = step_now - ((step_now - (ent >> 21)) & 0x7ffu);        // the entry's step (entries are younger than 2048 steps)
+		const unsigned pos = __ffs(t) - 1, j = pos & 3u, i = pos >> 2;
 		const uint32_t x = cx_s * 16 + 4 * j + i, y = y_first + 2u * es + ((unsigned) src >> 4);
 		unsigned       wv;        // (A, B, E, C)
 		const bool     staged = es >= first_staged;        // the step's taps and result row are still in shared memory
@@ -626,19 +622,19 @@ __global__ void __launch_bounds__(256, VKV_WALK_CTAS) gradient_walk_kernel(const
 		uint4 o      = make_uint4(out[0], out[1], out[2], out[3]);
 		if (dbg & 8) o = make_uint4(lo.m.x ^ eA, lo.p.y ^ eB, hi.m.z ^ eC, hi.p.w ^ eE);
 		S.rows[slot][warp][lane] = o;
-		const unsigned t = (tie[0] >> 7) | (tie[1] >> 6) | (tie[2] >> 5) | (tie[3] >> 4);
+		const unsigned t8 = (tie[0] >> 7) | (tie[1] >> 6) | (tie[2] >> 5) | (tie[3] >> 4);        // bit 8 i + j <=> voxel 4 j + i
 		{
-			const bool     push = t != 0u && active && !(dbg & 1);
+			const bool     push = t8 != 0u && active && !(dbg & 1);
 			const unsigned m    = __ballot_sync(0xffffffffu, push);
 			if (push) {
-				const unsigned e = (qtail + __popc(m & ((1u << lane) - 1u))) & (kWalkQ - 1);
-				S.q_t[warp][e] = t, S.q_id[warp][e] = (unsigned) lane | (sidx << 8);
+				const unsigned t16 = (t8 & 0xfu) | ((t8 >> 4) & 0xf0u) | ((t8 >> 8) & 0xf00u) | ((t8 >> 12) & 0xf000u);
+				S.q[warp][(qtail + __popc(m & ((1u << lane) - 1u))) & (kWalkQ - 1)] = t16 | ((unsigned) lane << 16) | (sidx << 21);
 			}
 			qtail += __popc(m);
 		}
 		y += 2;
 		const unsigned first_staged = sidx >= (unsigned) (kWalkRing - 1) ? sidx - (unsigned) (kWalkRing - 1) : 0u;
-		while (qtail - qhead >= 32u) walk_tie_pass<SURF>(S, qhead, qtail, warp, lane, first_staged, y_first, cx, z, V, G, surf, W, H, D, dbg);
+		while (qtail - qhead >= 32u) walk_tie_pass<SURF>(S, qhead, qtail, warp, lane, sidx, first_staged, y_first, cx, z, V, G, surf, W, H, D, dbg);
 		__syncwarp();        // the passes' byte patches are in the staged rows; their reads of the oldest stash slot are done
 		if (sidx >= (unsigned) (kWalkRing - 1)) store_row(sidx - (unsigned) (kWalkRing - 1));        // (its slot is the one the next step overwrites)
 		++sidx;
@@ -649,7 +645,7 @@ __global__ void __launch_bounds__(256, VKV_WALK_CTAS) gradient_walk_kernel(const
 		step(r2, r0, r1, kWalkRing == 3 ? 2 : (int) (sidx % kWalkRing));
 	}
 	// the last kWalkRing - 1 rows are still staged: the remaining ties first, then the rows
-	while (qtail != qhead) walk_tie_pass<SURF>(S, qhead, qtail, warp, lane, sidx - (unsigned) (kWalkRing - 1), y_first, cx, z, V, G, surf, W, H, D, dbg);
+	while (qtail != qhead) walk_tie_pass<SURF>(S, qhead, qtail, warp, lane, sidx - 1u, sidx - (unsigned) (kWalkRing - 1), y_first, cx, z, V, G, surf, W, H, D, dbg);
 	__syncwarp();
 #pragma unroll
 	for (int r = kWalkRing - 1; r >= 1; --r) store_row(sidx - (unsigned) r);
@@ -704,7 +700,7 @@ int launch_gradient(vkv_volume *vol, bool use_gradient, float modifier, cudaStre
 		auto           n_seg = [&](uint32_t st) { return (uint64_t) ((vol->dim[1] + 2 * st - 1) / (2 * st)); };
 		const uint64_t resident = (uint64_t) vol->ctx->sm_count * VKV_WALK_CTAS * 8;        // warps
 		while (steps > 3 && ncg * n_seg(steps) < 8 * resident) steps /= 2;
-		if (const char *e = getenv("VKV_GRAD_STEPS")) steps = (uint32_t) std::max(1, atoi(e)) * 3;
+		if (const char *e = getenv("VKV_GRAD_STEPS")) steps = (uint32_t) std::min(680, std::max(1, atoi(e))) * 3;        // (queue entries carry the step mod 2048)
 		const bool walk_ok = !getenv("VKV_GRAD_V1") && !getenv("VKV_GRAD_FLAT") && nch <= 65535 && vol->dim[1] <= 65535 && vol->dim[2] <= 65535 &&
 		                     ncg * n_seg(steps) < (1ull << 31) && ncols < (1ull << 31);
 		if (walk_ok) {
