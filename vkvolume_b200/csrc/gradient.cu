@@ -4,14 +4,17 @@
 // gradient, one invocation per voxel with four clamped imageLoads) and
 // ComputeGradientMap::compute (src/compute_gradient_map.cpp:57-81).
 //
-// B200 design: each thread produces 16 consecutive voxels from four 16-byte vector loads
-// (the four (y±1, z±1) rows the taps live on); the x±1 neighbours of the run come from the
-// adjacent lanes by warp shuffle, so every input byte is loaded once per output row.  Results
-// are packed into one 16-byte store.  The arithmetic follows the shader's operation order in
-// fp32 without contraction and with IEEE division / square root so the stored byte is
-// identical to the CPU oracle's (the byte feeds the occupancy LUT).  UNORM decode b/255 is
-// served from a 256-entry shared-memory table built with a true division.
-// Algorithmic bytes: read N + write N = 2 B/voxel.
+// B200 design (kernels in the order launch_gradient prefers them):
+//   * gradient_walk_kernel — the column walk (round 2): a thread owns a 16-voxel chunk of x at one z and walks every second row of a
+//     y segment (the rows loaded for row y serve row y + 2 again: two 16-byte loads per step), integer formulation of |g| on dp4a,
+//     exact ties resolved from a shared-memory stash before the row is stored, warps shaped for the texture array's surface stores;
+//   * gradient_flat_kernel / gradient_int_kernel — round 1's integer kernels (flat persistent walk, one row task per warp): fallbacks
+//     for extents whose indices do not fit the walk's packed queue entries, and the A/B references (VKV_GRAD_FLAT, VKV_GRAD_V1);
+//   * gradient_vec16_kernel — the shader's operation order in fp32 for every voxel (grad_magnitude_modifier != 1, VKV_GRAD_FP32);
+//   * gradient_scalar_kernel — any extents (W % 16 != 0).
+// Every kernel stores the byte the CPU oracle stores: fp32 without contraction, IEEE division and square root wherever the fp32
+// chain is evaluated, UNORM decode b / 255 from a 256-entry table built with a true division (the byte feeds the occupancy LUT).
+// Algorithmic bytes: read N + write N = 2 B/voxel (+ N for the copy of the map in the texture array the ray caster samples).
 #include <algorithm>
 #include <cstdlib>
 
