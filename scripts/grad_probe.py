@@ -21,7 +21,7 @@ capi.synth_volume(ctx, wl["kind"], wl["seed"], W, H, D, vol.device_voxels(), str
 vol.upload_device(vol.device_voxels(), stream)
 tfu = capi.transfer_function_uniform(VolumeOptions(gradient_min=0.0, gradient_max=0.2))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-VARIANTS = {"walk": {}, "walk_nosurf": {"VKV_GRAD_NOSURF": "1"}, "walk_s2": {"VKV_GRAD_STEPS": "2"}, "walk_s4": {"VKV_GRAD_STEPS": "4"},
+VARIANTS = {"walk": {}, **{f"steps{3 * n}": {"VKV_GRAD_STEPS": str(n)} for n in (3, 4, 5, 6, 7, 9, 10, 12, 14)}, "walk_nosurf": {"VKV_GRAD_NOSURF": "1"}, "walk_s2": {"VKV_GRAD_STEPS": "2"}, "walk_s4": {"VKV_GRAD_STEPS": "4"},
             "walk_s8": {"VKV_GRAD_STEPS": "8"}, "walk_s16": {"VKV_GRAD_STEPS": "16"}, "walk_s32": {"VKV_GRAD_STEPS": "32"},
             "dbg1": {"VKV_GRAD_STEPS": "4", "VKV_GRAD_DBG": "1"}, "dbg2": {"VKV_GRAD_STEPS": "4", "VKV_GRAD_DBG": "2"}, "dbg3": {"VKV_GRAD_STEPS": "4", "VKV_GRAD_DBG": "3"}, "dbg4": {"VKV_GRAD_STEPS": "4", "VKV_GRAD_DBG": "4"}, "dbg6": {"VKV_GRAD_STEPS": "4", "VKV_GRAD_DBG": "6"}, "dbg7": {"VKV_GRAD_STEPS": "4", "VKV_GRAD_DBG": "7"}, "dbg16": {"VKV_GRAD_DBG": "16"}, "dbg32": {"VKV_GRAD_DBG": "32"}, "dbg48": {"VKV_GRAD_DBG": "48"}, "dbg9": {"VKV_GRAD_STEPS": "4", "VKV_GRAD_DBG": "9"}, "dbg11": {"VKV_GRAD_STEPS": "4", "VKV_GRAD_DBG": "11"},
             "v1_int_surf": {"VKV_GRAD_V1": "1"}, "flat_nosurf": {"VKV_GRAD_NOSURF": "1", "VKV_GRAD_FLAT": "1"}, "flat_surf": {"VKV_GRAD_FLAT": "1"}}
