@@ -448,22 +448,38 @@ __global__ void __launch_bounds__(kTmaThreads, 1) occupancy_tma_kernel(const __g
 		unsigned cnt = 0;
 		auto classify = [&](auto hi_tag, auto edge_tag) {
 			constexpr bool HI = decltype(hi_tag)::value, EDGE = decltype(edge_tag)::value;
+			// With the fused count ahead and a texture whose visible set is not a rectangle (gradient transfer functions), the counted
+			// candidates stand in for the texture's bounding rectangle — they contain it (count_first) — and the second pass over the
+			// column only looks for the sure rectangle: one range test per word less (the count used to double the pass on such TFs).
+			const bool ana_for_tex = COUNT && count_first && !tex_exact;
+			unsigned   acc_a = 0;
 			if (COUNT && count_first) {
 				unsigned c128 = 0;        // 128 x (visible voxels of this column)
 #pragma unroll
 				for (int row = 0; row < kTmaRows; ++row) {
 					if (EDGE && !((rows >> row) & 1u)) continue;
-					c128 = __dp4a(rt_ana7.bits<USE_G, HI>(vw(row), gw(row)), 0x01010101u, c128);
+					const unsigned a = rt_ana7.bits<USE_G, HI>(vw(row), gw(row));
+					c128 = __dp4a(a, 0x01010101u, c128);
+					acc_a |= a;
 				}
 				cnt = c128 >> 7;
 				if (c128 == 0u || rt_tex.empty) return;        // no analytically visible voxel -> no texture-visible one either
 			}
 			unsigned acc_t = 0, acc_s = 0;
+			if (ana_for_tex) {
+				acc_t = acc_a;
 #pragma unroll
-			for (int row = 0; row < kTmaRows; ++row) {
-				if (EDGE && !((rows >> row) & 1u)) continue;
-				acc_t |= rt_tex.bits<USE_G, HI>(vw(row), gw(row));
-				if (!tex_exact) acc_s |= rt_sure.bits<USE_G, false>(vw(row), gw(row));
+				for (int row = 0; row < kTmaRows; ++row) {
+					if (EDGE && !((rows >> row) & 1u)) continue;
+					acc_s |= rt_sure.bits<USE_G, false>(vw(row), gw(row));
+				}
+			} else {
+#pragma unroll
+				for (int row = 0; row < kTmaRows; ++row) {
+					if (EDGE && !((rows >> row) & 1u)) continue;
+					acc_t |= rt_tex.bits<USE_G, HI>(vw(row), gw(row));
+					if (!tex_exact) acc_s |= rt_sure.bits<USE_G, false>(vw(row), gw(row));
+				}
 			}
 			acc_t &= 0x80808080u; acc_s &= 0x80808080u;
 			if (rt_tex.empty) acc_t = 0u;
